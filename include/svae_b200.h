@@ -1,0 +1,102 @@
+/* svae_b200.h -- C-ABI of the B200-native SVAE local E-step engine (libsvae_b200.so).
+ *
+ * Drop-in boundary ("native, primitive-level"): these entry points are what the
+ * reference's Cython primitives
+ *     svae/lds/cython_lds_inference.pyx:28-90   natural_filter_forward_general
+ *     svae/lds/cython_lds_inference.pyx:149-210 natural_smoother_general (+ _compute_stats)
+ *     svae/lds/cython_lds_inference.pyx:310-355 natural_sample_backward
+ *     svae/lds/cython_lds_inference.pyx:92-145, 236-306, 357-409   the three *_grad VJPs
+ *     svae/hmm/cython_hmm_inference.pyx:93-166  hmm_logZ / hmm_logZ_grad
+ *     svae/hmm/hmm_inference.py:21-41,54-63     hmm_estep / hmm_viterbi (pyhsmm)
+ * compute one sequence at a time on the CPU; here each call processes a BATCH of B independent
+ * sequences on the current CUDA device.  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions (identical to the reference's external arrays):
+ *   - all arrays are fp64, C-order (row-major), densely packed, DEVICE pointers;
+ *   - Gaussian natural parameters are (-1/2 J, h): `init_J`, `J11`, `J22`, `node_J` hold -1/2 x
+ *     (information matrix), `J12` holds (Sigma^-1 A)' exactly as svae/lds/gaussian.py:130-143;
+ *   - node potentials are diagonal: node_J (B,T,n), node_h (B,T,n), node_logZ (B,T) or NULL
+ *     (the Cython path is diagonal-only, cython_lds_inference.pyx:43,67-70);
+ *   - buffers are owned by the caller; kernels never allocate; calls are asynchronous on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream) and re-entrant per stream;
+ *   - return value: 0 on success, a negative SVAE_ERR_* for host-side argument errors.  A
+ *     non-positive Cholesky pivot (the reference's `assert`s on positive-definiteness,
+ *     svae/lds/gaussian.py:48,64; LAPACK `info` is ignored by the Cython path,
+ *     cython_gaussian_grads.pxd:54) is reported through the optional device word `status`
+ *     (set to 1 + index of a failing sequence; left untouched otherwise).
+ */
+#ifndef SVAE_B200_H_
+#define SVAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVAE_OK 0
+#define SVAE_ERR_BAD_ARG (-1)       /* NULL pointer / non-positive size                           */
+#define SVAE_ERR_UNSUPPORTED (-2)   /* n, K or num_samples outside the compiled range             */
+#define SVAE_ERR_WORKSPACE (-3)     /* workspace too small                                         */
+#define SVAE_ERR_CUDA (-4)          /* launch failed (cudaGetLastError != cudaSuccess)            */
+
+#define SVAE_LDS_MAX_N 16           /* latent dimension range compiled into the library: 1..16    */
+#define SVAE_HMM_MAX_K 64           /* discrete states: 1..64                                      */
+
+/* flags for svae_lds_estep_fwd */
+#define SVAE_LDS_PER_T_PAIR_STATS 1 /* also write per-time second moments (inhomogeneous E_pair)   */
+#define SVAE_LDS_SAVE_FOR_BWD 2     /* keep what svae_lds_estep_bwd needs in the workspace         */
+
+/* Library version / build info: "svae_b200 <version> sm_100a". */
+const char* svae_b200_version(void);
+
+/* Kernels launched by this library since load (all entry points), for bench.py's gpu_launches. */
+uint64_t svae_b200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * LDS local E-step, forward: fused information-form Kalman filter + RTS smoother + backward sampler.
+ * Replaces cython_natural_lds_inference_general (svae/lds/lds_inference.py:196-202), i.e. the
+ * composition natural_filter_forward_general -> natural_smoother_general -> natural_sample_backward,
+ * for B sequences at once.
+ *
+ *   init_J (n,n), init_h (n), init_logZ (1) or NULL          shared by the batch
+ *   J11, J12, J22 (n,n), pair_logZ (1) or NULL               homogeneous dynamics, shared; or, with
+ *       pair_stride_t != 0: (T-1,n,n)/(T-1) time-inhomogeneous, element (t) at ptr + t*pair_stride_t
+ *       (for pair_logZ the strides are divided by n*n); pair_stride_b != 0 adds a per-sequence stride
+ *       (SLDS: svae/models/slds_svae.py:92-103).  Strides are in doubles.
+ *   node_J, node_h (B,T,n), node_logZ (B,T) or NULL
+ *   eps (B,T,S,n) standard-normal noise, eps[b,t] consumed at time t; NULL iff S == 0.
+ *       (The reference draws randn(T,S,n) internally and consumes it in reverse time order,
+ *        cython_lds_inference.pyx:333 -- draw k is used at time T-1-k.)
+ * outputs (any may be NULL to skip):
+ *   E_init_xx (B,n,n) E[x0 x0'], E_init_x (B,n) E[x0]
+ *   E_pair_xx (B,n,n) sum_{t<T-1} E[x_t x_t'], E_pair_xxn (B,n,n) sum E[x_t x_{t+1}'],
+ *   E_pair_xnxn (B,n,n) sum E[x_{t+1} x_{t+1}']           (cython_lds_inference.pyx:198-210)
+ *   E_node_xx (B,T,n) diag E[x_t x_t'], E_node_x (B,T,n) E[x_t]
+ *   samples (B,T,S,n)
+ *   lognorm (B)
+ *   Exx_t (B,T,n,n), Exxn_t (B,T-1,n,n): per-time moments, only with SVAE_LDS_PER_T_PAIR_STATS
+ *   status: optional device int32
+ *   workspace: device scratch of at least svae_lds_estep_workspace_bytes() bytes, 16-byte aligned.
+ */
+size_t svae_lds_estep_workspace_bytes(int B, int T, int n, int S, int flags);
+
+int svae_lds_estep_fwd(
+    int B, int T, int n, int S, int flags,
+    const double* init_J, const double* init_h, const double* init_logZ,
+    const double* J11, const double* J12, const double* J22, const double* pair_logZ,
+    long long pair_stride_t, long long pair_stride_b,
+    const double* node_J, const double* node_h, const double* node_logZ,
+    const double* eps,
+    double* E_init_xx, double* E_init_x,
+    double* E_pair_xx, double* E_pair_xxn, double* E_pair_xnxn,
+    double* E_node_xx, double* E_node_x,
+    double* samples, double* lognorm,
+    double* Exx_t, double* Exxn_t,
+    int* status, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVAE_B200_H_ */

@@ -1,0 +1,88 @@
+"""ctypes binding of libsvae_b200.so (the C-ABI declared in include/svae_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every tensor crosses the boundary as a
+raw device pointer.  There is NO CPU fallback: if the CUDA library is missing or a tensor is not a
+CUDA fp64 tensor the call raises.
+"""
+from __future__ import annotations
+import ctypes, os
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvae_b200.so")
+
+SVAE_LDS_MAX_N = 16
+SVAE_LDS_PER_T_PAIR_STATS = 1
+SVAE_LDS_SAVE_FOR_BWD = 2
+
+_ERR = {-1: "SVAE_ERR_BAD_ARG", -2: "SVAE_ERR_UNSUPPORTED", -3: "SVAE_ERR_WORKSPACE", -4: "SVAE_ERR_CUDA"}
+
+_lib = None
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_LL = ctypes.c_longlong
+_SZ = ctypes.c_size_t
+
+_SIGNATURES = {
+    "svae_b200_version": (ctypes.c_char_p, []),
+    "svae_b200_launch_count": (ctypes.c_uint64, []),
+    "svae_lds_estep_workspace_bytes": (_SZ, [_I] * 5),
+    "svae_lds_estep_fwd": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 15 + [_P, _P, _SZ, _P]),
+}
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) the CUDA library; raise loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "svae_b200: %s is missing -- build it with `python -m svae_b200.build` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(code: int, what: str):
+    if code != 0:
+        raise RuntimeError("%s failed: %s (%d)" % (what, _ERR.get(code, "?"), code))
+
+
+def ptr(t: torch.Tensor | None):
+    """Raw device pointer of a contiguous CUDA fp64 tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("svae_b200: expected a CUDA tensor, got device=%s (no CPU path)" % t.device)
+    if not t.is_contiguous():
+        raise RuntimeError("svae_b200: tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def f64(x, device=None) -> torch.Tensor:
+    """Contiguous CUDA fp64 view/copy of x."""
+    if not torch.is_tensor(x):
+        x = torch.as_tensor(x, dtype=torch.float64, device=device)
+    if x.dtype != torch.float64:
+        x = x.to(torch.float64)
+    if device is not None and x.device != torch.device(device):
+        x = x.to(device)
+    return x.contiguous()
+
+
+def stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def launch_count() -> int:
+    return int(lib().svae_b200_launch_count())

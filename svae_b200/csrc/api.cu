@@ -1,0 +1,74 @@
+// api.cu -- the extern "C" boundary of libsvae_b200.so (see include/svae_b200.h).
+#include <atomic>
+#include "svae_b200.h"
+#include "launch.h"
+
+static std::atomic<uint64_t> g_launches{0};
+
+extern "C" const char* svae_b200_version(void) { return "svae_b200 0.1 sm_100a"; }
+extern "C" uint64_t svae_b200_launch_count(void) { return g_launches.load(); }
+
+namespace {
+typedef cudaError_t (*lds_fwd_fn)(const svae::LdsFwdParams&, int, bool, cudaStream_t);
+const lds_fwd_fn kLdsFwd[SVAE_LDS_MAX_N + 1] = {
+    nullptr,
+    svae::lds_fwd_launch_n1, svae::lds_fwd_launch_n2, svae::lds_fwd_launch_n3, svae::lds_fwd_launch_n4,
+    svae::lds_fwd_launch_n5, svae::lds_fwd_launch_n6, svae::lds_fwd_launch_n7, svae::lds_fwd_launch_n8,
+    svae::lds_fwd_launch_n9, svae::lds_fwd_launch_n10, svae::lds_fwd_launch_n11, svae::lds_fwd_launch_n12,
+    svae::lds_fwd_launch_n13, svae::lds_fwd_launch_n14, svae::lds_fwd_launch_n15, svae::lds_fwd_launch_n16};
+
+int pick_lps(int n, int S) {
+  if (n + 1 + S <= 16) return 16;
+  if (n + 1 + S <= 32) return 32;
+  return 0;
+}
+}  // namespace
+
+extern "C" size_t svae_lds_estep_workspace_bytes(int B, int T, int n, int S, int flags) {
+  (void)flags;
+  if (B <= 0 || T <= 0 || n <= 0 || S < 0) return 0;
+  return sizeof(double) * (size_t)B * (size_t)T * (size_t)svae::lds_stash_stride(n, S);
+}
+
+extern "C" int svae_lds_estep_fwd(
+    int B, int T, int n, int S, int flags,
+    const double* init_J, const double* init_h, const double* init_logZ,
+    const double* J11, const double* J12, const double* J22, const double* pair_logZ,
+    long long pair_stride_t, long long pair_stride_b,
+    const double* node_J, const double* node_h, const double* node_logZ,
+    const double* eps,
+    double* E_init_xx, double* E_init_x,
+    double* E_pair_xx, double* E_pair_xxn, double* E_pair_xnxn,
+    double* E_node_xx, double* E_node_x,
+    double* samples, double* lognorm,
+    double* Exx_t, double* Exxn_t,
+    int* status, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || T <= 0 || n <= 0 || S < 0) return SVAE_ERR_BAD_ARG;
+  if (!init_J || !init_h || !node_J || !node_h || !workspace) return SVAE_ERR_BAD_ARG;
+  if (T > 1 && (!J11 || !J12 || !J22)) return SVAE_ERR_BAD_ARG;
+  if (S > 0 && !eps) return SVAE_ERR_BAD_ARG;
+  if (n > SVAE_LDS_MAX_N) return SVAE_ERR_UNSUPPORTED;
+  const int lps = pick_lps(n, S);
+  if (!lps) return SVAE_ERR_UNSUPPORTED;
+  if (workspace_bytes < svae_lds_estep_workspace_bytes(B, T, n, S, flags)) return SVAE_ERR_WORKSPACE;
+
+  svae::LdsFwdParams p;
+  p.B = B; p.T = T; p.S = S; p.flags = flags;
+  p.init_J = init_J; p.init_h = init_h; p.init_logZ = init_logZ;
+  p.J11 = J11; p.J12 = J12; p.J22 = J22; p.pair_logZ = pair_logZ;
+  p.pair_stride_t = pair_stride_t; p.pair_stride_b = pair_stride_b;
+  p.node_J = node_J; p.node_h = node_h; p.node_logZ = node_logZ;
+  p.eps = eps;
+  p.E_init_xx = E_init_xx; p.E_init_x = E_init_x;
+  p.E_pair_xx = E_pair_xx; p.E_pair_xxn = E_pair_xxn; p.E_pair_xnxn = E_pair_xnxn;
+  p.E_node_xx = E_node_xx; p.E_node_x = E_node_x;
+  p.samples = samples; p.lognorm = lognorm;
+  const bool per_t = (flags & SVAE_LDS_PER_T_PAIR_STATS) != 0;
+  p.Exx_t = per_t ? Exx_t : nullptr; p.Exxn_t = per_t ? Exxn_t : nullptr;
+  p.status = status;
+  p.stash = static_cast<double*>(workspace);
+  const bool inhomog = (pair_stride_t != 0 || pair_stride_b != 0) && T > 1;
+  cudaError_t e = kLdsFwd[n](p, lps, inhomog, static_cast<cudaStream_t>(stream));
+  g_launches.fetch_add(1);
+  return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
+}

@@ -1,0 +1,220 @@
+"""Batched LDS local E-step on B200 -- host-side mirror of the reference's svae/lds/lds_inference.py.
+
+Same names, argument meaning and return structure as the reference drivers
+  natural_lds_inference_general / cython_natural_lds_inference_general   (lds_inference.py:185-202)
+  natural_lds_estep_general / cython_natural_lds_estep_general           (lds_inference.py:223-237)
+  natural_lds_sample / cython_natural_lds_sample                         (lds_inference.py:253-264)
+with one addition: node parameters may carry a leading batch axis of B independent sequences
+(the reference handles one sequence per call).  Unbatched (T,n) inputs are accepted and return
+unbatched results exactly like the reference.
+
+All arithmetic runs in the hand-written sm_100a kernels of libsvae_b200.so through the C-ABI in
+include/svae_b200.h; PyTorch only owns memory and streams.  No CPU path exists.
+"""
+from __future__ import annotations
+import ctypes
+import torch
+from .. import _lib
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter bookkeeping (lds_inference.py:44-80)
+# ------------------------------------------------------------------------------------------------
+
+def _canonical_init_params(init_params, device):
+    """(J, h, logZ...) -> (J, h, sum of the scalar terms) as in lds_inference.py:61-62."""
+    J = _lib.f64(init_params[0], device)
+    h = _lib.f64(init_params[1], device)
+    logZ = None
+    for term in init_params[2:]:
+        term = _lib.f64(term, device).reshape(())
+        logZ = term if logZ is None else logZ + term
+    return J, h, (None if logZ is None else logZ.reshape(1).contiguous())
+
+
+def _canonical_node_params(node_params, device):
+    """Accepts (J,h) or (J,h,logZ) with J diagonal; shapes (T,n) or (B,T,n)  (lds_inference.py:65-80).
+
+    Dense (T,n,n) node precisions -- accepted by the reference's pure-Python path only, never by its
+    Cython path (cython_lds_inference.pyx:43) -- are rejected with ValueError like any other bad shape.
+    """
+    if not isinstance(node_params, (tuple, list)) or len(node_params) not in (2, 3):
+        raise ValueError("node_params must be (J, h) or (J, h, logZ)")
+    J = _lib.f64(node_params[0], device)
+    h = _lib.f64(node_params[1], device)
+    batched = h.dim() == 3
+    if h.dim() not in (2, 3) or J.shape != h.shape:
+        raise ValueError("node_params shapes %s %s not supported (diagonal (T,n) or (B,T,n))"
+                         % (tuple(J.shape), tuple(h.shape)))
+    if not batched:
+        J, h = J[None], h[None]
+    logZ = None
+    if len(node_params) == 3 and node_params[2] is not None:
+        logZ = _lib.f64(node_params[2], device)
+        if not batched:
+            logZ = logZ[None]
+        if logZ.shape != h.shape[:2]:
+            raise ValueError("node logZ shape %s" % (tuple(logZ.shape),))
+    return J.contiguous(), h.contiguous(), logZ, batched
+
+
+def _canonical_pair_params(pair_params, B, T, n, device):
+    """Homogeneous (n,n) blocks, time-inhomogeneous (T-1,n,n) or per-sequence (B,T-1,n,n)
+    (_repeat_param, lds_inference.py:50-59; ensure_time_axis, cython_lds_inference.pyx:17-26)."""
+    J11, J12, J22 = (_lib.f64(x, device) for x in pair_params[:3])
+    logZ = _lib.f64(pair_params[3], device) if len(pair_params) > 3 and pair_params[3] is not None else None
+    if not (J11.shape == J12.shape == J22.shape) or J11.shape[-2:] != (n, n):
+        raise ValueError("pair_params shapes")
+    if J11.dim() == 2:
+        st, sb = 0, 0
+        if logZ is not None:
+            logZ = logZ.reshape(1)
+    elif J11.dim() == 3 and J11.shape[0] == T - 1:
+        st, sb = n * n, 0
+        if logZ is not None:
+            logZ = logZ.expand(T - 1).contiguous() if logZ.dim() == 0 else logZ.reshape(T - 1)
+    elif J11.dim() == 4 and J11.shape[:2] == (B, T - 1):
+        st, sb = n * n, (T - 1) * n * n
+        if logZ is not None:
+            logZ = logZ.expand(B, T - 1).contiguous()
+    else:
+        raise ValueError("pair_params leading shape %s" % (tuple(J11.shape[:-2]),))
+    return J11, J12, J22, logZ, st, sb
+
+
+# ------------------------------------------------------------------------------------------------
+# the kernel call
+# ------------------------------------------------------------------------------------------------
+
+def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=None,
+                      per_t_pair_stats=False, want_stats=True, generator=None, check_status=False):
+    """One launch of the fused filter + smoother + sampler kernel.  Returns a dict of raw tensors."""
+    h_any = node_params[1]
+    device = h_any.device if torch.is_tensor(h_any) and h_any.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    nJ, nh, nlogZ, batched = _canonical_node_params(node_params, device)
+    B, T, n = nh.shape
+    if n > _lib.SVAE_LDS_MAX_N:
+        raise ValueError("latent dimension %d > %d" % (n, _lib.SVAE_LDS_MAX_N))
+    iJ, ih, ilogZ = _canonical_init_params(init_params, device)
+    if iJ.shape != (n, n) or ih.shape != (n,):
+        raise ValueError("init_params shapes")
+    J11, J12, J22, plogZ, st, sb = _canonical_pair_params(pair_params, B, T, n, device)
+    S = int(num_samples) if num_samples else 0
+    if eps is not None:
+        eps = _lib.f64(eps, device)
+        if not batched and eps.dim() == 3:
+            eps = eps[None]
+        if eps.shape != (B, T, S, n):
+            raise ValueError("eps must be (B,T,S,n) = %s, got %s" % ((B, T, S, n), tuple(eps.shape)))
+        eps = eps.contiguous()
+    elif S > 0:
+        eps = torch.randn((B, T, S, n), dtype=torch.float64, device=device, generator=generator)
+
+    L = _lib.lib()
+    flags = _lib.SVAE_LDS_PER_T_PAIR_STATS if per_t_pair_stats else 0
+    new = lambda *shape: torch.empty(shape, dtype=torch.float64, device=device)
+    out = dict(B=B, T=T, n=n, S=S, batched=batched, eps=eps)
+    out["lognorm"] = new(B)
+    out["E_node_xx"], out["E_node_x"] = new(B, T, n), new(B, T, n)
+    out["samples"] = new(B, T, S, n) if S > 0 else None
+    if want_stats:
+        out["E_init_xx"], out["E_init_x"] = new(B, n, n), new(B, n)
+        out["E_pair_xx"], out["E_pair_xxn"], out["E_pair_xnxn"] = new(B, n, n), new(B, n, n), new(B, n, n)
+    if per_t_pair_stats:
+        out["Exx_t"], out["Exxn_t"] = new(B, T, n, n), new(B, max(T - 1, 0), n, n)
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    wbytes = L.svae_lds_estep_workspace_bytes(B, T, n, S, flags)
+    work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=device)
+    g = out.get
+    P = _lib.ptr
+    code = L.svae_lds_estep_fwd(
+        B, T, n, S, flags,
+        P(iJ), P(ih), P(ilogZ),
+        P(J11), P(J12), P(J22), P(plogZ), st, sb,
+        P(nJ), P(nh), P(nlogZ), P(eps),
+        P(g("E_init_xx")), P(g("E_init_x")),
+        P(g("E_pair_xx")), P(g("E_pair_xxn")), P(g("E_pair_xnxn")),
+        P(out["E_node_xx"]), P(out["E_node_x"]),
+        P(out["samples"]), P(out["lognorm"]),
+        P(g("Exx_t")), P(g("Exxn_t")),
+        ctypes.c_void_p(status.data_ptr()), ctypes.c_void_p(work.data_ptr()), wbytes,
+        _lib.stream_ptr(device))
+    _lib.check(code, "svae_lds_estep_fwd")
+    out["status"] = status
+    if check_status:
+        bad = int(status.item())
+        if bad:
+            raise FloatingPointError("LDS E-step: non-positive-definite pivot in sequence %d "
+                                     "(reference asserts: svae/lds/gaussian.py:48,64)" % (bad - 1))
+    return out
+
+
+def _pack_stats(o, homog):
+    B, T, n = o["B"], o["T"], o["n"]
+    dev = o["lognorm"].device
+    ones = lambda *s: torch.ones(s, dtype=torch.float64, device=dev)
+    E_init = (o["E_init_xx"], o["E_init_x"], ones(B), ones(B))
+    if homog:
+        E_pair = (o["E_pair_xx"], o["E_pair_xxn"], o["E_pair_xnxn"], (T - 1.0) * ones(B))
+    else:
+        E_pair = (o["Exx_t"][:, :-1], o["Exxn_t"], o["Exx_t"][:, 1:], ones(B, T - 1))
+    E_node = (o["E_node_xx"], o["E_node_x"], ones(B, T))
+    stats = (E_init, E_pair, E_node)
+    samples, lognorm = o["samples"], o["lognorm"]
+    if not o["batched"]:
+        sq = lambda x: x[0]
+        stats = tuple(tuple(sq(x) for x in part) for part in stats)
+        samples = None if samples is None else samples[0]
+        lognorm = lognorm[0]
+    return samples, stats, lognorm
+
+
+def _is_homog(pair_params):
+    x = pair_params[0]
+    return (x.dim() if torch.is_tensor(x) else torch.as_tensor(x).dim()) == 2
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-named drivers
+# ------------------------------------------------------------------------------------------------
+
+def natural_lds_inference_general(natparam, node_params, num_samples=1, eps=None, generator=None):
+    """(samples, (E_init_stats, E_pair_stats, E_node_stats), lognorm)  -- lds_inference.py:185-202.
+
+    samples (B,T,S,n) [or (T,S,n)]; E_init = (E[x0 x0'], E[x0], 1, 1); E_pair = (sum E[x_t x_t'],
+    sum E[x_t x_{t+1}'], sum E[x_{t+1} x_{t+1}'], T-1) for homogeneous dynamics, per-time arrays
+    otherwise (cython_lds_inference.pyx:198-210); E_node = (diag E[x_t x_t'], E[x_t], 1).
+    `eps` (B,T,S,n) injects the sampler's standard-normal noise, eps[:,t] consumed at time t; the
+    reference draws it internally in reverse time order (cython_lds_inference.pyx:333).
+    """
+    init_params, pair_params = natparam
+    homog = _is_homog(pair_params)
+    o = lds_estep_forward(init_params, pair_params, node_params, num_samples, eps,
+                          per_t_pair_stats=not homog, generator=generator)
+    return _pack_stats(o, homog)
+
+
+cython_natural_lds_inference_general = natural_lds_inference_general
+
+
+def natural_lds_estep_general(natparam, node_params):
+    """(lognorm, expected_stats) -- lds_inference.py:223-237."""
+    init_params, pair_params = natparam
+    homog = _is_homog(pair_params)
+    o = lds_estep_forward(init_params, pair_params, node_params, 0, None, per_t_pair_stats=not homog)
+    _, stats, lognorm = _pack_stats(o, homog)
+    return lognorm, stats
+
+
+cython_natural_lds_estep_general = natural_lds_estep_general
+
+
+def natural_lds_sample(natparam, node_params, num_samples=1, eps=None, generator=None):
+    """samples only -- lds_inference.py:253-264."""
+    init_params, pair_params = natparam
+    o = lds_estep_forward(init_params, pair_params, node_params, num_samples, eps,
+                          want_stats=False, generator=generator)
+    return o["samples"] if o["batched"] else o["samples"][0]
+
+
+cython_natural_lds_sample = natural_lds_sample

@@ -1,0 +1,152 @@
+"""GPU: parity of the fused CUDA LDS E-step (through the C-ABI) against the oracle and the
+committed golden vectors from the reference's own compiled kernels.
+
+Tolerance: BASELINE.json's north_star asks <= 1e-5 relative on posterior moments and ELBO terms; both
+sides are fp64, so the tests hold the kernels to RTOL = 1e-9 (max-abs error over max-abs value).
+"""
+import numpy as np
+import pytest
+import torch
+from oracle import lds_numpy as O
+from util import golden_cases, load, rel_err, golden_natparams
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def _gpu(x):
+    return torch.as_tensor(np.asarray(x), dtype=torch.float64, device="cuda")
+
+
+def _run(init, pair, node, eps, S):
+    from svae_b200.lds import lds_inference as K
+    natparam = (tuple(_gpu(x) for x in init), tuple(_gpu(x) for x in pair))
+    samples, stats, lognorm = K.natural_lds_inference_general(
+        natparam, tuple(_gpu(x) for x in node), num_samples=S, eps=None if eps is None else _gpu(eps))
+    torch.cuda.synchronize()
+    cpu = lambda x: None if x is None else x.cpu().numpy()
+    return cpu(samples), tuple(tuple(cpu(x) for x in part) for part in stats), cpu(lognorm)
+
+
+def _compare(got, want, tol=RTOL):
+    samples, (E_init, E_pair, E_node), lognorm = got
+    w_samples, (wE_init, wE_pair, wE_node), w_lognorm = want
+    assert rel_err(lognorm, w_lognorm) < tol
+    assert rel_err(E_node[0], wE_node[0]) < tol and rel_err(E_node[1], wE_node[1]) < tol
+    assert rel_err(E_init[0], wE_init[0]) < tol and rel_err(E_init[1], wE_init[1]) < tol
+    for k in range(3):
+        assert rel_err(E_pair[k], wE_pair[k]) < tol, "E_pair[%d]" % k
+    assert np.allclose(E_pair[3], wE_pair[3])
+    if w_samples is not None and w_samples.size:
+        assert rel_err(samples, w_samples) < tol
+
+
+@pytest.mark.parametrize("path", golden_cases("lds_"))
+def test_golden_vectors_from_reference(path):
+    d = load(path)
+    init, pair, node = golden_natparams(d)
+    S = d["eps"].shape[2]
+    got = _run(init, pair, node, d["eps"], S)
+    want = (d["samples"], ((d["E_init_xx"], d["E_init_x"]), (d["E_pair_xx"], d["E_pair_xxn"], d["E_pair_xnxn"], d["E_pair_n"]),
+                           (d["E_node_xx"], d["E_node_x"])), d["lognorm"])
+    _compare(got, want)
+
+
+@pytest.mark.parametrize("n,T,B,S", [
+    (8, 50, 256, 1),      # BASELINE configs[1]
+    (10, 200, 64, 1),     # metric shape, oracle-sized batch
+    (16, 200, 16, 1),     # configs[3] shape
+    (5, 7, 3, 4),         # ragged: B not a multiple of the tile, several samples
+    (1, 3, 5, 2),         # scalar latent
+    (16, 3, 33, 15),      # largest n with the most sample paths a 32-lane tile holds
+    (14, 4, 2, 1),        # largest n on a 16-lane tile
+    (15, 4, 2, 0),        # no samples
+    (3, 1, 4, 2),         # single time step: no pair potentials at all
+    (2, 2, 1, 1),
+])
+def test_parity_vs_oracle(n, T, B, S):
+    rng = np.random.default_rng(1000 * n + T)
+    init, pair = O.rand_lds_natparam(n, rng)
+    node = O.rand_node_potentials(B, T, n, rng)
+    node = (node[0], node[1], rng.standard_normal((B, T)))
+    eps = rng.standard_normal((B, T, S, n))
+    want = O.natural_lds_inference_general((init, pair), node, eps)
+    got = _run(init, pair, node, eps if S else None, S)
+    _compare(got, want)
+
+
+def test_full_size_properties():
+    """BASELINE metric config d=10 T=200 B=4096: size-independent properties instead of the oracle:
+    (a) permuting the batch permutes the outputs bit-exactly (sequences are independent),
+    (b) a sub-batch run through the oracle agrees,
+    (c) E[x x']_ii - E[x]_i^2 > 0 (valid marginal variances), symmetric second moments."""
+    from svae_b200.lds import lds_inference as K
+    n, T, B, S = 10, 200, 4096, 1
+    rng = np.random.default_rng(7)
+    init, pair = O.rand_lds_natparam(n, rng)
+    node = O.rand_node_potentials(B, T, n, rng)
+    eps = rng.standard_normal((B, T, S, n))
+    natparam = (tuple(_gpu(x) for x in init), tuple(_gpu(x) for x in pair))
+    gnode = tuple(_gpu(x) for x in node)
+    geps = _gpu(eps)
+    s0, (Ei0, Ep0, En0), l0 = K.natural_lds_inference_general(natparam, gnode, S, geps)
+    perm = torch.randperm(B, device="cuda")
+    s1, (Ei1, Ep1, En1), l1 = K.natural_lds_inference_general(
+        natparam, tuple(x[perm].contiguous() for x in gnode), S, geps[perm].contiguous())
+    assert torch.equal(s1, s0[perm]) and torch.equal(l1, l0[perm])
+    assert torch.equal(En1[0], En0[0][perm]) and torch.equal(Ep1[1], Ep0[1][perm])
+    var = En0[0] - En0[1] ** 2
+    assert bool((var > 0).all())
+    assert float((Ep0[0] - Ep0[0].transpose(-1, -2)).abs().max()) < 1e-9 * float(Ep0[0].abs().max())
+    sub = slice(0, 8)
+    want = O.natural_lds_inference_general((init, pair), tuple(x[sub] for x in node), eps[sub])
+    cpu = lambda x: x[sub].cpu().numpy()
+    got = (cpu(s0), (tuple(cpu(x) for x in Ei0), tuple(cpu(x) for x in Ep0), tuple(cpu(x) for x in En0)), cpu(l0))
+    _compare(got, want)
+
+
+def test_inhomogeneous_pair_params():
+    from svae_b200.lds import lds_inference as K
+    n, T, B, S = 4, 9, 5, 1
+    rng = np.random.default_rng(21)
+    init, _ = O.rand_lds_natparam(n, rng)
+    pairs = [O.rand_lds_natparam(n, rng)[1] for _ in range(T - 1)]
+    pair = tuple(np.stack([p[k] for p in pairs]) for k in range(4))
+    node = O.rand_node_potentials(B, T, n, rng)
+    eps = rng.standard_normal((B, T, S, n))
+    want = O.natural_lds_inference_general((init, pair), node, eps)
+    got = _run(init, pair, node, eps, S)
+    samples, (E_init, E_pair, E_node), lognorm = got
+    w_samples, (wE_init, wE_pair, wE_node), w_lognorm = want
+    assert rel_err(lognorm, w_lognorm) < RTOL and rel_err(samples, w_samples) < RTOL
+    assert E_pair[0].shape == (B, T - 1, n, n)
+    for k in range(3):
+        assert rel_err(E_pair[k], wE_pair[k]) < RTOL
+    assert rel_err(E_node[0], wE_node[0]) < RTOL and rel_err(E_node[1], wE_node[1]) < RTOL
+
+
+def test_non_positive_definite_is_reported():
+    from svae_b200.lds import lds_inference as K
+    n, T, B = 3, 4, 2
+    rng = np.random.default_rng(3)
+    init, pair = O.rand_lds_natparam(n, rng)
+    J, h, _ = O.rand_node_potentials(B, T, n, rng)
+    J[1, 2, :] = +50.0   # natural param -1/2 J > 0  =>  negative node precision, M_t indefinite
+    with pytest.raises(FloatingPointError):
+        K.lds_estep_forward(tuple(_gpu(x) for x in init), tuple(_gpu(x) for x in pair), (_gpu(J), _gpu(h)),
+                            1, None, check_status=True)
+
+
+def test_unbatched_like_the_reference():
+    from svae_b200.lds import lds_inference as K
+    n, T = 3, 6
+    rng = np.random.default_rng(4)
+    init, pair = O.rand_lds_natparam(n, rng)
+    node = O.rand_node_potentials(1, T, n, rng)
+    eps = rng.standard_normal((1, T, 2, n))
+    samples, (E_init, E_pair, E_node), lognorm = K.natural_lds_inference_general(
+        (tuple(_gpu(x) for x in init), tuple(_gpu(x) for x in pair)), (_gpu(node[0][0]), _gpu(node[1][0])), 2, _gpu(eps[0]))
+    assert samples.shape == (T, 2, n) and lognorm.dim() == 0 and E_pair[1].shape == (n, n)
+    with pytest.raises(ValueError):
+        K.natural_lds_inference_general((tuple(_gpu(x) for x in init), tuple(_gpu(x) for x in pair)),
+                                        (_gpu(np.zeros((T, n, n))), _gpu(node[1][0])), 1)

@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- LDS-SVAE local E-step throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                  (N>1: launched by torchrun)
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]
+
+A "step" is one pass of the hot path over one minibatch of synthetic sequences: the fused
+information-form Kalman filter + RTS smoother + backward sampler (one CUDA kernel launch through the
+C-ABI of libsvae_b200.so) for B sequences of shape d=10, T=200 per GPU, followed by the reduction of
+the global expected-sufficient-statistic accumulators over the minibatch and -- for N > 1 -- the
+single NCCL all-reduce of that accumulator per SVI step.  Sequences shard across
+ranks with no other collective: "scaling": "weak" (B per GPU fixed).
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` is the same
+metric through the public API with HOST (pinned) buffers, host<->device copies inside the timed
+region; `roofline` divides the algorithmic bytes of SURVEY.md §8(d) by the kernel's CUDA-event
+duration; `cpu_baseline` times the reference's own compiled Cython kernels (oracle/_ref) on the host
+cores.  `--impl reference` times that reference CPU path alone (rank 0 only).
+"""
+from __future__ import annotations
+import argparse, json, os, subprocess, sys, threading, time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lds_estep_sequences_per_sec"
+UNIT = "sequences/s"
+D, T_LEN, BATCH, NUM_SAMPLES = 10, 200, 4096, 1
+
+
+def alg_bytes_per_seq(n, T):
+    """reads J_node,h_node (16Tn) + writes E_node (16Tn), samples (8Tn),
+    E_init 8(n^2+n), sum E_pair 24 n^2, lognorm 8  =  8(5Tn + 4n^2 + n + 1)."""
+    return 8 * (5 * T * n + 4 * n * n + n + 1)
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------------------------------
+# reference CPU arm: the reference's own Cython kernels (oracle/_ref), one sequence per call
+# --------------------------------------------------------------------------------------------------
+
+def _cpu_worker(args):
+    """Runs `count` sequences of the named shape through the reference primitives; returns seconds."""
+    seed, count, n, T, S = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import numpy as np
+    from oracle import ref, lds_numpy as O
+    rng = np.random.default_rng(0)
+    init, pair = O.rand_lds_natparam(n, rng)           # same dynamics for every worker (seed 0)
+    rng = np.random.default_rng(1000 + seed)
+    J, h, logZ = O.rand_node_potentials(min(count, 64), T, n, rng)
+    ref.lds_estep_one(init, pair, (J[0], h[0], logZ[0]), S, seed=seed)   # warm-up / import
+    t0 = time.perf_counter()
+    for i in range(count):
+        k = i % J.shape[0]
+        ref.lds_estep_one(init, pair, (J[k], h[k], logZ[k]), S)
+    return time.perf_counter() - t0
+
+
+def _cpu_port_worker(args):
+    seed, count, n, T, S = args
+    import numpy as np
+    from oracle import lds_numpy as O
+    rng = np.random.default_rng(0)
+    init, pair = O.rand_lds_natparam(n, rng)
+    rng = np.random.default_rng(1000 + seed)
+    node = O.rand_node_potentials(count, T, n, rng)
+    eps = rng.standard_normal((count, T, S, n))
+    t0 = time.perf_counter()
+    O.natural_lds_inference_general((init, pair), node, eps)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(n, T, S, target_seconds=4.0, cores=None):
+    """sequences/s of the reference CPU path using all host cores (one sequence stream per process)."""
+    import multiprocessing as mp
+    from oracle import ref
+    cores = cores or os.cpu_count() or 1
+    kind = "reference" if ref.available() else "port"
+    worker = _cpu_worker if kind == "reference" else _cpu_port_worker
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        # calibrate on one core, then size the sample for ~target_seconds of wall time on all cores
+        t_one = worker((0, 8, n, T, S)) / 8
+        per_proc = max(8, int(target_seconds / max(t_one, 1e-6)))
+        t0 = time.perf_counter()
+        times = pool.map(worker, [(i, per_proc, n, T, S) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    total = per_proc * cores
+    # rate from the slowest worker's compute time (excludes process start-up and imports)
+    rate = total / max(times)
+    return dict(value=rate, unit=UNIT, cores=cores, kind=kind,
+                sample="%d sequences (d=%d,T=%d,S=%d) = %d per process x %d processes, %.1f s wall; "
+                       "single-core %.1f seq/s" % (total, n, T, S, per_proc, cores, wall, 1.0 / t_one))
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(self.samples))
+
+
+# --------------------------------------------------------------------------------------------------
+# main arms
+# --------------------------------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, T, S = D, T_LEN, NUM_SAMPLES
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        # each step: a bounded sample of the workload on all host cores
+        info = cpu_reference_rate(n, T, S, target_seconds=max(1.0, min(4.0, 60.0 / (args.warmup + args.steps))))
+        if i >= args.warmup:
+            vals.append(info["value"])
+    value = sum(vals) / len(vals)
+    info["value"] = value
+    line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=BATCH / value * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload="LDS-SVAE E-step d=%d T=%d batch=%d S=%d" % (n, T, BATCH, S),
+                            note="reference Cython kernels (oracle/_ref), one sequence per call, all host cores"),
+                cpu_baseline=info,
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle import lds_numpy as O          # synthetic-problem recipe only (host side, untimed)
+    from svae_b200.lds import lds_inference as K
+    from svae_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, T, B, S = D, T_LEN, BATCH, NUM_SAMPLES
+
+    rng = np.random.default_rng(0)
+    init, pair = O.rand_lds_natparam(n, rng)
+    g = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float64, device=dev)
+    gi, gp = tuple(g(x) for x in init), tuple(g(x) for x in pair)
+    gen = torch.Generator(device=dev); gen.manual_seed(1000 + rank)
+    NSETS = 2   # rotate input sets; each set (node potentials + noise = 196 MB) exceeds the 126 MB L2
+    sets = []
+    for _ in range(NSETS):
+        nJ = -0.5 * torch.nn.functional.softplus(torch.randn(B, T, n, dtype=torch.float64, device=dev, generator=gen))
+        nh = torch.randn(B, T, n, dtype=torch.float64, device=dev, generator=gen)
+        eps = torch.randn(B, T, S, n, dtype=torch.float64, device=dev, generator=gen)
+        sets.append((nJ, nh, eps))
+
+    def step(i):
+        nJ, nh, eps = sets[i % NSETS]
+        o = K.lds_estep_forward(gi, gp, (nJ, nh), S, eps)
+        # global expected-statistic accumulator: sum over the minibatch, one all-reduce per SVI step
+        acc = torch.cat([o["E_init_xx"].sum(0).reshape(-1), o["E_init_x"].sum(0), o["E_pair_xx"].sum(0).reshape(-1),
+                         o["E_pair_xxn"].sum(0).reshape(-1), o["E_pair_xnxn"].sum(0).reshape(-1),
+                         o["lognorm"].sum().reshape(1)])
+        if world > 1:
+            dist.all_reduce(acc)
+        return o, acc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    # ---- device-timed region: exactly K steps -----------------------------------------------------
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clk:
+        e0.record()
+        for i in range(args.steps):
+            nJ, nh, eps = sets[i % NSETS]
+            kev[i][0].record()
+            o = K.lds_estep_forward(gi, gp, (nJ, nh), S, eps)
+            kev[i][1].record()
+            acc = torch.cat([o["E_init_xx"].sum(0).reshape(-1), o["E_init_x"].sum(0), o["E_pair_xx"].sum(0).reshape(-1),
+                             o["E_pair_xxn"].sum(0).reshape(-1), o["E_pair_xnxn"].sum(0).reshape(-1),
+                             o["lognorm"].sum().reshape(1)])
+            if world > 1:
+                dist.all_reduce(acc)
+        e1.record()
+        barrier()
+    launches = _lib.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the public API with host buffers ------------------------------------
+    h_nJ = sets[0][0].cpu().pin_memory(); h_nh = sets[0][1].cpu().pin_memory()
+    out_host = dict(
+        samples=torch.empty((B, T, S, n), dtype=torch.float64).pin_memory(),
+        E_node_xx=torch.empty((B, T, n), dtype=torch.float64).pin_memory(),
+        E_node_x=torch.empty((B, T, n), dtype=torch.float64).pin_memory(),
+        lognorm=torch.empty((B,), dtype=torch.float64).pin_memory(),
+        acc=torch.empty((4 * n * n + n + 1,), dtype=torch.float64).pin_memory())
+
+    def e2e_step(i):
+        d_nJ = h_nJ.to(dev, non_blocking=True); d_nh = h_nh.to(dev, non_blocking=True)
+        samples, (E_init, E_pair, E_node), lognorm = K.natural_lds_inference_general((gi, gp), (d_nJ, d_nh), S, generator=gen)
+        acc = torch.cat([E_init[0].sum(0).reshape(-1), E_init[1].sum(0), E_pair[0].sum(0).reshape(-1),
+                         E_pair[1].sum(0).reshape(-1), E_pair[2].sum(0).reshape(-1), lognorm.sum().reshape(1)])
+        if world > 1:
+            dist.all_reduce(acc)
+        out_host["samples"].copy_(samples, non_blocking=True)
+        out_host["E_node_xx"].copy_(E_node[0], non_blocking=True)
+        out_host["E_node_x"].copy_(E_node[1], non_blocking=True)
+        out_host["lognorm"].copy_(lognorm, non_blocking=True)
+        out_host["acc"].copy_(acc, non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e2e_steps = args.steps
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    f1.record()
+    barrier()
+    t = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps
+    h2d = h_nJ.numel() * 8 + h_nh.numel() * 8
+    d2h = sum(v.numel() * 8 for v in out_host.values())
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        ab = alg_bytes_per_seq(n, T) * B
+        achieved = ab / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("lds_estep_fwd_d10_T200_B4096")
+            except Exception:
+                traffic = None
+        try:
+            if args.no_cpu_baseline:
+                raise RuntimeError("skipped (--no-cpu-baseline)")
+            cpu = cpu_reference_rate(n, T, S, target_seconds=4.0)
+        except Exception as e:  # pragma: no cover
+            cpu = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample=repr(e))
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+            ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+            data="synthetic",
+            config=dict(workload="LDS-SVAE E-step d=%d T=%d batch=%d per GPU S=%d" % (n, T, B, S),
+                        global_batch=world * B, parallelism="dp%d" % world,
+                        l2="inputs per step (196 MB node potentials+noise, 1.4 GB stash) exceed the 126 MB L2; "
+                           "%d input sets rotated" % NSETS,
+                        step="fused filter+smoother+sampler kernel, minibatch reduction of global stats"
+                             + (", NCCL all-reduce of the %d-double accumulator" % (4 * n * n + n + 1) if world > 1 else "")),
+            e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                     ms_per_step=e2e_ms),
+            gpu_launches=int(launches),
+            clocks=clk.summary(),
+            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                          traffic=traffic, peak_source=peak_src, kernel="lds_estep_fwd_kernel<10,16>",
+                          kernel_ms=kern_ms, algorithmic_bytes_per_launch=ab,
+                          note="fp64 ALU/latency-bound at ~31 flop/B (SURVEY.md §8d); see DESIGN.md"),
+            cpu_baseline=cpu)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-core baseline (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

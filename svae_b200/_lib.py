@@ -9,7 +9,7 @@ import ctypes, os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvae_b200.so")
+LIB_PATH = os.environ.get("SVAE_B200_LIB") or os.path.join(_HERE, "libsvae_b200.so")
 
 SVAE_LDS_MAX_N = 16
 SVAE_LDS_PER_T_PAIR_STATS = 1

@@ -12,14 +12,16 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "build")
+# experiment hooks: SVAE_BUILD_TAG=<tag> SVAE_BUILD_FLAGS="-DX=1 ..." builds libsvae_b200_<tag>.so
+TAG = os.environ.get("SVAE_BUILD_TAG", "")
+OBJ = os.path.join(CSRC, "build" + ("_" + TAG if TAG else ""))
 INC = os.path.join(os.path.dirname(HERE), "include")
-LIB = os.path.join(HERE, "libsvae_b200.so")
+LIB = os.path.join(HERE, "libsvae_b200%s.so" % ("_" + TAG if TAG else ""))
 MAX_N = 16
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-I", INC, "-I", CSRC]
+         "-Xcompiler", "-fPIC", "-I", INC, "-I", CSRC] + os.environ.get("SVAE_BUILD_FLAGS", "").split()
 
 
 def _units():

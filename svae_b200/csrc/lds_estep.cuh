@@ -12,16 +12,19 @@
 //   * one sub-warp tile of LPS lanes per sequence (LPS = 16 -> 2 sequences per warp, or 32);
 //     lane c < N owns COLUMN c of every n x n matrix in registers, lane N owns the mean/potential
 //     vector, lanes N+1..N+S own one sample path each.  All register arrays are fully unrolled over
-//     the compile-time N; cross-lane traffic is broadcast reads from shared memory.
+//     the compile-time N; cross-lane traffic is 16-byte broadcast reads from shared memory.
 //   * filter step t (same arithmetic result as _natural_condition_diag + _natural_predict):
 //       M_t = J_pred + diag(J_node) + J11        (information form)
 //       M_t = L~ D L~'                           square-root-free LDL' (N reciprocals, no sqrt chain)
-//       [Y | m] = M_t^-1 [J12 | h_f]             one augmented two-sided solve, lane = rhs column
+//       [Y | m] = M_t^-1 [J12 | h_f]             augmented two-sided solve, lane = rhs column,
+//       M_t^-1                                   second rhs set (identity) fused in the same sweep
 //       J_pred' = J22 - J12' Y, h_pred' = -J12' m
 //       lognorm += 1/2 h_f' m - 1/2 sum log d_k
 //     and, off the recursion's critical path, everything the backward sweep needs:
-//       G_t = -Y (smoother gain), M_t^-1, m_t, b_t = m_t + L^-T eps_t   -> "stash" in HBM.
-//   * backward step t is then pure multiply-add on the stash (no factorisation, no solve):
+//       G_t = -Y (smoother gain), M_t^-1, m_t, b_t = m_t + L^-T eps_t   -> "stash" record in HBM.
+//     Node potentials and noise for step t+1 are staged by cp.async (LDGSTS) while step t computes.
+//   * backward step t is pure multiply-add on the stash record, which a 1-D TMA bulk copy
+//     (cp.async.bulk + mbarrier, double-buffered) lands in shared memory two steps ahead:
 //       [C | mu_t | x_t] = G_t [Sigma_{t+1} | mu_{t+1} | x_{t+1}] + [0 | m_t | b_t]
 //       Sigma_t = M_t^-1 + C G_t'
 //       E[x_t x_{t+1}'] = C + mu_t mu_{t+1}',  E[x_t x_t'] = Sigma_t + mu_t mu_t'
@@ -31,6 +34,11 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "async_copy.cuh"
+
+#ifndef SVAE_LDS_TMA
+#define SVAE_LDS_TMA 1
+#endif
 
 namespace svae {
 
@@ -47,22 +55,26 @@ struct LdsFwdParams {
   double* stash;
 };
 
-// doubles per (sequence, time) stash record: G (N*N) | Minv (N*N) | m (N) | b (S*N), padded to even
-__host__ __device__ inline int lds_stash_stride(int N, int S) {
-  int s = 2 * N * N + N + S * N;
-  return (s + 1) & ~1;
-}
+__host__ __device__ constexpr int lds_np(int N) { return (N + 1) & ~1; }   // even row stride
 
-// shared-memory doubles per sequence tile
+// doubles per (sequence, time) stash record: G (N x NP) | Minv (N x NP) | m (NP) | b (S x NP)
+__host__ __device__ inline int lds_stash_stride(int N, int S) { return (2 * N + 1 + S) * lds_np(N); }
+
+// shared-memory doubles per sequence tile (see the carve-up in the kernel)
 __host__ __device__ inline int lds_tile_doubles(int N, int S, bool inhomog) {
-  // Lr | Gs | Cs | hbuf | sq | mbuf | mu_s | ebuf(S*N) | xs(S*N) | vb((1+S)*N) [| J11 J12 J22]
-  int d = 3 * N * N + 4 * N + 2 * S * N + (1 + S) * N + (inhomog ? 3 * N * N : 0);
-  return (d + 1) & ~1;
+  const int NP = lds_np(N);
+  return 2 /*mbarriers*/ + 2 * N * NP /*Lr, Cs*/ + 2 * lds_stash_stride(N, S) /*stash ring*/ +
+         2 * (2 + S) * NP /*node ring*/ + 3 * NP /*sq, mbuf, mu_s*/ + S * NP /*xs*/ +
+         (inhomog ? 3 * N * NP : 0);
 }
 
+#ifndef SVAE_LDS_MINB
+#define SVAE_LDS_MINB 8
+#endif
 template <int N, int LPS, bool INHOMOG>
-__global__ void __launch_bounds__(128) lds_estep_fwd_kernel(const LdsFwdParams p) {
+__global__ void __launch_bounds__(32, SVAE_LDS_MINB) lds_estep_fwd_kernel(const LdsFwdParams p) {
   constexpr int SPW = 32 / LPS;
+  constexpr int NP = lds_np(N);
   constexpr int NN = N * N;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -72,37 +84,44 @@ __global__ void __launch_bounds__(128) lds_estep_fwd_kernel(const LdsFwdParams p
   const bool valid = seq < p.B;
   const long long b = valid ? seq : (long long)p.B - 1;
   const bool mat = c < N, vec = c == N, smp = (c > N) && (c <= N + S);
-  const int s = c - N - 1;
+  const int s = smp ? c - N - 1 : 0;
+  const int cm = mat ? c : 0;   // safe column index for lanes that do not own a matrix column
   const int SS = lds_stash_stride(N, S);
+  const int NODE = (2 + S) * NP;
 
-  // ---- shared memory carve-up -------------------------------------------------------------
+  // ---- shared memory carve-up (all offsets even => 16-byte aligned) --------------------------
   double* shJ11 = smem;           // CTA-shared homogeneous pair parameters, information form
-  double* shJ12 = shJ11 + NN;
-  double* shJ22 = shJ12 + NN;
-  double* tile = shJ22 + NN + (size_t)(warp * SPW + sub) * lds_tile_doubles(N, S, INHOMOG);
-  double* Lr = tile;              // Lr[k*N+i]: raw LDL' column k (i >= k), Lr[k*N+k] = d_k
-  double* Gs = Lr + NN;           // Gs[i*N+k] = G[i][k]
-  double* Cs = Gs + NN;           // Cs[k*N+i] = C[i][k]
-  double* hbuf = Cs + NN;         // node h for this step
-  double* sq = hbuf + N;          // 1/sqrt(d_k)
-  double* mbuf = sq + N;          // m_t
-  double* mu_s = mbuf + N;        // mu_t
-  double* ebuf = mu_s + N;        // eps[s][k]
-  double* xs = ebuf + S * N;      // x_t[s][k]
-  double* vb = xs + S * N;        // staged m | b from the stash
-  double* tJ11 = vb + (1 + S) * N;  // per-tile pair parameters (INHOMOG only)
-  double* tJ12 = tJ11 + NN;
-  double* tJ22 = tJ12 + NN;
+  double* shJ12 = shJ11 + N * NP;
+  double* shJ22 = shJ12 + N * NP;
+  double* tile = shJ22 + N * NP + (size_t)(warp * SPW + sub) * lds_tile_doubles(N, S, INHOMOG);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tile);   // 2 mbarriers
+  double* Lr = tile + 2;          // Lr[k*NP+i]: raw LDL' column k (i >= k), Lr[k*NP+k] = d_k
+  double* Cs = Lr + N * NP;       // Cs[k*NP+i] = C[i][k]
+  double* ring = Cs + N * NP;     // 2 stash records
+  double* nring = ring + 2 * SS;  // 2 x { J_node row | h_node row | eps rows }
+  double* sq = nring + 2 * NODE;  // 1/sqrt(d_k)
+  double* mbuf = sq + NP;         // m_t
+  double* mu_s = mbuf + NP;       // mu_t
+  double* xs = mu_s + NP;         // x_t[s][k]
+  double* tJ11 = xs + S * NP;     // per-tile pair parameters (INHOMOG only)
+  double* tJ12 = tJ11 + N * NP;
+  double* tJ22 = tJ12 + N * NP;
   const double* J11s = INHOMOG ? tJ11 : shJ11;
   const double* J12s = INHOMOG ? tJ12 : shJ12;
   const double* J22s = INHOMOG ? tJ22 : shJ22;
 
   if (!INHOMOG) {
     for (int e = threadIdx.x; e < NN; e += blockDim.x) {
-      shJ11[e] = -2.0 * p.J11[e];
-      shJ12[e] = -p.J12[e];
-      shJ22[e] = -2.0 * p.J22[e];
+      const int i = e / N, j = e % N;
+      shJ11[i * NP + j] = -2.0 * p.J11[e];
+      shJ12[i * NP + j] = -p.J12[e];
+      shJ22[i * NP + j] = -2.0 * p.J22[e];
     }
+  }
+  if (c == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
   }
   __syncthreads();
 
@@ -111,144 +130,182 @@ __global__ void __launch_bounds__(128) lds_estep_fwd_kernel(const LdsFwdParams p
   const double* nh = p.node_h + (size_t)b * T * N;
   const double* eps = p.eps ? p.eps + (size_t)b * T * S * N : nullptr;
 
+  // stage the node potentials (+ noise) of time t into node-ring slot t&1 with cp.async
+  auto stage_node = [&](int t) {
+    if (mat) {
+      double* dst = nring + (t & 1) * NODE;
+      cp_async8(dst + c, nJ + (size_t)t * N + c);
+      cp_async8(dst + NP + c, nh + (size_t)t * N + c);
+      for (int ss = 0; ss < S; ++ss) cp_async8(dst + (2 + ss) * NP + c, eps + ((size_t)t * S + ss) * N + c);
+    }
+    cp_async_commit();
+  };
+
   // [J_pred | h_pred] column owned by this lane (information form)
   double col[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) col[i] = mat ? -2.0 * p.init_J[i * N + c] : (vec ? p.init_h[i] : 0.0);
 
   double lacc = 0.0;   // per-lane partial of lognorm (reduced over the tile at the end)
+  double dprod = 1.0;  // running product of this lane's pivots (log taken every 8 steps)
   bool bad = false;
   double z[N];         // backward-sweep state: column of [Sigma | mu | x]
+
+  stage_node(0);
 
   // =========================== forward in time: information filter ===========================
   for (int t = 0; t < T; ++t) {
     const bool last = (t == T - 1);
-    double jo = 0.0;
-    if (mat) {
-      jo = -2.0 * nJ[(size_t)t * N + c];
-      hbuf[c] = nh[(size_t)t * N + c];
-      for (int ss = 0; ss < S; ++ss) ebuf[ss * N + c] = eps[((size_t)t * S + ss) * N + c];
-    }
+    if (!last) stage_node(t + 1); else cp_async_commit();
     if (INHOMOG && !last) {
       const size_t off = (size_t)t * p.pair_stride_t + (size_t)b * p.pair_stride_b;
       if (mat) {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          tJ11[i * N + c] = -2.0 * p.J11[off + i * N + c];
-          tJ12[i * N + c] = -p.J12[off + i * N + c];
-          tJ22[i * N + c] = -2.0 * p.J22[off + i * N + c];
+          tJ11[i * NP + c] = -2.0 * p.J11[off + i * N + c];
+          tJ12[i * NP + c] = -p.J12[off + i * N + c];
+          tJ22[i * NP + c] = -2.0 * p.J22[off + i * N + c];
         }
       }
     }
+    cp_async_wait<1>();   // this step's node slot has landed (the group just committed may be in flight)
     __syncwarp();
+    const double* nd = nring + (t & 1) * NODE;
 
-    // a = column c of M_t (mat lanes); hf = h_filtered (vec lane)
+    // a = column c of M_t (mat lanes); r = h_filtered (vec lane) or J12 column (mat lanes)
     double a[N], r[N];
+    {
+      const double jo = -2.0 * nd[cm];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      a[i] = col[i] + (last ? 0.0 : J11s[i * N + (mat ? c : 0)]) + (i == c ? jo : 0.0);
-      r[i] = vec ? col[i] + hbuf[i] : (last ? 0.0 : J12s[i * N + (mat ? c : 0)]);
+      for (int i = 0; i < N; ++i) {
+        a[i] = col[i] + (last ? 0.0 : J11s[i * NP + cm]) + ((i == c) ? jo : 0.0);
+        r[i] = vec ? col[i] + nd[NP + i] : (last ? 0.0 : J12s[i * NP + cm]);
+      }
     }
 
-    // ---- square-root-free LDL' of M_t, lanes = rows, columns broadcast through Lr ----------
+    // ---- square-root-free LDL' of M_t: lanes = rows, pivot column broadcast through Lr ------
     double invd[N];
     double dc = 1.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      if (mat) Lr[k * N + c] = a[k];
+      if (mat) Lr[k * NP + c] = a[k];
       __syncwarp();
-      const double piv = Lr[k * N + k];
+      double row[NP];
+#pragma unroll
+      for (int q2 = k / 2; q2 < NP / 2; ++q2) {
+        const double2 v = ld2(&Lr[k * NP + 2 * q2]);
+        row[2 * q2] = v.x;
+        row[2 * q2 + 1] = v.y;
+      }
+      const double piv = row[k];
       bad |= !(piv > 0.0);
-      invd[k] = 1.0 / piv;
+      invd[k] = fast_rcp(piv);
       if (k == c) dc = piv;
       const double tk = a[k] * invd[k];
 #pragma unroll
-      for (int j = k + 1; j < N; ++j) a[j] = fma(-tk, Lr[k * N + j], a[j]);
+      for (int j = k + 1; j < N; ++j) a[j] = fma(-tk, row[j], a[j]);
     }
     if (mat) {
-      lacc -= 0.5 * log(dc);
-      sq[c] = sqrt(1.0 / dc);
+      dprod *= dc;
+      sq[c] = rsqrt(dc);
+    }
+    if ((t & 7) == 7 || last) {
+      lacc -= 0.5 * log(dprod);
+      dprod = 1.0;
     }
     __syncwarp();
 
-    // ---- augmented solve  M_t [Y | m] = [J12 | h_f]  (forward, scale, backward) -------------
-    double w[N], y[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      w[k] = r[k] * invd[k];
-      if (vec) lacc = fma(0.5 * r[k], w[k], lacc);
-#pragma unroll
-      for (int i = k + 1; i < N; ++i) r[i] = fma(-Lr[k * N + i], w[k], r[i]);
-    }
-    if (smp) {
-#pragma unroll
-      for (int k = 0; k < N; ++k) w[k] = ebuf[s * N + k] * sq[k];   // D^-1/2 eps
-    }
-#pragma unroll
-    for (int k = N - 1; k >= 0; --k) {
-      double acc = 0.0;
-#pragma unroll
-      for (int i = k + 1; i < N; ++i) acc = fma(Lr[k * N + i], y[i], acc);
-      y[k] = fma(-invd[k], acc, w[k]);
-    }
-    // mat: y = M^-1 J12[:,c] = -G[:,c];  vec: y = m;  smp: y = L^-T eps
-    if (vec) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) mbuf[i] = y[i];
-    }
-    __syncwarp();
-    if (smp) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        y[i] += mbuf[i];   // b_t = m_t + L^-T eps_t
-        xs[s * N + i] = y[i];
-      }
-    }
-
-    // ---- M_t^-1 column c (second solve, rhs = e_c) -----------------------------------------
-    double q[N], u[N];
+    // ---- fused dual solve:  M_t [Y | m] = [J12 | h_f]  and  M_t U = I  ------------------------
+    double q[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) q[i] = (i == c) ? 1.0 : 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const double wk = q[k] * invd[k];
+      const double wk = r[k] * invd[k];
+      const double qk = q[k] * invd[k];
+      if (vec) lacc = fma(0.5 * r[k], wk, lacc);
 #pragma unroll
-      for (int i = k + 1; i < N; ++i) q[i] = fma(-Lr[k * N + i], wk, q[i]);
-      q[k] = wk;
+      for (int q2 = (k + 1) / 2; q2 < NP / 2; ++q2) {
+        const double2 v = ld2(&Lr[k * NP + 2 * q2]);
+        if (2 * q2 > k && 2 * q2 < N) {
+          r[2 * q2] = fma(-v.x, wk, r[2 * q2]);
+          q[2 * q2] = fma(-v.x, qk, q[2 * q2]);
+        }
+        if (2 * q2 + 1 > k && 2 * q2 + 1 < N) {
+          r[2 * q2 + 1] = fma(-v.y, wk, r[2 * q2 + 1]);
+          q[2 * q2 + 1] = fma(-v.y, qk, q[2 * q2 + 1]);
+        }
+      }
+      r[k] = wk;
+      q[k] = qk;
     }
+    if (smp) {
+      const double* ep = nd + (2 + s) * NP;
+#pragma unroll
+      for (int k = 0; k < N; ++k) r[k] = ep[k] * sq[k];   // D^-1/2 eps
+    }
+    // backward substitution with L~' (in place: r -> y, q -> u)
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
-      double acc = 0.0;
+      double accr = 0.0, accq = 0.0;
 #pragma unroll
-      for (int i = k + 1; i < N; ++i) acc = fma(Lr[k * N + i], u[i], acc);
-      u[k] = fma(-invd[k], acc, q[k]);
+      for (int q2 = (k + 1) / 2; q2 < NP / 2; ++q2) {
+        const double2 v = ld2(&Lr[k * NP + 2 * q2]);
+        if (2 * q2 > k && 2 * q2 < N) {
+          accr = fma(v.x, r[2 * q2], accr);
+          accq = fma(v.x, q[2 * q2], accq);
+        }
+        if (2 * q2 + 1 > k && 2 * q2 + 1 < N) {
+          accr = fma(v.y, r[2 * q2 + 1], accr);
+          accq = fma(v.y, q[2 * q2 + 1], accq);
+        }
+      }
+      r[k] = fma(-invd[k], accr, r[k]);
+      q[k] = fma(-invd[k], accq, q[k]);
+    }
+    // mat: r = M^-1 J12[:,c] = -G[:,c], q = M^-1[:,c];  vec: r = m;  smp: r = L^-T eps
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) mbuf[i] = r[i];
+    }
+    __syncwarp();
+    if (smp) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) r[i] += mbuf[i];   // b_t = m_t + L^-T eps_t
     }
 
     if (!last) {
-      // ---- stash for the backward sweep -----------------------------------------------------
-      __syncwarp();   // xs visible
+      // ---- stash record for the backward sweep ----------------------------------------------
       double* st = stash + (size_t)t * SS;
-      if (mat && valid) {
+      if (valid) {
+        if (mat) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          st[i * N + c] = -y[i];
-          st[NN + i * N + c] = u[i];
+          for (int i = 0; i < N; ++i) {
+            st[i * NP + c] = -r[i];
+            st[N * NP + i * NP + c] = q[i];
+          }
+          st[2 * N * NP + c] = mbuf[c];
+        } else if (smp) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) st[(2 * N + 1 + s) * NP + i] = r[i];
         }
-        st[2 * NN + c] = mbuf[c];
-        for (int ss = 0; ss < S; ++ss) st[2 * NN + N + ss * N + c] = xs[ss * N + c];
       }
       // ---- predict: [J_pred' | h_pred'] = [J22 | 0] - J12' [Y | m] ----------------------------
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        double acc = mat ? J22s[i * N + c] : 0.0;
+      for (int i = 0; i < N; ++i) col[i] = mat ? J22s[i * NP + c] : 0.0;
 #pragma unroll
-        for (int k = 0; k < N; ++k) acc = fma(-J12s[k * N + i], y[k], acc);
-        col[i] = acc;
+      for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int q2 = 0; q2 < NP / 2; ++q2) {
+          const double2 v = ld2(&J12s[k * NP + 2 * q2]);
+          col[2 * q2] = fma(-v.x, r[k], col[2 * q2]);
+          if (2 * q2 + 1 < N) col[2 * q2 + 1] = fma(-v.y, r[k], col[2 * q2 + 1]);
+        }
       }
     } else {
       // terminal step: the smoothed marginal at T-1 is the filtered one
 #pragma unroll
-      for (int i = 0; i < N; ++i) z[i] = mat ? u[i] : y[i];
+      for (int i = 0; i < N; ++i) z[i] = mat ? q[i] : r[i];
     }
     __syncwarp();
   }
@@ -276,41 +333,58 @@ __global__ void __launch_bounds__(128) lds_estep_fwd_kernel(const LdsFwdParams p
   if (bad && p.status) atomicMax(p.status, (int)b + 1);
 
   // =========================== backward in time: smoother + sampler ==========================
-  double acc_mid[N], acc_xxn[N];
+  // stash records were written through the generic proxy; order them before the async-proxy reads
+  __threadfence_block();
+  fence_proxy_async();
+  __syncwarp();
+  auto fetch = [&](int t, int j) {   // j-th backward step (t = T-2-j) -> ring slot j&1
+#if SVAE_LDS_TMA
+    if (c == 0) {
+      mbar_arrive_expect_tx(&bars[j & 1], (uint32_t)(SS * sizeof(double)));
+      tma_load_1d(ring + (j & 1) * SS, stash + (size_t)t * SS, (uint32_t)(SS * sizeof(double)), &bars[j & 1]);
+    }
+#else
+    double* dst = ring + (j & 1) * SS;
+    const double* src = stash + (size_t)t * SS;
+    for (int e = c; e < SS; e += LPS) dst[e] = src[e];
+#endif
+  };
+  if (T >= 2) fetch(T - 2, 0);
+  if (T >= 3) fetch(T - 3, 1);
+
+  double acc_mid[N], acc_xxn[N], cc[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) acc_mid[i] = acc_xxn[i] = 0.0;
+  for (int i = 0; i < N; ++i) acc_mid[i] = acc_xxn[i] = cc[i] = 0.0;
   double mun_c = 0.0;
-  double cc[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) cc[i] = 0.0;
 
   for (int t = T - 1; t >= 0; --t) {
     if (t < T - 1) {
-      const double* st = stash + (size_t)t * SS;
-      double minv[N];
-      if (mat) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-          Gs[i * N + c] = st[i * N + c];
-          minv[i] = st[NN + i * N + c];
-        }
-        vb[c] = st[2 * NN + c];
-        for (int ss = 0; ss < S; ++ss) vb[N + ss * N + c] = st[2 * NN + N + ss * N + c];
-      }
+      const int j = T - 2 - t;
+      const double* rec = ring + (j & 1) * SS;
+#if SVAE_LDS_TMA
+      mbar_wait(&bars[j & 1], (uint32_t)((j >> 1) & 1));
+#else
       __syncwarp();
+#endif
+      const double* G = rec;
+      const double* Minv = rec + N * NP;
       // C = G z  for every column of [Sigma_{t+1} | mu_{t+1} | x_{t+1}]
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         double acc = 0.0;
 #pragma unroll
-        for (int k = 0; k < N; ++k) acc = fma(Gs[i * N + k], z[k], acc);
+        for (int q2 = 0; q2 < NP / 2; ++q2) {
+          const double2 g = ld2(&G[i * NP + 2 * q2]);
+          acc = fma(g.x, z[2 * q2], acc);
+          if (2 * q2 + 1 < N) acc = fma(g.y, z[2 * q2 + 1], acc);
+        }
         cc[i] = acc;
       }
       if (mat) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) Cs[c * N + i] = cc[i];
+        for (int i = 0; i < N; ++i) Cs[c * NP + i] = cc[i];
       } else if (vec || smp) {
-        const double* base = vb + (vec ? 0 : N + s * N);
+        const double* base = rec + (2 * N + (vec ? 0 : 1 + s)) * NP;
 #pragma unroll
         for (int i = 0; i < N; ++i) z[i] = base[i] + cc[i];
       }
@@ -318,13 +392,21 @@ __global__ void __launch_bounds__(128) lds_estep_fwd_kernel(const LdsFwdParams p
       if (mat) {
         double grow[N];
 #pragma unroll
-        for (int k = 0; k < N; ++k) grow[k] = Gs[c * N + k];
+        for (int q2 = 0; q2 < NP / 2; ++q2) {
+          const double2 g = ld2(&G[c * NP + 2 * q2]);
+          grow[2 * q2] = g.x;
+          if (2 * q2 + 1 < N) grow[2 * q2 + 1] = g.y;
+        }
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          double acc = minv[i];
+        for (int i = 0; i < N; ++i) z[i] = Minv[i * NP + c];
 #pragma unroll
-          for (int k = 0; k < N; ++k) acc = fma(Cs[k * N + i], grow[k], acc);
-          z[i] = acc;   // Sigma_t[i][c]
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+          for (int q2 = 0; q2 < NP / 2; ++q2) {
+            const double2 v = ld2(&Cs[k * NP + 2 * q2]);
+            z[2 * q2] = fma(v.x, grow[k], z[2 * q2]);
+            if (2 * q2 + 1 < N) z[2 * q2 + 1] = fma(v.y, grow[k], z[2 * q2 + 1]);   // Sigma_t[:, c]
+          }
         }
       }
     }
@@ -334,9 +416,10 @@ __global__ void __launch_bounds__(128) lds_estep_fwd_kernel(const LdsFwdParams p
       for (int i = 0; i < N; ++i) mu_s[i] = z[i];
     } else if (smp) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) xs[s * N + i] = z[i];
+      for (int i = 0; i < N; ++i) xs[s * NP + i] = z[i];
     }
     __syncwarp();
+    if (t >= 2 && t < T - 1) fetch(t - 2, T - t);   // the slot just consumed is free: prefetch
     if (mat) {
       const double mu_c = mu_s[c];
       double exx[N];
@@ -351,7 +434,7 @@ __global__ void __launch_bounds__(128) lds_estep_fwd_kernel(const LdsFwdParams p
         if (p.E_node_x) p.E_node_x[bt * N + c] = mu_c;
         if (p.E_node_xx) p.E_node_xx[bt * N + c] = diag;
         if (p.samples)
-          for (int ss = 0; ss < S; ++ss) p.samples[(bt * S + ss) * N + c] = xs[ss * N + c];
+          for (int ss = 0; ss < S; ++ss) p.samples[(bt * S + ss) * N + c] = xs[ss * NP + c];
         if (p.Exx_t) {
 #pragma unroll
           for (int i = 0; i < N; ++i) p.Exx_t[bt * NN + i * N + c] = exx[i];

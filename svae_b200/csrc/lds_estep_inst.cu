@@ -16,7 +16,7 @@ static cudaError_t launch_one(const LdsFwdParams& p, cudaStream_t stream) {
   const long long tiles = (p.B + SPW - 1) / SPW;
   const long long grid = (tiles + warps_per_cta - 1) / warps_per_cta;
   const size_t smem = sizeof(double) *
-      (3 * N * N + (size_t)warps_per_cta * SPW * lds_tile_doubles(N, p.S, INHOMOG));
+      (3 * N * lds_np(N) + (size_t)warps_per_cta * SPW * lds_tile_doubles(N, p.S, INHOMOG));
   auto kern = lds_estep_fwd_kernel<N, LPS, INHOMOG>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

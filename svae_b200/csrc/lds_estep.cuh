@@ -63,16 +63,22 @@ __host__ __device__ inline int lds_stash_stride(int N, int S) { return (2 * N + 
 // shared-memory doubles per sequence tile (see the carve-up in the kernel)
 __host__ __device__ inline int lds_tile_doubles(int N, int S, bool inhomog) {
   const int NP = lds_np(N);
-  return 2 /*mbarriers*/ + 2 * N * NP /*Lr, Cs*/ + 2 * lds_stash_stride(N, S) /*stash ring*/ +
+  return 2 /*mbarriers*/ + 3 * N * NP /*Lr, Lt, Cs*/ + 2 * lds_stash_stride(N, S) /*stash ring*/ +
          2 * (2 + S) * NP /*node ring*/ + 3 * NP /*sq, mbuf, mu_s*/ + S * NP /*xs*/ +
          (inhomog ? 3 * N * NP : 0);
 }
 
+// register budget: one warp per CTA; SVAE_LDS_MAXREG caps registers/thread (144 -> 14 CTAs per SM)
+#if defined(SVAE_LDS_MAXREG)
+#define SVAE_LDS_BOUNDS __maxnreg__(SVAE_LDS_MAXREG)
+#else
 #ifndef SVAE_LDS_MINB
 #define SVAE_LDS_MINB 8
 #endif
+#define SVAE_LDS_BOUNDS __launch_bounds__(32, SVAE_LDS_MINB)
+#endif
 template <int N, int LPS, bool INHOMOG>
-__global__ void __launch_bounds__(32, SVAE_LDS_MINB) lds_estep_fwd_kernel(const LdsFwdParams p) {
+__global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
   constexpr int SPW = 32 / LPS;
   constexpr int NP = lds_np(N);
   constexpr int NN = N * N;
@@ -96,7 +102,8 @@ __global__ void __launch_bounds__(32, SVAE_LDS_MINB) lds_estep_fwd_kernel(const 
   double* tile = shJ22 + N * NP + (size_t)(warp * SPW + sub) * lds_tile_doubles(N, S, INHOMOG);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tile);   // 2 mbarriers
   double* Lr = tile + 2;          // Lr[k*NP+i]: raw LDL' column k (i >= k), Lr[k*NP+k] = d_k
-  double* Cs = Lr + N * NP;       // Cs[k*NP+i] = C[i][k]
+  double* Lt = Lr + N * NP;       // Lt[k*NP+i]: unit-lower L~[i][k] (i > k)
+  double* Cs = Lt + N * NP;       // Cs[k*NP+i] = C[i][k]
   double* ring = Cs + N * NP;     // 2 stash records
   double* nring = ring + 2 * SS;  // 2 x { J_node row | h_node row | eps rows }
   double* sq = nring + 2 * NODE;  // 1/sqrt(d_k)
@@ -106,14 +113,15 @@ __global__ void __launch_bounds__(32, SVAE_LDS_MINB) lds_estep_fwd_kernel(const 
   double* tJ11 = xs + S * NP;     // per-tile pair parameters (INHOMOG only)
   double* tJ12 = tJ11 + N * NP;
   double* tJ22 = tJ12 + N * NP;
-  const double* J11s = INHOMOG ? tJ11 : shJ11;
   const double* J12s = INHOMOG ? tJ12 : shJ12;
   const double* J22s = INHOMOG ? tJ22 : shJ22;
 
   if (!INHOMOG) {
+    // shJ11 holds J22 + J11 (the information matrix every non-terminal prediction lands in),
+    // shJ12 = J12, shJ22 = J22, all in information form
     for (int e = threadIdx.x; e < NN; e += blockDim.x) {
       const int i = e / N, j = e % N;
-      shJ11[i * NP + j] = -2.0 * p.J11[e];
+      shJ11[i * NP + j] = -2.0 * p.J22[e] - 2.0 * p.J11[e];
       shJ12[i * NP + j] = -p.J12[e];
       shJ22[i * NP + j] = -2.0 * p.J22[e];
     }
@@ -141,51 +149,57 @@ __global__ void __launch_bounds__(32, SVAE_LDS_MINB) lds_estep_fwd_kernel(const 
     cp_async_commit();
   };
 
-  // [J_pred | h_pred] column owned by this lane (information form)
-  double col[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) col[i] = mat ? -2.0 * p.init_J[i * N + c] : (vec ? p.init_h[i] : 0.0);
-
   double lacc = 0.0;   // per-lane partial of lognorm (reduced over the tile at the end)
   double dprod = 1.0;  // running product of this lane's pivots (log taken every 8 steps)
   bool bad = false;
-  double z[N];         // backward-sweep state: column of [Sigma | mu | x]
 
   stage_node(0);
+  if (T > 1) stage_node(1); else cp_async_commit();
+  cp_async_wait<1>();
+  __syncwarp();
+
+  // a: mat lanes -- column c of M_t = J_pred + J11 (the node precision is added at the pivot);
+  //    vec lane  -- h_filtered = h_pred + h_node.   Information form.
+  double a[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    if (mat) {
+      a[i] = -2.0 * p.init_J[i * N + c];
+      if (!INHOMOG && T > 1) a[i] -= 2.0 * p.J11[i * N + c];
+    } else {
+      a[i] = vec ? p.init_h[i] + nring[NP + i] : 0.0;
+    }
+  }
 
   // =========================== forward in time: information filter ===========================
   for (int t = 0; t < T; ++t) {
     const bool last = (t == T - 1);
-    if (!last) stage_node(t + 1); else cp_async_commit();
     if (INHOMOG && !last) {
       const size_t off = (size_t)t * p.pair_stride_t + (size_t)b * p.pair_stride_b;
       if (mat) {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          tJ11[i * NP + c] = -2.0 * p.J11[off + i * N + c];
+          const double j11 = -2.0 * p.J11[off + i * N + c];
+          a[i] += j11;
           tJ12[i * NP + c] = -p.J12[off + i * N + c];
           tJ22[i * NP + c] = -2.0 * p.J22[off + i * N + c];
         }
       }
+      __syncwarp();
     }
-    cp_async_wait<1>();   // this step's node slot has landed (the group just committed may be in flight)
-    __syncwarp();
     const double* nd = nring + (t & 1) * NODE;
 
-    // a = column c of M_t (mat lanes); r = h_filtered (vec lane) or J12 column (mat lanes)
-    double a[N], r[N];
-    {
-      const double jo = -2.0 * nd[cm];
+    // right-hand sides: r = J12 column (mat), q = identity column (mat -> M^-1 column)
+    double r[N], q[N];
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        a[i] = col[i] + (last ? 0.0 : J11s[i * NP + cm]) + ((i == c) ? jo : 0.0);
-        r[i] = vec ? col[i] + nd[NP + i] : (last ? 0.0 : J12s[i * NP + cm]);
-      }
+    for (int i = 0; i < N; ++i) {
+      r[i] = last ? 0.0 : J12s[i * NP + cm];
+      q[i] = (i == c) ? 1.0 : 0.0;
     }
 
-    // ---- square-root-free LDL' of M_t: lanes = rows, pivot column broadcast through Lr ------
-    double invd[N];
-    double dc = 1.0;
+    // ---- square-root-free LDL' of M_t fused with the forward substitution of all right-hand
+    //      sides: lanes = rows; the pivot column is broadcast through Lr; the vec lane's `a`
+    //      rides along as a bordered row, which IS its forward substitution ----------------------
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       if (mat) Lr[k * NP + c] = a[k];
@@ -197,15 +211,24 @@ __global__ void __launch_bounds__(32, SVAE_LDS_MINB) lds_estep_fwd_kernel(const 
         row[2 * q2] = v.x;
         row[2 * q2 + 1] = v.y;
       }
-      const double piv = row[k];
+      const double piv = fma(-2.0, nd[k], row[k]);     // + node precision on the diagonal
       bad |= !(piv > 0.0);
-      invd[k] = fast_rcp(piv);
-      if (k == c) dc = piv;
-      const double tk = a[k] * invd[k];
+      const double ik = fast_rcp(piv);
+      const double ta = a[k] * ik, tr = r[k] * ik, tq = q[k] * ik;
+      if (mat) Lt[k * NP + c] = ta;                      // unit-lower factor, column k
+      if (vec) lacc = fma(0.5 * a[k], ta, lacc);         // 1/2 z_k^2 / d_k
 #pragma unroll
-      for (int j = k + 1; j < N; ++j) a[j] = fma(-tk, row[j], a[j]);
+      for (int j = k + 1; j < N; ++j) {
+        a[j] = fma(-ta, row[j], a[j]);
+        r[j] = fma(-tr, row[j], r[j]);
+        q[j] = fma(-tq, row[j], q[j]);
+      }
+      a[k] = ta;
+      r[k] = tr;
+      q[k] = tq;
     }
     if (mat) {
+      const double dc = fma(-2.0, nd[c], Lr[c * NP + c]);
       dprod *= dc;
       sq[c] = rsqrt(dc);
     }
@@ -213,44 +236,23 @@ __global__ void __launch_bounds__(32, SVAE_LDS_MINB) lds_estep_fwd_kernel(const 
       lacc -= 0.5 * log(dprod);
       dprod = 1.0;
     }
-    __syncwarp();
-
-    // ---- fused dual solve:  M_t [Y | m] = [J12 | h_f]  and  M_t U = I  ------------------------
-    double q[N];
+    if (vec) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) q[i] = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      const double wk = r[k] * invd[k];
-      const double qk = q[k] * invd[k];
-      if (vec) lacc = fma(0.5 * r[k], wk, lacc);
-#pragma unroll
-      for (int q2 = (k + 1) / 2; q2 < NP / 2; ++q2) {
-        const double2 v = ld2(&Lr[k * NP + 2 * q2]);
-        if (2 * q2 > k && 2 * q2 < N) {
-          r[2 * q2] = fma(-v.x, wk, r[2 * q2]);
-          q[2 * q2] = fma(-v.x, qk, q[2 * q2]);
-        }
-        if (2 * q2 + 1 > k && 2 * q2 + 1 < N) {
-          r[2 * q2 + 1] = fma(-v.y, wk, r[2 * q2 + 1]);
-          q[2 * q2 + 1] = fma(-v.y, qk, q[2 * q2 + 1]);
-        }
-      }
-      r[k] = wk;
-      q[k] = qk;
+      for (int i = 0; i < N; ++i) r[i] = a[i];
     }
+    __syncwarp();
     if (smp) {
       const double* ep = nd + (2 + s) * NP;
 #pragma unroll
       for (int k = 0; k < N; ++k) r[k] = ep[k] * sq[k];   // D^-1/2 eps
     }
-    // backward substitution with L~' (in place: r -> y, q -> u)
+    // ---- backward substitution with the unit-upper factor L~' (in place) ----------------------
 #pragma unroll
-    for (int k = N - 1; k >= 0; --k) {
+    for (int k = N - 2; k >= 0; --k) {
       double accr = 0.0, accq = 0.0;
 #pragma unroll
       for (int q2 = (k + 1) / 2; q2 < NP / 2; ++q2) {
-        const double2 v = ld2(&Lr[k * NP + 2 * q2]);
+        const double2 v = ld2(&Lt[k * NP + 2 * q2]);
         if (2 * q2 > k && 2 * q2 < N) {
           accr = fma(v.x, r[2 * q2], accr);
           accq = fma(v.x, q[2 * q2], accq);
@@ -260,8 +262,8 @@ __global__ void __launch_bounds__(32, SVAE_LDS_MINB) lds_estep_fwd_kernel(const 
           accq = fma(v.y, q[2 * q2 + 1], accq);
         }
       }
-      r[k] = fma(-invd[k], accr, r[k]);
-      q[k] = fma(-invd[k], accq, q[k]);
+      r[k] -= accr;
+      q[k] -= accq;
     }
     // mat: r = M^-1 J12[:,c] = -G[:,c], q = M^-1[:,c];  vec: r = m;  smp: r = L^-T eps
     if (vec) {
@@ -290,25 +292,38 @@ __global__ void __launch_bounds__(32, SVAE_LDS_MINB) lds_estep_fwd_kernel(const 
           for (int i = 0; i < N; ++i) st[(2 * N + 1 + s) * NP + i] = r[i];
         }
       }
-      // ---- predict: [J_pred' | h_pred'] = [J22 | 0] - J12' [Y | m] ----------------------------
+      // next step's node slot has landed; its ring slot from two steps ago is free again
+      cp_async_wait<0>();
+      __syncwarp();
+      if (t + 2 < T) stage_node(t + 2);
+      // ---- predict straight into next step's M / h_f:
+      //      [J_pred' + J11 | h_pred' + h_node'] = [J22 + J11 | h_node'] - J12' [Y | m] -----------
+      {
+        const double* ndn = nring + ((t + 1) & 1) * NODE;
+        const double* pm = INHOMOG ? J22s : ((t + 1 == T - 1) ? shJ22 : shJ11);
+        const double* pinit = mat ? pm + c : ndn + NP;
+        const int pstr = mat ? NP : 1;
 #pragma unroll
-      for (int i = 0; i < N; ++i) col[i] = mat ? J22s[i * NP + c] : 0.0;
+        for (int i = 0; i < N; ++i) a[i] = pinit[i * pstr];
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
+        for (int k = 0; k < N; ++k) {
 #pragma unroll
-        for (int q2 = 0; q2 < NP / 2; ++q2) {
-          const double2 v = ld2(&J12s[k * NP + 2 * q2]);
-          col[2 * q2] = fma(-v.x, r[k], col[2 * q2]);
-          if (2 * q2 + 1 < N) col[2 * q2 + 1] = fma(-v.y, r[k], col[2 * q2 + 1]);
+          for (int q2 = 0; q2 < NP / 2; ++q2) {
+            const double2 v = ld2(&J12s[k * NP + 2 * q2]);
+            a[2 * q2] = fma(-v.x, r[k], a[2 * q2]);
+            if (2 * q2 + 1 < N) a[2 * q2 + 1] = fma(-v.y, r[k], a[2 * q2 + 1]);
+          }
         }
       }
     } else {
       // terminal step: the smoothed marginal at T-1 is the filtered one
 #pragma unroll
-      for (int i = 0; i < N; ++i) z[i] = mat ? q[i] : r[i];
+      for (int i = 0; i < N; ++i) a[i] = mat ? q[i] : r[i];
     }
     __syncwarp();
   }
+  // backward-sweep state: column of [Sigma | mu | x]  (reuses the registers of a)
+  double (&z)[N] = a;
 
   // lognorm: reduce the per-lane partials over the tile, add the constant terms
   {

@@ -39,6 +39,7 @@
 #ifndef SVAE_LDS_TMA
 #define SVAE_LDS_TMA 1
 #endif
+#define SVAE_LDS_CONST_NN 256
 
 namespace svae {
 
@@ -60,13 +61,24 @@ __host__ __device__ constexpr int lds_np(int N) { return (N + 1) & ~1; }   // ev
 // doubles per (sequence, time) stash record: G (N x NP) | Minv (N x NP) | m (NP) | b (S x NP)
 __host__ __device__ inline int lds_stash_stride(int N, int S) { return (2 * N + 1 + S) * lds_np(N); }
 
-// shared-memory doubles per sequence tile (see the carve-up in the kernel)
+// shared-memory doubles per sequence tile.  The filter sweep (LDL' factors, node ring, per-tile pair
+// parameters) and the backward sweep (stash ring, C) never overlap in time, so they share storage.
+__host__ __device__ inline int lds_tile_filter_doubles(int N, int S, bool inhomog) {
+  const int NP = lds_np(N);
+  return 2 * N * NP /*Lr, Lt*/ + 2 * (2 + S) * NP /*node ring*/ + (inhomog ? 2 * N * NP : 0);
+}
+__host__ __device__ inline int lds_tile_backward_doubles(int N, int S) {
+  return 2 * lds_stash_stride(N, S) /*stash ring*/ + N * lds_np(N) /*Cs*/;
+}
 __host__ __device__ inline int lds_tile_doubles(int N, int S, bool inhomog) {
   const int NP = lds_np(N);
-  return 2 /*mbarriers*/ + 3 * N * NP /*Lr, Lt, Cs*/ + 2 * lds_stash_stride(N, S) /*stash ring*/ +
-         2 * (2 + S) * NP /*node ring*/ + 3 * NP /*sq, mbuf, mu_s*/ + S * NP /*xs*/ +
-         (inhomog ? 3 * N * NP : 0);
+  const int fa = lds_tile_filter_doubles(N, S, inhomog), fb = lds_tile_backward_doubles(N, S);
+  return 2 /*mbarriers*/ + 3 * NP /*sq, mbuf, mu_s*/ + S * NP /*xs*/ + (fa > fb ? fa : fb);
 }
+
+// homogeneous J12 (natural form, row-major n x n) lives in the constant bank so the prediction's
+// multiply-adds take it as an immediate-offset constant operand: no shared-memory traffic at all.
+static __constant__ double c_J12[SVAE_LDS_CONST_NN];
 
 // register budget: one warp per CTA; SVAE_LDS_MAXREG caps registers/thread (144 -> 14 CTAs per SM)
 #if defined(SVAE_LDS_MAXREG)
@@ -101,18 +113,20 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
   double* shJ22 = shJ12 + N * NP;
   double* tile = shJ22 + N * NP + (size_t)(warp * SPW + sub) * lds_tile_doubles(N, S, INHOMOG);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tile);   // 2 mbarriers
-  double* Lr = tile + 2;          // Lr[k*NP+i]: raw LDL' column k (i >= k), Lr[k*NP+k] = d_k
-  double* Lt = Lr + N * NP;       // Lt[k*NP+i]: unit-lower L~[i][k] (i > k)
-  double* Cs = Lt + N * NP;       // Cs[k*NP+i] = C[i][k]
-  double* ring = Cs + N * NP;     // 2 stash records
-  double* nring = ring + 2 * SS;  // 2 x { J_node row | h_node row | eps rows }
-  double* sq = nring + 2 * NODE;  // 1/sqrt(d_k)
+  double* sq = tile + 2;          // 1/sqrt(d_k)
   double* mbuf = sq + NP;         // m_t
   double* mu_s = mbuf + NP;       // mu_t
   double* xs = mu_s + NP;         // x_t[s][k]
-  double* tJ11 = xs + S * NP;     // per-tile pair parameters (INHOMOG only)
-  double* tJ12 = tJ11 + N * NP;
+  double* uni = xs + S * NP;      // ---- phase-shared storage ----
+  // filter sweep
+  double* Lr = uni;               // Lr[k*NP+i]: raw LDL' column k (i >= k), Lr[k*NP+k] = d_k - node
+  double* Lt = Lr + N * NP;       // Lt[k*NP+i]: unit-lower L~[i][k] (i > k)
+  double* nring = Lt + N * NP;    // 2 x { J_node row | h_node row | eps rows }
+  double* tJ12 = nring + 2 * NODE;  // per-tile pair parameters (INHOMOG only)
   double* tJ22 = tJ12 + N * NP;
+  // backward sweep
+  double* ring = uni;             // 2 stash records
+  double* Cs = ring + 2 * SS;     // Cs[k*NP+i] = C[i][k]
   const double* J12s = INHOMOG ? tJ12 : shJ12;
   const double* J22s = INHOMOG ? tJ22 : shJ22;
 
@@ -305,13 +319,22 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
         const int pstr = mat ? NP : 1;
 #pragma unroll
         for (int i = 0; i < N; ++i) a[i] = pinit[i * pstr];
+        if (INHOMOG) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
+          for (int k = 0; k < N; ++k) {
 #pragma unroll
-          for (int q2 = 0; q2 < NP / 2; ++q2) {
-            const double2 v = ld2(&J12s[k * NP + 2 * q2]);
-            a[2 * q2] = fma(-v.x, r[k], a[2 * q2]);
-            if (2 * q2 + 1 < N) a[2 * q2 + 1] = fma(-v.y, r[k], a[2 * q2 + 1]);
+            for (int q2 = 0; q2 < NP / 2; ++q2) {
+              const double2 v = ld2(&J12s[k * NP + 2 * q2]);
+              a[2 * q2] = fma(-v.x, r[k], a[2 * q2]);
+              if (2 * q2 + 1 < N) a[2 * q2 + 1] = fma(-v.y, r[k], a[2 * q2 + 1]);
+            }
+          }
+        } else {
+          // information-form J12 = -(natural J12):  a -= J12_info' r  ==  a += J12_nat' r
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) a[i] = fma(c_J12[k * N + i], r[k], a[i]);
           }
         }
       }
@@ -367,9 +390,9 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
   if (T >= 2) fetch(T - 2, 0);
   if (T >= 3) fetch(T - 3, 1);
 
-  double acc_mid[N], acc_xxn[N], cc[N];
+  double acc_mid[N], acc_xxn[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) acc_mid[i] = acc_xxn[i] = cc[i] = 0.0;
+  for (int i = 0; i < N; ++i) acc_mid[i] = acc_xxn[i] = 0.0;
   double mun_c = 0.0;
 
   for (int t = T - 1; t >= 0; --t) {
@@ -384,43 +407,43 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
       const double* G = rec;
       const double* Minv = rec + N * NP;
       // C = G z  for every column of [Sigma_{t+1} | mu_{t+1} | x_{t+1}]
+      {
+        double cc[N];
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        double acc = 0.0;
+        for (int i = 0; i < N; ++i) {
+          double acc = 0.0;
 #pragma unroll
-        for (int q2 = 0; q2 < NP / 2; ++q2) {
-          const double2 g = ld2(&G[i * NP + 2 * q2]);
-          acc = fma(g.x, z[2 * q2], acc);
-          if (2 * q2 + 1 < N) acc = fma(g.y, z[2 * q2 + 1], acc);
+          for (int q2 = 0; q2 < NP / 2; ++q2) {
+            const double2 g = ld2(&G[i * NP + 2 * q2]);
+            acc = fma(g.x, z[2 * q2], acc);
+            if (2 * q2 + 1 < N) acc = fma(g.y, z[2 * q2 + 1], acc);
+          }
+          cc[i] = acc;
         }
-        cc[i] = acc;
-      }
-      if (mat) {
+        if (mat) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) Cs[c * NP + i] = cc[i];
-      } else if (vec || smp) {
-        const double* base = rec + (2 * N + (vec ? 0 : 1 + s)) * NP;
+          for (int i = 0; i < N; ++i) {
+            Cs[c * NP + i] = cc[i];
+            acc_xxn[i] += cc[i];     // Cov(x_t, x_{t+1})[i][c]; the mean outer product is added below
+          }
+        } else if (vec || smp) {
+          const double* base = rec + (2 * N + (vec ? 0 : 1 + s)) * NP;
 #pragma unroll
-        for (int i = 0; i < N; ++i) z[i] = base[i] + cc[i];
+          for (int i = 0; i < N; ++i) z[i] = base[i] + cc[i];
+        }
       }
       __syncwarp();
       if (mat) {
-        double grow[N];
-#pragma unroll
-        for (int q2 = 0; q2 < NP / 2; ++q2) {
-          const double2 g = ld2(&G[c * NP + 2 * q2]);
-          grow[2 * q2] = g.x;
-          if (2 * q2 + 1 < N) grow[2 * q2 + 1] = g.y;
-        }
 #pragma unroll
         for (int i = 0; i < N; ++i) z[i] = Minv[i * NP + c];
 #pragma unroll
         for (int k = 0; k < N; ++k) {
+          const double gk = G[c * NP + k];
 #pragma unroll
           for (int q2 = 0; q2 < NP / 2; ++q2) {
             const double2 v = ld2(&Cs[k * NP + 2 * q2]);
-            z[2 * q2] = fma(v.x, grow[k], z[2 * q2]);
-            if (2 * q2 + 1 < N) z[2 * q2 + 1] = fma(v.y, grow[k], z[2 * q2 + 1]);   // Sigma_t[:, c]
+            z[2 * q2] = fma(v.x, gk, z[2 * q2]);
+            if (2 * q2 + 1 < N) z[2 * q2 + 1] = fma(v.y, gk, z[2 * q2 + 1]);   // Sigma_t[:, c]
           }
         }
       }
@@ -434,59 +457,60 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
       for (int i = 0; i < N; ++i) xs[s * NP + i] = z[i];
     }
     __syncwarp();
-    if (t >= 2 && t < T - 1) fetch(t - 2, T - t);   // the slot just consumed is free: prefetch
     if (mat) {
       const double mu_c = mu_s[c];
-      double exx[N];
+      const size_t bt = (size_t)b * T + t;
+      const bool first = (t == 0), lastt = (t == T - 1);
+      // hot path: running sums only
       double diag = 0.0;
+      if (!first && !lastt) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        exx[i] = fma(mu_s[i], mu_c, z[i]);
-        if (i == c) diag = exx[i];
+        for (int i = 0; i < N; ++i) {
+          const double mi = mu_s[i];
+          const double exx = fma(mi, mu_c, z[i]);           // E[x_t x_t'][i][c]
+          if (i == c) diag = exx;
+          acc_xxn[i] = fma(mi, mun_c, acc_xxn[i]);
+          acc_mid[i] += exx;
+        }
+      } else {
+        // first / last time step: E_init, the end corrections of the pair sums
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const double mi = mu_s[i];
+          const double exx = fma(mi, mu_c, z[i]);
+          if (i == c) diag = exx;
+          if (!lastt) acc_xxn[i] = fma(mi, mun_c, acc_xxn[i]);
+          if (valid) {
+            const size_t o = (size_t)b * NN + i * N + c;
+            if (lastt && p.E_pair_xnxn) p.E_pair_xnxn[o] = (T > 1) ? exx : 0.0;
+            if (first) {
+              if (p.E_init_xx) p.E_init_xx[o] = exx;
+              if (p.E_pair_xx) p.E_pair_xx[o] = (T > 1) ? acc_mid[i] + exx : 0.0;
+              if (p.E_pair_xxn) p.E_pair_xxn[o] = acc_xxn[i];
+              if (p.E_pair_xnxn && T > 1) p.E_pair_xnxn[o] = (lastt ? 0.0 : p.E_pair_xnxn[o]) + acc_mid[i];
+            }
+          }
+        }
+        if (first && valid && p.E_init_x) p.E_init_x[(size_t)b * N + c] = mu_c;
       }
       if (valid) {
-        const size_t bt = (size_t)b * T + t;
         if (p.E_node_x) p.E_node_x[bt * N + c] = mu_c;
         if (p.E_node_xx) p.E_node_xx[bt * N + c] = diag;
         if (p.samples)
           for (int ss = 0; ss < S; ++ss) p.samples[(bt * S + ss) * N + c] = xs[ss * NP + c];
-        if (p.Exx_t) {
+        if (p.Exx_t) {   // per-time second moments (inhomogeneous E_pair): cold path
 #pragma unroll
-          for (int i = 0; i < N; ++i) p.Exx_t[bt * NN + i * N + c] = exx[i];
-        }
-        if (t < T - 1 && p.Exxn_t) {
-#pragma unroll
-          for (int i = 0; i < N; ++i)
-            p.Exxn_t[((size_t)b * (T - 1) + t) * NN + i * N + c] = fma(mu_s[i], mun_c, cc[i]);
-        }
-      }
-      if (t < T - 1) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) acc_xxn[i] += fma(mu_s[i], mun_c, cc[i]);
-      }
-      if (t == T - 1) {
-        if (valid && p.E_pair_xnxn) {
-#pragma unroll
-          for (int i = 0; i < N; ++i) p.E_pair_xnxn[(size_t)b * NN + i * N + c] = (T > 1) ? exx[i] : 0.0;
-        }
-      } else if (t > 0) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) acc_mid[i] += exx[i];
-      }
-      if (t == 0 && valid) {
-        if (p.E_init_x) p.E_init_x[(size_t)b * N + c] = mu_c;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-          const size_t o = (size_t)b * NN + i * N + c;
-          if (p.E_init_xx) p.E_init_xx[o] = exx[i];
-          if (p.E_pair_xx) p.E_pair_xx[o] = (T > 1) ? acc_mid[i] + exx[i] : 0.0;
-          if (p.E_pair_xxn) p.E_pair_xxn[o] = acc_xxn[i];
-          if (p.E_pair_xnxn && T > 1) p.E_pair_xnxn[o] += acc_mid[i];
+          for (int i = 0; i < N; ++i) {
+            p.Exx_t[bt * NN + i * N + c] = fma(mu_s[i], mu_c, z[i]);
+            if (!lastt && p.Exxn_t)
+              p.Exxn_t[((size_t)b * (T - 1) + t) * NN + i * N + c] = fma(mu_s[i], mun_c, Cs[c * NP + i]);
+          }
         }
       }
       mun_c = mu_c;
     }
     __syncwarp();
+    if (t >= 2 && t < T - 1) fetch(t - 2, T - t);   // the slot just consumed is free: prefetch
   }
 }
 

@@ -1,5 +1,10 @@
 // One translation unit per latent dimension: compiled with -DSVAE_N=<n> for n = 1..SVAE_LDS_MAX_N so
 // the fully-unrolled kernels build in parallel.  Exposes svae::lds_fwd_launch_n<n>().
+// register cap: for n <= 10 the whole metric batch (2048 one-warp CTAs at B = 4096) is resident in ONE
+// wave at 128 registers/thread (16 CTAs/SM); larger n needs the registers more than the occupancy.
+#if !defined(SVAE_LDS_MAXREG) && !defined(SVAE_LDS_MINB) && SVAE_N <= 10
+#define SVAE_LDS_MAXREG 128
+#endif
 #include "lds_estep.cuh"
 #include "launch.h"
 
@@ -7,7 +12,31 @@
 #error "compile with -DSVAE_N=<latent dim>"
 #endif
 
+#include <mutex>
+#include <cstdlib>
+
 namespace svae {
+
+// The homogeneous J12 is handed to the kernel through this translation unit's __constant__ array.
+// One array per latent dimension: uses from different streams are ordered with an event so a copy
+// never overwrites the bank while an earlier launch on another stream may still read it.
+static std::mutex g_const_mu;
+static cudaEvent_t g_const_ev = nullptr;
+static cudaStream_t g_const_stream = nullptr;
+static bool g_const_used = false;
+
+template <int N>
+static cudaError_t stage_const_J12(const double* J12, cudaStream_t stream) {
+  if (!g_const_ev) {
+    cudaError_t e = cudaEventCreateWithFlags(&g_const_ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  if (g_const_used && g_const_stream != stream) {
+    cudaError_t e = cudaStreamWaitEvent(stream, g_const_ev, 0);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaMemcpyToSymbolAsync(c_J12, J12, sizeof(double) * N * N, 0, cudaMemcpyDeviceToDevice, stream);
+}
 
 template <int N, int LPS, bool INHOMOG>
 static cudaError_t launch_one(const LdsFwdParams& p, cudaStream_t stream) {
@@ -18,9 +47,29 @@ static cudaError_t launch_one(const LdsFwdParams& p, cudaStream_t stream) {
   const size_t smem = sizeof(double) *
       (3 * N * lds_np(N) + (size_t)warps_per_cta * SPW * lds_tile_doubles(N, p.S, INHOMOG));
   auto kern = lds_estep_fwd_kernel<N, LPS, INHOMOG>;
+  {
+    // many small CTAs per SM: optional shared-memory carve-out hint (percent), SVAE_LDS_CARVEOUT
+    static bool carved = false;
+    if (!carved) {
+      const char* e = getenv("SVAE_LDS_CARVEOUT");
+      if (e) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+      carved = true;
+    }
+  }
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+  }
+  if (!INHOMOG && p.T > 1) {
+    std::lock_guard<std::mutex> lock(g_const_mu);
+    cudaError_t e = stage_const_J12<N>(p.J12, stream);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)grid, warps_per_cta * 32, smem, stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    g_const_used = true;
+    g_const_stream = stream;
+    return cudaEventRecord(g_const_ev, stream);
   }
   kern<<<(unsigned)grid, warps_per_cta * 32, smem, stream>>>(p);
   return cudaGetLastError();

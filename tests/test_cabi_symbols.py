@@ -27,7 +27,8 @@ def test_library_exports_header_symbols():
 def test_argument_errors_without_gpu():
     from svae_b200 import _lib
     L = _lib.lib()
-    assert L.svae_lds_estep_workspace_bytes(4, 10, 3, 1, 0) == 8 * 4 * 10 * 24
+    # stash record = (2n + 1 + S) rows of even stride: n=3, S=1 -> 8 rows x 4 doubles
+    assert L.svae_lds_estep_workspace_bytes(4, 10, 3, 1, 0) == 8 * 4 * 10 * (2 * 3 + 1 + 1) * 4
     assert L.svae_lds_estep_workspace_bytes(0, 10, 3, 1, 0) == 0
 
 

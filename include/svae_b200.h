@@ -96,6 +96,34 @@ int svae_lds_estep_fwd(
     double* Exx_t, double* Exxn_t,
     int* status, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * LDS local E-step, backward: the VJP of svae_lds_estep_fwd with respect to the node potentials
+ * (node_J, node_h), given cotangents of every output.  Replaces the composition
+ *   natural_sample_backward_grad + natural_smoother_general_grad -> natural_filter_grad
+ * (svae/lds/cython_lds_inference.pyx:357-409, 236-306, 92-145) as wired at svae/lds/lds_inference.py:26-39;
+ * like the reference, gradients flow to the node parameters only (lds_inference.py:27-29).
+ *
+ * The forward call must have been made with SVAE_LDS_SAVE_FOR_BWD; `workspace` is that call's workspace
+ * (it is consumed: single use, as the reference's `intermediates` are -- pyx:472,481), `E_node_x`,
+ * `samples` and `eps` are that call's outputs / noise.
+ *   cotangents (device pointers, any may be NULL = zero), shaped like the corresponding outputs:
+ *     g_samples (B,T,S,n); g_E_init_xx (B,n,n), g_E_init_x (B,n);
+ *     g_E_pair_xx, g_E_pair_xxn, g_E_pair_xnxn (B,n,n)          [homogeneous sums]
+ *     g_Exx_t (B,T,n,n), g_Exxn_t (B,T-1,n,n)                   [per-time moments]
+ *     g_E_node_xx, g_E_node_x (B,T,n); g_lognorm (B)
+ *   outputs: g_node_J, g_node_h (B,T,n).  (d lognorm / d node_logZ is g_lognorm itself.)
+ */
+int svae_lds_estep_bwd(
+    int B, int T, int n, int S, int flags,
+    const double* E_node_x, const double* samples, const double* eps,
+    const double* g_samples,
+    const double* g_E_init_xx, const double* g_E_init_x,
+    const double* g_E_pair_xx, const double* g_E_pair_xxn, const double* g_E_pair_xnxn,
+    const double* g_Exx_t, const double* g_Exxn_t,
+    const double* g_E_node_xx, const double* g_E_node_x, const double* g_lognorm,
+    double* g_node_J, double* g_node_h,
+    void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,7 +80,9 @@ def lds_vjp_one(init_params, pair_params, node_params, g_samples, g_stats, g_log
     np.random.seed(seed)
     samples, saved_b = lds.natural_sample_backward(msgs, pair_params, num_samples)
     eps_time = np.ascontiguousarray(np.asarray(saved_b[3]).T.copy())
-    gm_b = lds.natural_sample_backward_grad(_c(g_samples), saved_b)
+    # natural_sample_backward_grad accumulates into its cotangent argument in place
+    # (_natural_condition_on_grad writes g_y += ..., cython_gaussian_grads.pxd:524): hand it a copy
+    gm_b = lds.natural_sample_backward_grad(np.array(g_samples, dtype=np.float64, order='C'), saved_b)
     # _compute_stats_grad mutates its inputs (pyx:223-224): hand it copies
     g_E_init, g_E_pair, g_E_node = g_stats
     g_copy = (tuple(np.array(x, dtype=np.float64) if np.ndim(x) else x for x in g_E_init),

@@ -29,6 +29,7 @@ _SIGNATURES = {
     "svae_b200_launch_count": (ctypes.c_uint64, []),
     "svae_lds_estep_workspace_bytes": (_SZ, [_I] * 5),
     "svae_lds_estep_fwd": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 15 + [_P, _P, _SZ, _P]),
+    "svae_lds_estep_bwd": (_I, [_I] * 5 + [_P] * 16 + [_P, _SZ, _P]),
 }
 
 

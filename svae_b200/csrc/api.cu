@@ -17,6 +17,14 @@ const lds_fwd_fn kLdsFwd[SVAE_LDS_MAX_N + 1] = {
     svae::lds_fwd_launch_n9, svae::lds_fwd_launch_n10, svae::lds_fwd_launch_n11, svae::lds_fwd_launch_n12,
     svae::lds_fwd_launch_n13, svae::lds_fwd_launch_n14, svae::lds_fwd_launch_n15, svae::lds_fwd_launch_n16};
 
+typedef cudaError_t (*lds_bwd_fn)(const svae::LdsBwdParams&, int, cudaStream_t);
+const lds_bwd_fn kLdsBwd[SVAE_LDS_MAX_N + 1] = {
+    nullptr,
+    svae::lds_bwd_launch_n1, svae::lds_bwd_launch_n2, svae::lds_bwd_launch_n3, svae::lds_bwd_launch_n4,
+    svae::lds_bwd_launch_n5, svae::lds_bwd_launch_n6, svae::lds_bwd_launch_n7, svae::lds_bwd_launch_n8,
+    svae::lds_bwd_launch_n9, svae::lds_bwd_launch_n10, svae::lds_bwd_launch_n11, svae::lds_bwd_launch_n12,
+    svae::lds_bwd_launch_n13, svae::lds_bwd_launch_n14, svae::lds_bwd_launch_n15, svae::lds_bwd_launch_n16};
+
 int pick_lps(int n, int S) {
   if (n + 1 + S <= 16) return 16;
   if (n + 1 + S <= 32) return 32;
@@ -25,9 +33,9 @@ int pick_lps(int n, int S) {
 }  // namespace
 
 extern "C" size_t svae_lds_estep_workspace_bytes(int B, int T, int n, int S, int flags) {
-  (void)flags;
   if (B <= 0 || T <= 0 || n <= 0 || S < 0) return 0;
-  return sizeof(double) * (size_t)B * (size_t)T * (size_t)svae::lds_stash_stride(n, S);
+  const bool save = (flags & SVAE_LDS_SAVE_FOR_BWD) != 0;
+  return sizeof(double) * (size_t)B * (size_t)T * (size_t)svae::lds_record_stride(n, S, save);
 }
 
 extern "C" int svae_lds_estep_fwd(
@@ -69,6 +77,38 @@ extern "C" int svae_lds_estep_fwd(
   p.stash = static_cast<double*>(workspace);
   const bool inhomog = (pair_stride_t != 0 || pair_stride_b != 0) && T > 1;
   cudaError_t e = kLdsFwd[n](p, lps, inhomog, static_cast<cudaStream_t>(stream));
+  g_launches.fetch_add(1);
+  return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
+}
+
+extern "C" int svae_lds_estep_bwd(
+    int B, int T, int n, int S, int flags,
+    const double* E_node_x, const double* samples, const double* eps,
+    const double* g_samples,
+    const double* g_E_init_xx, const double* g_E_init_x,
+    const double* g_E_pair_xx, const double* g_E_pair_xxn, const double* g_E_pair_xnxn,
+    const double* g_Exx_t, const double* g_Exxn_t,
+    const double* g_E_node_xx, const double* g_E_node_x, const double* g_lognorm,
+    double* g_node_J, double* g_node_h,
+    void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || T <= 0 || n <= 0 || S < 0) return SVAE_ERR_BAD_ARG;
+  if (!E_node_x || !workspace || !g_node_J || !g_node_h) return SVAE_ERR_BAD_ARG;
+  if (S > 0 && (!samples || !eps)) return SVAE_ERR_BAD_ARG;
+  if (n > SVAE_LDS_MAX_N) return SVAE_ERR_UNSUPPORTED;
+  const int lps = pick_lps(n, S);
+  if (!lps) return SVAE_ERR_UNSUPPORTED;
+  if (workspace_bytes < svae_lds_estep_workspace_bytes(B, T, n, S, flags | SVAE_LDS_SAVE_FOR_BWD)) return SVAE_ERR_WORKSPACE;
+  svae::LdsBwdParams p;
+  p.B = B; p.T = T; p.S = S; p.flags = flags;
+  p.E_node_x = E_node_x; p.samples = samples; p.eps = eps;
+  p.g_samples = g_samples;
+  p.g_E_init_xx = g_E_init_xx; p.g_E_init_x = g_E_init_x;
+  p.g_E_pair_xx = g_E_pair_xx; p.g_E_pair_xxn = g_E_pair_xxn; p.g_E_pair_xnxn = g_E_pair_xnxn;
+  p.g_Exx_t = g_Exx_t; p.g_Exxn_t = g_Exxn_t;
+  p.g_E_node_xx = g_E_node_xx; p.g_E_node_x = g_E_node_x; p.g_lognorm = g_lognorm;
+  p.g_node_J = g_node_J; p.g_node_h = g_node_h;
+  p.stash = static_cast<double*>(workspace);
+  cudaError_t e = kLdsBwd[n](p, lps, static_cast<cudaStream_t>(stream));
   g_launches.fetch_add(1);
   return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
 }

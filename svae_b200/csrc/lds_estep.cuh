@@ -58,8 +58,14 @@ struct LdsFwdParams {
 
 __host__ __device__ constexpr int lds_np(int N) { return (N + 1) & ~1; }   // even row stride
 
-// doubles per (sequence, time) stash record: G (N x NP) | Minv (N x NP) | m (NP) | b (S x NP)
+// doubles per (sequence, time) stash record: G (N x NP) | Minv (N x NP) | m (NP) | b (S x NP): this
+// prefix is what the smoother sweep fetches.  With SVAE_LDS_SAVE_FOR_BWD the record grows by
+// K = L^-1 (N x NP, lower triangular) and the smoothed covariance Sigma_t (N x NP) for the VJP kernel.
 __host__ __device__ inline int lds_stash_stride(int N, int S) { return (2 * N + 1 + S) * lds_np(N); }
+__host__ __device__ inline int lds_record_stride(int N, int S, bool save) {
+  return (save ? 4 * N + 1 + S : 2 * N + 1 + S) * lds_np(N);
+}
+#define SVAE_LDS_FLAG_SAVE 2
 
 // shared-memory doubles per sequence tile.  The filter sweep (LDL' factors, node ring, per-tile pair
 // parameters) and the backward sweep (stash ring, C) never overlap in time, so they share storage.
@@ -104,7 +110,9 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
   const bool mat = c < N, vec = c == N, smp = (c > N) && (c <= N + S);
   const int s = smp ? c - N - 1 : 0;
   const int cm = mat ? c : 0;   // safe column index for lanes that do not own a matrix column
-  const int SS = lds_stash_stride(N, S);
+  const int SS = lds_stash_stride(N, S);               // fetched prefix of a record
+  const bool save = (p.flags & SVAE_LDS_FLAG_SAVE) != 0;
+  const int RS = lds_record_stride(N, S, save);         // record stride in HBM
   const int NODE = (2 + S) * NP;
 
   // ---- shared memory carve-up (all offsets even => 16-byte aligned) --------------------------
@@ -147,7 +155,7 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
   }
   __syncthreads();
 
-  double* stash = p.stash + (size_t)b * T * SS;
+  double* stash = p.stash + (size_t)b * T * RS;
   const double* nJ = p.node_J + (size_t)b * T * N;
   const double* nh = p.node_h + (size_t)b * T * N;
   const double* eps = p.eps ? p.eps + (size_t)b * T * S * N : nullptr;
@@ -244,7 +252,9 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
     if (mat) {
       const double dc = fma(-2.0, nd[c], Lr[c * NP + c]);
       dprod *= dc;
-      sq[c] = rsqrt(dc);
+      const double rs = rsqrt(dc);
+      sq[c] = rs;
+      if (save) mbuf[c] = dc * rs;   // sqrt(d_c), consumed below (mbuf is free until m_t is published)
     }
     if ((t & 7) == 7 || last) {
       lacc -= 0.5 * log(dprod);
@@ -259,6 +269,15 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
       const double* ep = nd + (2 + s) * NP;
 #pragma unroll
       for (int k = 0; k < N; ++k) r[k] = ep[k] * sq[k];   // D^-1/2 eps
+    }
+    if (save) {
+      // K = L^-1 column c: (L~^-1 e_c)_i / sqrt(d_i) = q_i sqrt(d_i)   (q is D^-1 L~^-1 e_c here)
+      if (mat && valid) {
+        double* kt = stash + (size_t)t * RS + (2 * N + 1 + S) * NP;
+#pragma unroll
+        for (int i = 0; i < N; ++i) kt[i * NP + c] = q[i] * mbuf[i];
+      }
+      __syncwarp();   // mbuf is rewritten with m_t below
     }
     // ---- backward substitution with the unit-upper factor L~' (in place) ----------------------
 #pragma unroll
@@ -290,9 +309,9 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
       for (int i = 0; i < N; ++i) r[i] += mbuf[i];   // b_t = m_t + L^-T eps_t
     }
 
-    if (!last) {
-      // ---- stash record for the backward sweep ----------------------------------------------
-      double* st = stash + (size_t)t * SS;
+    if (!last || save) {
+      // ---- stash record for the backward sweep (and, when saving, for the VJP kernel) ---------
+      double* st = stash + (size_t)t * RS;
       if (valid) {
         if (mat) {
 #pragma unroll
@@ -306,6 +325,8 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
           for (int i = 0; i < N; ++i) st[(2 * N + 1 + s) * NP + i] = r[i];
         }
       }
+    }
+    if (!last) {
       // next step's node slot has landed; its ring slot from two steps ago is free again
       cp_async_wait<0>();
       __syncwarp();
@@ -379,11 +400,11 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
 #if SVAE_LDS_TMA
     if (c == 0) {
       mbar_arrive_expect_tx(&bars[j & 1], (uint32_t)(SS * sizeof(double)));
-      tma_load_1d(ring + (j & 1) * SS, stash + (size_t)t * SS, (uint32_t)(SS * sizeof(double)), &bars[j & 1]);
+      tma_load_1d(ring + (j & 1) * SS, stash + (size_t)t * RS, (uint32_t)(SS * sizeof(double)), &bars[j & 1]);
     }
 #else
     double* dst = ring + (j & 1) * SS;
-    const double* src = stash + (size_t)t * SS;
+    const double* src = stash + (size_t)t * RS;
     for (int e = c; e < SS; e += LPS) dst[e] = src[e];
 #endif
   };
@@ -457,6 +478,11 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
       for (int i = 0; i < N; ++i) xs[s * NP + i] = z[i];
     }
     __syncwarp();
+    if (mat && save && valid) {
+      double* sg = stash + (size_t)t * RS + (3 * N + 1 + S) * NP;
+#pragma unroll
+      for (int i = 0; i < N; ++i) sg[i * NP + c] = z[i];   // Sigma_t[:, c]
+    }
     if (mat) {
       const double mu_c = mu_s[c];
       const size_t bt = (size_t)b * T + t;

@@ -87,8 +87,10 @@ def _canonical_pair_params(pair_params, B, T, n, device):
 # ------------------------------------------------------------------------------------------------
 
 def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=None,
-                      per_t_pair_stats=False, want_stats=True, generator=None, check_status=False):
-    """One launch of the fused filter + smoother + sampler kernel.  Returns a dict of raw tensors."""
+                      per_t_pair_stats=False, want_stats=True, generator=None, check_status=False,
+                      save_for_bwd=False):
+    """One launch of the fused filter + smoother + sampler kernel.  Returns a dict of raw tensors.
+    With save_for_bwd the workspace keeps what lds_estep_backward needs (returned as out["workspace"])."""
     h_any = node_params[1]
     device = h_any.device if torch.is_tensor(h_any) and h_any.is_cuda else torch.device("cuda", torch.cuda.current_device())
     nJ, nh, nlogZ, batched = _canonical_node_params(node_params, device)
@@ -111,7 +113,7 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
         eps = torch.randn((B, T, S, n), dtype=torch.float64, device=device, generator=generator)
 
     L = _lib.lib()
-    flags = _lib.SVAE_LDS_PER_T_PAIR_STATS if per_t_pair_stats else 0
+    flags = (_lib.SVAE_LDS_PER_T_PAIR_STATS if per_t_pair_stats else 0) | (_lib.SVAE_LDS_SAVE_FOR_BWD if save_for_bwd else 0)
     new = lambda *shape: torch.empty(shape, dtype=torch.float64, device=device)
     out = dict(B=B, T=T, n=n, S=S, batched=batched, eps=eps)
     out["lognorm"] = new(B)
@@ -141,12 +143,104 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
         _lib.stream_ptr(device))
     _lib.check(code, "svae_lds_estep_fwd")
     out["status"] = status
+    if save_for_bwd:
+        out["workspace"], out["workspace_bytes"] = work, wbytes
     if check_status:
         bad = int(status.item())
         if bad:
             raise FloatingPointError("LDS E-step: non-positive-definite pivot in sequence %d "
                                      "(reference asserts: svae/lds/gaussian.py:48,64)" % (bad - 1))
     return out
+
+
+def lds_estep_backward(o, g):
+    """VJP w.r.t. (node_J, node_h): one launch of the reverse-mode kernel.
+
+    `o` is the dict lds_estep_forward(..., save_for_bwd=True) returned (its workspace is consumed),
+    `g` maps output names (samples, E_init_xx, E_init_x, E_pair_xx, E_pair_xxn, E_pair_xnxn, Exx_t, Exxn_t,
+    E_node_xx, E_node_x, lognorm) to cotangent tensors (missing / None = zero).
+    Mirrors natural_sample_backward_grad + natural_smoother_general_grad -> natural_filter_grad
+    (cython_lds_inference.pyx:357-409, 236-306, 92-145; wiring lds_inference.py:26-39).
+    """
+    if "workspace" not in o or o["workspace"] is None:
+        raise RuntimeError("lds_estep_backward: forward was not run with save_for_bwd=True (or already consumed)")
+    B, T, n, S = o["B"], o["T"], o["n"], o["S"]
+    dev = o["lognorm"].device
+    gp = lambda k: None if g.get(k) is None else _lib.f64(g[k], dev)
+    keep = {k: gp(k) for k in ("samples", "E_init_xx", "E_init_x", "E_pair_xx", "E_pair_xxn", "E_pair_xnxn",
+                               "Exx_t", "Exxn_t", "E_node_xx", "E_node_x", "lognorm")}
+    gJ = torch.empty((B, T, n), dtype=torch.float64, device=dev)
+    gh = torch.empty((B, T, n), dtype=torch.float64, device=dev)
+    P = _lib.ptr
+    code = _lib.lib().svae_lds_estep_bwd(
+        B, T, n, S, 0,
+        P(o["E_node_x"]), P(o["samples"]), P(o["eps"]),
+        P(keep["samples"]), P(keep["E_init_xx"]), P(keep["E_init_x"]),
+        P(keep["E_pair_xx"]), P(keep["E_pair_xxn"]), P(keep["E_pair_xnxn"]),
+        P(keep["Exx_t"]), P(keep["Exxn_t"]),
+        P(keep["E_node_xx"]), P(keep["E_node_x"]), P(keep["lognorm"]),
+        P(gJ), P(gh),
+        ctypes.c_void_p(o["workspace"].data_ptr()), o["workspace_bytes"], _lib.stream_ptr(dev))
+    _lib.check(code, "svae_lds_estep_bwd")
+    o["workspace"] = None   # single use, like the reference's intermediates
+    return gJ, gh
+
+
+_OUT_HOMOG = ("samples", "lognorm", "E_node_xx", "E_node_x", "E_init_xx", "E_init_x", "E_pair_xx", "E_pair_xxn", "E_pair_xnxn")
+_OUT_PER_T = ("samples", "lognorm", "E_node_xx", "E_node_x", "E_init_xx", "E_init_x", "Exx_t", "Exxn_t")
+
+
+class _LDSEStepFn(torch.autograd.Function):
+    """Differentiable fused E-step: gradients flow to the node potentials only, exactly as the reference
+    defines them (defgrad on argument 2 of the filter, lds_inference.py:27-29)."""
+
+    @staticmethod
+    def forward(ctx, nJ, nh, nlogZ, eps, init_params, pair_params, S, per_t):
+        node = (nJ, nh) if nlogZ is None else (nJ, nh, nlogZ)
+        o = lds_estep_forward(init_params, pair_params, node, S, eps, per_t_pair_stats=per_t, save_for_bwd=True)
+        ctx.o, ctx.names, ctx.has_logZ = o, (_OUT_PER_T if per_t else _OUT_HOMOG), nlogZ is not None
+        ctx.set_materialize_grads(False)
+        outs = tuple(o[k] for k in ctx.names)
+        if o["samples"] is None:
+            outs = (torch.empty(0, device=nh.device, dtype=torch.float64),) + outs[1:]
+        return outs
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gs):
+        g = dict(zip(ctx.names, gs))
+        if ctx.o["samples"] is None:
+            g["samples"] = None
+        gJ, gh = lds_estep_backward(ctx.o, g)
+        g_logZ = None
+        if ctx.has_logZ and g.get("lognorm") is not None:
+            g_logZ = g["lognorm"][:, None].expand(ctx.o["B"], ctx.o["T"]).contiguous()
+        return gJ, gh, g_logZ, None, None, None, None, None
+
+
+def _estep(init_params, pair_params, node_params, S, eps, per_t, generator=None):
+    """Dispatch: plain launch when nothing requires grad, autograd Function otherwise."""
+    needs_grad = torch.is_grad_enabled() and any(torch.is_tensor(x) and x.requires_grad for x in node_params)
+    if not needs_grad:
+        return lds_estep_forward(init_params, pair_params, node_params, S, eps, per_t_pair_stats=per_t,
+                                 generator=generator)
+    h_any = node_params[1]
+    device = h_any.device
+    nJ, nh, nlogZ, batched = _canonical_node_params(node_params, device)
+    S = int(S) if S else 0
+    B, T, n = nh.shape
+    if eps is None and S > 0:
+        eps = torch.randn((B, T, S, n), dtype=torch.float64, device=device, generator=generator)
+    elif eps is not None:
+        eps = _lib.f64(eps, device)
+        eps = eps[None] if (not batched and eps.dim() == 3) else eps
+    outs = _LDSEStepFn.apply(nJ, nh, nlogZ, eps, init_params, pair_params, S, per_t)
+    names = _OUT_PER_T if per_t else _OUT_HOMOG
+    o = dict(zip(names, outs))
+    o.update(B=B, T=T, n=n, S=S, batched=batched, eps=eps)
+    if S == 0:
+        o["samples"] = None
+    return o
 
 
 def _pack_stats(o, homog):
@@ -189,8 +283,7 @@ def natural_lds_inference_general(natparam, node_params, num_samples=1, eps=None
     """
     init_params, pair_params = natparam
     homog = _is_homog(pair_params)
-    o = lds_estep_forward(init_params, pair_params, node_params, num_samples, eps,
-                          per_t_pair_stats=not homog, generator=generator)
+    o = _estep(init_params, pair_params, node_params, num_samples, eps, not homog, generator)
     return _pack_stats(o, homog)
 
 
@@ -201,7 +294,7 @@ def natural_lds_estep_general(natparam, node_params):
     """(lognorm, expected_stats) -- lds_inference.py:223-237."""
     init_params, pair_params = natparam
     homog = _is_homog(pair_params)
-    o = lds_estep_forward(init_params, pair_params, node_params, 0, None, per_t_pair_stats=not homog)
+    o = _estep(init_params, pair_params, node_params, 0, None, not homog)
     _, stats, lognorm = _pack_stats(o, homog)
     return lognorm, stats
 

@@ -42,7 +42,7 @@ extern "C" {
 #define SVAE_ERR_CUDA (-4)          /* launch failed (cudaGetLastError != cudaSuccess)            */
 
 #define SVAE_LDS_MAX_N 16           /* latent dimension range compiled into the library: 1..16    */
-#define SVAE_HMM_MAX_K 64           /* discrete states: 1..64                                      */
+#define SVAE_HMM_MAX_K 32           /* discrete states: 1..32 (lane = state)                       */
 
 /* flags for svae_lds_estep_fwd */
 #define SVAE_LDS_PER_T_PAIR_STATS 1 /* also write per-time second moments (inhomogeneous E_pair)   */
@@ -123,6 +123,28 @@ int svae_lds_estep_bwd(
     const double* g_E_node_xx, const double* g_E_node_x, const double* g_lognorm,
     double* g_node_J, double* g_node_h,
     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * HMM local E-step for B sequences: log-normaliser and expected statistics by scaled forward-backward.
+ * Replaces hmm_logZ / hmm_logZ_grad (svae/hmm/cython_hmm_inference.pyx:93-166; with cotangent 1 the
+ * gradient IS the E-step, svae/hmm/hmm_inference.py:65) and hmm_estep (hmm_inference.py:21-41, pyhsmm).
+ *   log_pi (K), log_A (K,K) row = from-state  (unnormalised log values allowed), shared by the batch
+ *   node (B,T,K) log node potentials
+ * outputs: logZ (B); Ez0 (B,K) = E[z_0]; Etrans (B,K,K) expected transition counts; Ez (B,T,K) = E[z_t].
+ * With SVAE_HMM_LOGZ_ONLY only logZ is written (Ez0, Etrans, Ez may be NULL); otherwise Ez is required
+ * (it doubles as the scratch for the scaled forward messages).  The VJP of logZ w.r.t. (log_pi, log_A,
+ * node) is cotangent x (Ez0, Etrans, Ez) -- exactly hmm_logZ_grad (pyx:126-166).
+ */
+#define SVAE_HMM_LOGZ_ONLY 1
+int svae_hmm_estep(int B, int T, int K, int flags, const double* log_pi, const double* log_A,
+                   const double* node, double* logZ, double* Ez0, double* Etrans, double* Ez,
+                   void* stream);
+
+/* Viterbi path (svae/hmm/hmm_inference.py:54-63, pyhsmm `viterbi`): path (B,T) int32, first maximal
+ * index on ties.  workspace: svae_hmm_viterbi_workspace_bytes() bytes of device scratch (back-pointers). */
+size_t svae_hmm_viterbi_workspace_bytes(int B, int T, int K);
+int svae_hmm_viterbi(int B, int T, int K, const double* log_pi, const double* log_A, const double* node,
+                     int32_t* path, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

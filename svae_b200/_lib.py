@@ -14,6 +14,8 @@ LIB_PATH = os.environ.get("SVAE_B200_LIB") or os.path.join(_HERE, "libsvae_b200.
 SVAE_LDS_MAX_N = 16
 SVAE_LDS_PER_T_PAIR_STATS = 1
 SVAE_LDS_SAVE_FOR_BWD = 2
+SVAE_HMM_MAX_K = 32
+SVAE_HMM_LOGZ_ONLY = 1
 
 _ERR = {-1: "SVAE_ERR_BAD_ARG", -2: "SVAE_ERR_UNSUPPORTED", -3: "SVAE_ERR_WORKSPACE", -4: "SVAE_ERR_CUDA"}
 
@@ -30,6 +32,9 @@ _SIGNATURES = {
     "svae_lds_estep_workspace_bytes": (_SZ, [_I] * 5),
     "svae_lds_estep_fwd": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 15 + [_P, _P, _SZ, _P]),
     "svae_lds_estep_bwd": (_I, [_I] * 5 + [_P] * 16 + [_P, _SZ, _P]),
+    "svae_hmm_estep": (_I, [_I] * 4 + [_P] * 7 + [_P]),
+    "svae_hmm_viterbi_workspace_bytes": (_SZ, [_I] * 3),
+    "svae_hmm_viterbi": (_I, [_I] * 3 + [_P] * 4 + [_P, _SZ, _P]),
 }
 
 

@@ -3,10 +3,10 @@
 #include "svae_b200.h"
 #include "launch.h"
 
-static std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_svae_launches{0};
 
 extern "C" const char* svae_b200_version(void) { return "svae_b200 0.1 sm_100a"; }
-extern "C" uint64_t svae_b200_launch_count(void) { return g_launches.load(); }
+extern "C" uint64_t svae_b200_launch_count(void) { return g_svae_launches.load(); }
 
 namespace {
 typedef cudaError_t (*lds_fwd_fn)(const svae::LdsFwdParams&, int, bool, cudaStream_t);
@@ -77,7 +77,7 @@ extern "C" int svae_lds_estep_fwd(
   p.stash = static_cast<double*>(workspace);
   const bool inhomog = (pair_stride_t != 0 || pair_stride_b != 0) && T > 1;
   cudaError_t e = kLdsFwd[n](p, lps, inhomog, static_cast<cudaStream_t>(stream));
-  g_launches.fetch_add(1);
+  g_svae_launches.fetch_add(1);
   return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
 }
 
@@ -109,6 +109,6 @@ extern "C" int svae_lds_estep_bwd(
   p.g_node_J = g_node_J; p.g_node_h = g_node_h;
   p.stash = static_cast<double*>(workspace);
   cudaError_t e = kLdsBwd[n](p, lps, static_cast<cudaStream_t>(stream));
-  g_launches.fetch_add(1);
+  g_svae_launches.fetch_add(1);
   return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
 }

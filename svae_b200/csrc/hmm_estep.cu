@@ -1,0 +1,301 @@
+// hmm_estep.cu -- batched HMM local E-step (forward-backward), log-normaliser and Viterbi for sm_100a.
+//
+// What it replaces (reference, one sequence per call):
+//   svae/hmm/cython_hmm_inference.pyx:93-121   hmm_logZ       (log-space forward, T K^2 exp)
+//   svae/hmm/cython_hmm_inference.pyx:126-166  hmm_logZ_grad  (reverse sweep; with g = 1 the E-step)
+//   svae/hmm/cython_hmm_inference.pyx:59-88    hmm_logZ_normalized (the scaled-forward formulation)
+//   svae/hmm/hmm_inference.py:21-41,54-63      hmm_estep / hmm_viterbi (pyhsmm log messages + Viterbi)
+//
+// B200 design: one sub-warp tile of LPS = 2^k >= K lanes per sequence, lane j = state j (32/LPS sequences
+// per warp).  SCALED forward-backward (T K exps instead of T K^2, hmm_logZ_normalized's formulation):
+//   forward : alpha_t  ~ (alpha_{t-1}' P) .* exp(node_t - max_t),  P = exp(log A - max log A) held as one
+//             COLUMN per lane in registers, alpha broadcast through shared memory; logZ accumulates log c_t;
+//             alpha_t is parked in the E[z_t] output buffer (no extra workspace);
+//   backward: beta~_t ~ P (exp(node_{t+1} - max) .* beta~_{t+1}),  P held as one ROW per lane;
+//             E[z_t] = alpha_t beta~_t / s_t,  s_t = <alpha_t, beta~_t>;
+//             E[#i->j] = P[i][j] * sum_t alpha_t[i] w_{t+1}[j] / s_t  accumulated as one column per lane.
+// Node potentials stream once forward and once backward with a one-step register prefetch.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <atomic>
+#include "svae_b200.h"
+
+namespace svae {
+
+struct HmmParams {
+  int B, T, K, flags;
+  const double *log_pi, *log_A, *node;   // (K), (K,K) row = from, (B,T,K)
+  double *logZ, *Ez0, *Etrans, *Ez;      // (B), (B,K), (B,K,K), (B,T,K)
+};
+
+template <int LPS>
+__device__ __forceinline__ double tile_sum(double v) {
+#pragma unroll
+  for (int o = LPS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, LPS);
+  return v;
+}
+template <int LPS>
+__device__ __forceinline__ float tile_maxf(float v) {
+#pragma unroll
+  for (int o = LPS / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o, LPS));
+  return v;
+}
+
+// flags: bit0 = forward only (logZ), else full E-step
+template <int LPS>
+__global__ void __launch_bounds__(32) hmm_estep_kernel(const HmmParams p) {
+  constexpr int SPW = 32 / LPS;
+  constexpr int LP = (LPS + 1) & ~1;
+  __shared__ __align__(16) double sbuf[SPW][2][LP < 2 ? 2 : LP];
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPS, j = lane % LPS;
+  const int K = p.K, T = p.T;
+  const long long seq = (long long)blockIdx.x * SPW + sub;
+  const bool valid = seq < p.B;
+  const long long b = valid ? seq : (long long)p.B - 1;
+  const bool act = j < K;
+  double* abuf = sbuf[sub][0];
+  double* wbuf = sbuf[sub][1];
+  const bool fwd_only = (p.flags & 1) != 0;
+
+  // global shift of log A so that P = exp(log A - gmax) <= 1
+  float gmf = -INFINITY;
+  for (int e = j; e < K * K; e += LPS) gmf = fmaxf(gmf, (float)p.log_A[e]);
+  const double gmax = (double)tile_maxf<LPS>(gmf);
+
+  double Pc[LPS];   // column j of P (forward):  Pc[i] = P[i][j]
+#pragma unroll
+  for (int i = 0; i < LPS; ++i) Pc[i] = (act && i < K) ? exp(p.log_A[i * K + j] - gmax) : 0.0;
+
+  const double* node = p.node + (size_t)b * T * K;
+  double* Ez = p.Ez + (size_t)b * T * K;
+  const double NEG = -1.0e300;
+
+  // ------------------------------------ forward ---------------------------------------------
+  double x = act ? node[j] : NEG;
+  double xn = (act && T > 1) ? node[K + j] : NEG;
+  double a0 = act ? p.log_pi[j] + x : NEG;
+  float mf = tile_maxf<LPS>((float)a0);
+  double e = act ? exp(a0 - (double)mf) : 0.0;
+  double c = tile_sum<LPS>(e);
+  double alpha = e / c;
+  double logZ = (double)mf;
+  double cprod = c;
+  if (act && valid && !fwd_only) Ez[j] = alpha;
+  for (int t = 1; t < T; ++t) {
+    x = xn;
+    if (t + 1 < T) xn = act ? node[(size_t)(t + 1) * K + j] : NEG;
+    abuf[j] = alpha;
+    __syncwarp();
+    double pj = 0.0;
+#pragma unroll
+    for (int i2 = 0; i2 < LPS / 2; ++i2) {
+      const double2 a2 = *reinterpret_cast<const double2*>(&abuf[2 * i2]);
+      pj = fma(a2.x, Pc[2 * i2], pj);
+      pj = fma(a2.y, Pc[2 * i2 + 1], pj);
+    }
+    if (LPS == 1) pj = abuf[0] * Pc[0];
+    mf = tile_maxf<LPS>((float)x);
+    e = act ? pj * exp(x - (double)mf) : 0.0;
+    c = tile_sum<LPS>(e);
+    alpha = e / c;
+    logZ += (double)mf;
+    cprod *= c;
+    if ((t & 7) == 7) {
+      logZ += log(cprod);
+      cprod = 1.0;
+    }
+    if (act && valid && !fwd_only) Ez[(size_t)t * K + j] = alpha;
+    __syncwarp();
+  }
+  logZ += log(cprod) + (double)(T - 1) * gmax;
+  if (j == 0 && valid && p.logZ) p.logZ[b] = logZ;
+  if (fwd_only) return;
+
+  // ------------------------------------ backward --------------------------------------------
+  double Pr[LPS];   // row j of P:  Pr[i] = P[j][i]
+#pragma unroll
+  for (int i = 0; i < LPS; ++i) Pr[i] = (act && i < K) ? exp(p.log_A[j * K + i] - gmax) : 0.0;
+  double O[LPS];    // column j of sum_t alpha_t (x) w_{t+1} / s_t
+#pragma unroll
+  for (int i = 0; i < LPS; ++i) O[i] = 0.0;
+  double beta = act ? 1.0 : 0.0;
+  // x currently holds node[T-1]; alpha holds alpha_{T-1} (= E[z_{T-1}], already stored)
+  double xc = x;
+  double an = (act && T > 1) ? 0.0 : 0.0;
+  if (T > 1) an = act ? Ez[(size_t)(T - 2) * K + j] : 0.0;   // visible: same thread wrote it
+  for (int t = T - 2; t >= 0; --t) {
+    // w = exp(node_{t+1} - max) * beta_{t+1}
+    mf = tile_maxf<LPS>((float)xc);
+    const double w = act ? exp(xc - (double)mf) * beta : 0.0;
+    wbuf[j] = w;
+    const double at = an;
+    // prefetch for the next iteration
+    xc = act ? node[(size_t)t * K + j] : NEG;
+    if (t > 0) an = act ? Ez[(size_t)(t - 1) * K + j] : 0.0;
+    __syncwarp();
+    double bu = 0.0;
+#pragma unroll
+    for (int i2 = 0; i2 < LPS / 2; ++i2) {
+      const double2 w2 = *reinterpret_cast<const double2*>(&wbuf[2 * i2]);
+      bu = fma(w2.x, Pr[2 * i2], bu);
+      bu = fma(w2.y, Pr[2 * i2 + 1], bu);
+    }
+    if (LPS == 1) bu = wbuf[0] * Pr[0];
+    const double s = tile_sum<LPS>(at * bu);
+    const double invs = 1.0 / s;
+    if (act && valid) Ez[(size_t)t * K + j] = at * bu * invs;
+    abuf[j] = at * invs;
+    __syncwarp();
+#pragma unroll
+    for (int i2 = 0; i2 < LPS / 2; ++i2) {
+      const double2 a2 = *reinterpret_cast<const double2*>(&abuf[2 * i2]);
+      O[2 * i2] = fma(a2.x, w, O[2 * i2]);
+      O[2 * i2 + 1] = fma(a2.y, w, O[2 * i2 + 1]);
+    }
+    if (LPS == 1) O[0] = fma(abuf[0], w, O[0]);
+    beta = bu * invs;
+    __syncwarp();
+  }
+  if (act && valid) {
+    if (p.Ez0) p.Ez0[(size_t)b * K + j] = Ez[j];
+    if (p.Etrans) {
+#pragma unroll
+      for (int i = 0; i < LPS; ++i)
+        if (i < K) p.Etrans[(size_t)b * K * K + i * K + j] = exp(p.log_A[i * K + j] - gmax) * O[i];
+    }
+  }
+}
+
+// Viterbi: max-product forward with byte back-pointers in the workspace, then a serial back-track.
+struct ViterbiParams {
+  int B, T, K;
+  const double *log_pi, *log_A, *node;
+  int32_t* path;           // (B,T)
+  uint8_t* back;           // workspace (B,T,K)
+};
+
+template <int LPS>
+__global__ void __launch_bounds__(32) hmm_viterbi_kernel(const ViterbiParams p) {
+  constexpr int SPW = 32 / LPS;
+  constexpr int LP = (LPS + 1) & ~1;
+  __shared__ __align__(16) double sbuf[SPW][LP < 2 ? 2 : LP];
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPS, j = lane % LPS;
+  const int K = p.K, T = p.T;
+  const long long seq = (long long)blockIdx.x * SPW + sub;
+  const bool valid = seq < p.B;
+  const long long b = valid ? seq : (long long)p.B - 1;
+  const bool act = j < K;
+  double* dbuf = sbuf[sub];
+  const double NEG = -1.0e300;
+  double Ac[LPS];   // column j of log A
+#pragma unroll
+  for (int i = 0; i < LPS; ++i) Ac[i] = (act && i < K) ? p.log_A[i * K + j] : NEG;
+  const double* node = p.node + (size_t)b * T * K;
+  uint8_t* back = p.back + (size_t)b * T * K;
+  double delta = act ? p.log_pi[j] + node[j] : NEG;
+  for (int t = 1; t < T; ++t) {
+    dbuf[j] = delta;
+    __syncwarp();
+    double best = NEG * 2.0;
+    int arg = 0;
+#pragma unroll
+    for (int i = 0; i < LPS; ++i) {
+      const double v = dbuf[i] + Ac[i];
+      if (v > best) { best = v; arg = i; }      // strict '>' keeps the FIRST maximal index
+    }
+    delta = act ? best + node[(size_t)t * K + j] : NEG;
+    if (act && valid) back[(size_t)t * K + j] = (uint8_t)arg;
+    __syncwarp();
+  }
+  // argmax over the tile (first max): reduce (value, index) pairs
+  double bv = delta;
+  int bi = j;
+#pragma unroll
+  for (int o = LPS / 2; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o, LPS);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o, LPS);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  __syncwarp();
+  __threadfence_block();
+  if (j == 0 && valid) {
+    int32_t* path = p.path + (size_t)b * T;
+    int z = bi;
+    path[T - 1] = z;
+    for (int t = T - 2; t >= 0; --t) {
+      z = back[(size_t)(t + 1) * K + z];
+      path[t] = z;
+    }
+  }
+}
+
+template <int LPS>
+static cudaError_t launch_hmm(const HmmParams& p, cudaStream_t s) {
+  constexpr int SPW = 32 / LPS;
+  hmm_estep_kernel<LPS><<<(unsigned)((p.B + SPW - 1) / SPW), 32, 0, s>>>(p);
+  return cudaGetLastError();
+}
+template <int LPS>
+static cudaError_t launch_vit(const ViterbiParams& p, cudaStream_t s) {
+  constexpr int SPW = 32 / LPS;
+  hmm_viterbi_kernel<LPS><<<(unsigned)((p.B + SPW - 1) / SPW), 32, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t hmm_estep_launch(const HmmParams& p, cudaStream_t s) {
+  if (p.K <= 2) return launch_hmm<2>(p, s);
+  if (p.K <= 4) return launch_hmm<4>(p, s);
+  if (p.K <= 8) return launch_hmm<8>(p, s);
+  if (p.K <= 16) return launch_hmm<16>(p, s);
+  return launch_hmm<32>(p, s);
+}
+cudaError_t hmm_viterbi_launch(const ViterbiParams& p, cudaStream_t s) {
+  if (p.K <= 2) return launch_vit<2>(p, s);
+  if (p.K <= 4) return launch_vit<4>(p, s);
+  if (p.K <= 8) return launch_vit<8>(p, s);
+  if (p.K <= 16) return launch_vit<16>(p, s);
+  return launch_vit<32>(p, s);
+}
+
+}  // namespace svae
+
+extern std::atomic<uint64_t> g_svae_launches;
+
+extern "C" int svae_hmm_estep(int B, int T, int K, int flags, const double* log_pi, const double* log_A,
+                              const double* node, double* logZ, double* Ez0, double* Etrans, double* Ez,
+                              void* stream) {
+  if (B <= 0 || T <= 0 || K <= 0) return SVAE_ERR_BAD_ARG;
+  if (!log_pi || !log_A || !node) return SVAE_ERR_BAD_ARG;
+  const bool fwd_only = (flags & SVAE_HMM_LOGZ_ONLY) != 0;
+  if (!fwd_only && !Ez) return SVAE_ERR_BAD_ARG;
+  if (K > SVAE_HMM_MAX_K) return SVAE_ERR_UNSUPPORTED;
+  svae::HmmParams p;
+  p.B = B; p.T = T; p.K = K; p.flags = fwd_only ? 1 : 0;
+  p.log_pi = log_pi; p.log_A = log_A; p.node = node;
+  p.logZ = logZ; p.Ez0 = Ez0; p.Etrans = Etrans; p.Ez = Ez;
+  cudaError_t e = svae::hmm_estep_launch(p, static_cast<cudaStream_t>(stream));
+  g_svae_launches.fetch_add(1);
+  return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
+}
+
+extern "C" size_t svae_hmm_viterbi_workspace_bytes(int B, int T, int K) {
+  if (B <= 0 || T <= 0 || K <= 0) return 0;
+  return (size_t)B * (size_t)T * (size_t)K;
+}
+
+extern "C" int svae_hmm_viterbi(int B, int T, int K, const double* log_pi, const double* log_A, const double* node,
+                                int32_t* path, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || T <= 0 || K <= 0) return SVAE_ERR_BAD_ARG;
+  if (!log_pi || !log_A || !node || !path || !workspace) return SVAE_ERR_BAD_ARG;
+  if (K > SVAE_HMM_MAX_K) return SVAE_ERR_UNSUPPORTED;
+  if (workspace_bytes < svae_hmm_viterbi_workspace_bytes(B, T, K)) return SVAE_ERR_WORKSPACE;
+  svae::ViterbiParams p;
+  p.B = B; p.T = T; p.K = K; p.log_pi = log_pi; p.log_A = log_A; p.node = node;
+  p.path = path; p.back = static_cast<uint8_t*>(workspace);
+  cudaError_t e = svae::hmm_viterbi_launch(p, static_cast<cudaStream_t>(stream));
+  g_svae_launches.fetch_add(1);
+  return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
+}

@@ -1,0 +1,66 @@
+"""GPU: HMM forward-backward / logZ / Viterbi kernels against the golden vectors of the reference's compiled
+cython_hmm_inference and against the NumPy oracle.  Moments to 1e-9 relative, Viterbi paths EXACT."""
+import numpy as np
+import pytest
+import torch
+from oracle import hmm_numpy as H
+from util import golden_cases, load, rel_err
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+_g = lambda x, grad=False: torch.as_tensor(np.asarray(x), dtype=torch.float64, device="cuda").requires_grad_(grad)
+
+
+@pytest.mark.parametrize("path", golden_cases("hmm_"))
+def test_hmm_golden(path):
+    from svae_b200.hmm import hmm_inference as K
+    d = load(path)
+    nat = (_g(d["log_pi"]), _g(d["log_A"]), _g(d["node"]))
+    logZ, (Ez0, Etrans, Ez) = K.hmm_estep(nat)
+    assert rel_err(logZ.cpu().numpy(), d["logZ"]) < RTOL
+    assert rel_err(Ez.cpu().numpy(), d["Ez"]) < RTOL and rel_err(Ez0.cpu().numpy(), d["Ez0"]) < RTOL
+    if d["node"].shape[1] > 1:
+        assert rel_err(Etrans.cpu().numpy(), d["Etrans"]) < RTOL
+    assert np.array_equal(K.hmm_viterbi(nat).cpu().numpy(), d["viterbi"])
+    assert rel_err(K.hmm_logZ(nat).cpu().numpy(), d["logZ"]) < RTOL
+
+
+@pytest.mark.parametrize("K_,T,B", [(32, 500, 64), (8, 200, 37), (1, 4, 3), (2, 1, 5), (17, 33, 9), (5, 7, 1)])
+def test_hmm_vs_oracle(K_, T, B):
+    from svae_b200.hmm import hmm_inference as K
+    rng = np.random.default_rng(K_ * 1000 + T)
+    lp, lA = H.rand_hmm_natparam(K_, rng)
+    node = 3.0 * rng.standard_normal((B, T, K_))
+    w_logZ, (wE0, wEt, wEz) = H.hmm_estep((lp, lA, node))
+    nat = (_g(lp), _g(lA), _g(node))
+    logZ, (Ez0, Etrans, Ez) = K.hmm_estep(nat)
+    assert rel_err(logZ.cpu().numpy(), w_logZ) < RTOL
+    assert rel_err(Ez.cpu().numpy(), wEz) < RTOL and rel_err(Ez0.cpu().numpy(), wE0) < RTOL
+    if T > 1:
+        assert rel_err(Etrans.cpu().numpy(), wEt) < RTOL
+    assert np.array_equal(K.hmm_viterbi(nat).cpu().numpy(), H.hmm_viterbi((lp, lA, node)))
+
+
+def test_hmm_logZ_vjp_is_the_estep():
+    from svae_b200.hmm import hmm_inference as K
+    rng = np.random.default_rng(3)
+    K_, T, B = 6, 12, 4
+    lp, lA = H.rand_hmm_natparam(K_, rng)
+    node = rng.standard_normal((B, T, K_))
+    g = rng.standard_normal(B)
+    a, b_, c = _g(lp, True), _g(lA, True), _g(node, True)
+    (K.hmm_logZ((a, b_, c)) * _g(g)).sum().backward()
+    _, (E0, Et, Ez) = H.hmm_estep((lp, lA, node))
+    assert rel_err(a.grad.cpu().numpy(), (g[:, None] * E0).sum(0)) < RTOL
+    assert rel_err(b_.grad.cpu().numpy(), (g[:, None, None] * Et).sum(0)) < RTOL
+    assert rel_err(c.grad.cpu().numpy(), g[:, None, None] * Ez) < RTOL
+
+
+def test_hmm_unbatched_like_reference():
+    from svae_b200.hmm import hmm_inference as K
+    rng = np.random.default_rng(4)
+    lp, lA = H.rand_hmm_natparam(4, rng)
+    node = rng.standard_normal((9, 4))
+    logZ, (E0, Et, Ez) = K.hmm_estep((_g(lp), _g(lA), _g(node)))
+    assert logZ.dim() == 0 and E0.shape == (4,) and Et.shape == (4, 4) and Ez.shape == (9, 4)
+    assert K.hmm_viterbi((_g(lp), _g(lA), _g(node))).shape == (9,)

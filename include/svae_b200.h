@@ -47,6 +47,7 @@ extern "C" {
 /* flags for svae_lds_estep_fwd */
 #define SVAE_LDS_PER_T_PAIR_STATS 1 /* also write per-time second moments (inhomogeneous E_pair)   */
 #define SVAE_LDS_SAVE_FOR_BWD 2     /* keep what svae_lds_estep_bwd needs in the workspace         */
+#define SVAE_LDS_INIT_PER_SEQ 4     /* init_J (B,n,n), init_h (B,n), init_logZ (B): one per sequence */
 
 /* Library version / build info: "svae_b200 <version> sm_100a". */
 const char* svae_b200_version(void);
@@ -60,7 +61,8 @@ uint64_t svae_b200_launch_count(void);
  * composition natural_filter_forward_general -> natural_smoother_general -> natural_sample_backward,
  * for B sequences at once.
  *
- *   init_J (n,n), init_h (n), init_logZ (1) or NULL          shared by the batch
+ *   init_J (n,n), init_h (n), init_logZ (1) or NULL          shared by the batch (per sequence with
+ *       SVAE_LDS_INIT_PER_SEQ: the SLDS initial-state mixture, svae/models/slds_svae.py:92-103)
  *   J11, J12, J22 (n,n), pair_logZ (1) or NULL               homogeneous dynamics, shared; or, with
  *       pair_stride_t != 0: (T-1,n,n)/(T-1) time-inhomogeneous, element (t) at ptr + t*pair_stride_t
  *       (for pair_logZ the strides are divided by n*n); pair_stride_b != 0 adds a per-sequence stride

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("SVAE_B200_LIB") or os.path.join(_HERE, "libsvae_b200.
 SVAE_LDS_MAX_N = 16
 SVAE_LDS_PER_T_PAIR_STATS = 1
 SVAE_LDS_SAVE_FOR_BWD = 2
+SVAE_LDS_INIT_PER_SEQ = 4
 SVAE_HMM_MAX_K = 32
 SVAE_HMM_LOGZ_ONLY = 1
 

@@ -66,6 +66,7 @@ __host__ __device__ inline int lds_record_stride(int N, int S, bool save) {
   return (save ? 4 * N + 1 + S : 2 * N + 1 + S) * lds_np(N);
 }
 #define SVAE_LDS_FLAG_SAVE 2
+#define SVAE_LDS_FLAG_INIT_PER_SEQ 4
 
 // shared-memory doubles per sequence tile.  The filter sweep (LDL' factors, node ring, per-tile pair
 // parameters) and the backward sweep (stash ring, C) never overlap in time, so they share storage.
@@ -183,13 +184,16 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
   // a: mat lanes -- column c of M_t = J_pred + J11 (the node precision is added at the pivot);
   //    vec lane  -- h_filtered = h_pred + h_node.   Information form.
   double a[N];
+  const bool init_per_seq = (p.flags & SVAE_LDS_FLAG_INIT_PER_SEQ) != 0;
+  const double* iJ = p.init_J + (init_per_seq ? (size_t)b * NN : 0);
+  const double* ih = p.init_h + (init_per_seq ? (size_t)b * N : 0);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     if (mat) {
-      a[i] = -2.0 * p.init_J[i * N + c];
+      a[i] = -2.0 * iJ[i * N + c];
       if (!INHOMOG && T > 1) a[i] -= 2.0 * p.J11[i * N + c];
     } else {
-      a[i] = vec ? p.init_h[i] + nring[NP + i] : 0.0;
+      a[i] = vec ? ih[i] + nring[NP + i] : 0.0;
     }
   }
 
@@ -375,7 +379,7 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
 #pragma unroll
     for (int o = LPS / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o, LPS);
     if (c == 0 && valid && p.lognorm) {
-      double konst = p.init_logZ ? p.init_logZ[0] : 0.0;
+      double konst = p.init_logZ ? p.init_logZ[init_per_seq ? b : 0] : 0.0;
       if (p.pair_logZ) {
         if (!INHOMOG) {
           konst += (double)(T - 1) * p.pair_logZ[0];

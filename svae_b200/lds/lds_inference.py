@@ -27,9 +27,9 @@ def _canonical_init_params(init_params, device):
     h = _lib.f64(init_params[1], device)
     logZ = None
     for term in init_params[2:]:
-        term = _lib.f64(term, device).reshape(())
+        term = _lib.f64(term, device)
         logZ = term if logZ is None else logZ + term
-    return J, h, (None if logZ is None else logZ.reshape(1).contiguous())
+    return J, h, (None if logZ is None else logZ.reshape(-1).contiguous())
 
 
 def _canonical_node_params(node_params, device):
@@ -98,7 +98,11 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
     if n > _lib.SVAE_LDS_MAX_N:
         raise ValueError("latent dimension %d > %d" % (n, _lib.SVAE_LDS_MAX_N))
     iJ, ih, ilogZ = _canonical_init_params(init_params, device)
-    if iJ.shape != (n, n) or ih.shape != (n,):
+    init_per_seq = iJ.dim() == 3
+    if init_per_seq:
+        if iJ.shape != (B, n, n) or ih.shape != (B, n) or (ilogZ is not None and ilogZ.numel() != B):
+            raise ValueError("per-sequence init_params shapes")
+    elif iJ.shape != (n, n) or ih.shape != (n,):
         raise ValueError("init_params shapes")
     J11, J12, J22, plogZ, st, sb = _canonical_pair_params(pair_params, B, T, n, device)
     S = int(num_samples) if num_samples else 0
@@ -113,7 +117,8 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
         eps = torch.randn((B, T, S, n), dtype=torch.float64, device=device, generator=generator)
 
     L = _lib.lib()
-    flags = (_lib.SVAE_LDS_PER_T_PAIR_STATS if per_t_pair_stats else 0) | (_lib.SVAE_LDS_SAVE_FOR_BWD if save_for_bwd else 0)
+    flags = (_lib.SVAE_LDS_PER_T_PAIR_STATS if per_t_pair_stats else 0) | (_lib.SVAE_LDS_SAVE_FOR_BWD if save_for_bwd else 0) \
+        | (_lib.SVAE_LDS_INIT_PER_SEQ if init_per_seq else 0)
     new = lambda *shape: torch.empty(shape, dtype=torch.float64, device=device)
     out = dict(B=B, T=T, n=n, S=S, batched=batched, eps=eps)
     out["lognorm"] = new(B)

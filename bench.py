@@ -83,7 +83,7 @@ def cpu_reference_rate(n, T, S, target_seconds=4.0, cores=None):
     """sequences/s of the reference CPU path using all host cores (one sequence stream per process)."""
     import multiprocessing as mp
     from oracle import ref
-    cores = cores or os.cpu_count() or 1
+    cores = cores or (len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()) or 1
     kind = "reference" if ref.available() else "port"
     worker = _cpu_worker if kind == "reference" else _cpu_port_worker
     ctx = mp.get_context("spawn")
@@ -107,42 +107,42 @@ def cpu_reference_rate(n, T, S, target_seconds=4.0, cores=None):
 # --------------------------------------------------------------------------------------------------
 
 class ClockSampler:
+    """Samples SM clocks / throttle reasons with one `nvidia-smi -lms` process while the GPU is under load."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.samples, self._stop = index, [], threading.Event()
-        self.th = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        self.index, self.proc, self.lines = index, None, []
 
     def __enter__(self):
-        self.th.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self.th.join(timeout=6)
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            self.lines = [l for l in out.splitlines() if l.strip()]
 
     def summary(self):
-        if not self.samples:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        rows = [[x.strip() for x in l.split(",")] for l in self.lines]
+        rows = [r for r in rows if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        sm = sorted(int(r[0]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for k, nm in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=reasons, samples=len(self.samples))
+        reasons = [nm for k, nm in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in rows)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(int(r[1]) for r in rows if r[1].isdigit()),
+                    reasons=reasons, samples=len(rows))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -203,15 +203,16 @@ def run_ours(args):
         eps = torch.randn(B, T, S, n, dtype=torch.float64, device=dev, generator=gen)
         sets.append((nJ, nh, eps))
 
-    def step(i):
+    def step(i, kev=None):
         nJ, nh, eps = sets[i % NSETS]
+        if kev is not None:
+            kev[0].record()
         o = K.lds_estep_forward(gi, gp, (nJ, nh), S, eps)
-        # global expected-statistic accumulator: sum over the minibatch, one all-reduce per SVI step
-        acc = torch.cat([o["E_init_xx"].sum(0).reshape(-1), o["E_init_x"].sum(0), o["E_pair_xx"].sum(0).reshape(-1),
-                         o["E_pair_xxn"].sum(0).reshape(-1), o["E_pair_xnxn"].sum(0).reshape(-1),
-                         o["lognorm"].sum().reshape(1)])
+        if kev is not None:
+            kev[1].record()
+        acc = K.lds_reduce_global_stats(o)      # sum_b [E_init | E_pair | lognorm]
         if world > 1:
-            dist.all_reduce(acc)
+            dist.all_reduce(acc)                # the single collective of an SVI step
         return o, acc
 
     def barrier():
@@ -219,25 +220,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
-    # ---- device-timed region: exactly K steps -----------------------------------------------------
-    l0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local) as clk:
+        # warm-up: at least W (>= 3) steps and at least ~1 s so the clock sampler sees the GPU under load
+        t0 = time.perf_counter()
+        i = 0
+        while i < max(args.warmup, 3) or time.perf_counter() - t0 < 1.0:
+            step(i); i += 1
+            if i % 16 == 0:
+                torch.cuda.synchronize()
+        barrier()
+        # ---- device-timed region: exactly K steps -------------------------------------------------
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         e0.record()
         for i in range(args.steps):
-            nJ, nh, eps = sets[i % NSETS]
-            kev[i][0].record()
-            o = K.lds_estep_forward(gi, gp, (nJ, nh), S, eps)
-            kev[i][1].record()
-            acc = torch.cat([o["E_init_xx"].sum(0).reshape(-1), o["E_init_x"].sum(0), o["E_pair_xx"].sum(0).reshape(-1),
-                             o["E_pair_xxn"].sum(0).reshape(-1), o["E_pair_xnxn"].sum(0).reshape(-1),
-                             o["lognorm"].sum().reshape(1)])
-            if world > 1:
-                dist.all_reduce(acc)
+            step(i, kev[i])
         e1.record()
         barrier()
     launches = _lib.launch_count() - l0
@@ -250,32 +248,25 @@ def run_ours(args):
     ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
-    # ---- end-to-end through the public API with host buffers ------------------------------------
+    # ---- end-to-end through the public API with HOST buffers ------------------------------------
     h_nJ = sets[0][0].cpu().pin_memory(); h_nh = sets[0][1].cpu().pin_memory()
     out_host = dict(
         samples=torch.empty((B, T, S, n), dtype=torch.float64).pin_memory(),
         E_node_xx=torch.empty((B, T, n), dtype=torch.float64).pin_memory(),
         E_node_x=torch.empty((B, T, n), dtype=torch.float64).pin_memory(),
-        lognorm=torch.empty((B,), dtype=torch.float64).pin_memory(),
-        acc=torch.empty((4 * n * n + n + 1,), dtype=torch.float64).pin_memory())
+        lognorm=torch.empty((B,), dtype=torch.float64).pin_memory())
+    acc_host = torch.empty((4 * n * n + n + 1,), dtype=torch.float64).pin_memory()
 
     def e2e_step(i):
-        d_nJ = h_nJ.to(dev, non_blocking=True); d_nh = h_nh.to(dev, non_blocking=True)
-        samples, (E_init, E_pair, E_node), lognorm = K.natural_lds_inference_general((gi, gp), (d_nJ, d_nh), S, generator=gen)
-        acc = torch.cat([E_init[0].sum(0).reshape(-1), E_init[1].sum(0), E_pair[0].sum(0).reshape(-1),
-                         E_pair[1].sum(0).reshape(-1), E_pair[2].sum(0).reshape(-1), lognorm.sum().reshape(1)])
+        acc = K.lds_estep_host((gi, gp), (h_nJ, h_nh), S, out_host, chunks=8, generator=gen, device=dev)
         if world > 1:
             dist.all_reduce(acc)
-        out_host["samples"].copy_(samples, non_blocking=True)
-        out_host["E_node_xx"].copy_(E_node[0], non_blocking=True)
-        out_host["E_node_x"].copy_(E_node[1], non_blocking=True)
-        out_host["lognorm"].copy_(lognorm, non_blocking=True)
-        out_host["acc"].copy_(acc, non_blocking=True)
+        acc_host.copy_(acc, non_blocking=True)
 
     for i in range(3):
         e2e_step(i)
     barrier()
-    e2e_steps = args.steps
+    e2e_steps = max(3, min(args.steps, 20))
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(e2e_steps):
@@ -287,11 +278,45 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / e2e_steps
     h2d = h_nJ.numel() * 8 + h_nh.numel() * 8
-    d2h = sum(v.numel() * 8 for v in out_host.values())
+    d2h = sum(v.numel() * 8 for v in out_host.values()) + acc_host.numel() * 8
+
+    # ---- secondary numbers (not the headline): training E-step (forward + VJP), HMM config ------------
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        try:
+            nJ, nh, eps = sets[0]
+            w = torch.randn(B, T, S, n, dtype=torch.float64, device=dev, generator=gen)
+            def fb():
+                o = K.lds_estep_forward(gi, gp, (nJ, nh), S, eps, save_for_bwd=True)
+                K.lds_estep_backward(o, dict(samples=w, E_node_xx=nJ, E_node_x=nh, lognorm=-torch.ones(B, dtype=torch.float64, device=dev)))
+            for _ in range(2):
+                fb()
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                fb()
+            b_.record(); torch.cuda.synchronize()
+            extra["lds_estep_fwd_plus_vjp_seq_per_s"] = B / (a.elapsed_time(b_) / 5 * 1e-3)
+            from svae_b200.hmm import hmm_inference as HK
+            from oracle import hmm_numpy as HO
+            lp, lA = HO.rand_hmm_natparam(32, rng)
+            hnode = torch.randn(2048, 500, 32, dtype=torch.float64, device=dev, generator=gen)
+            nat = (g(lp), g(lA), hnode)
+            for _ in range(2):
+                HK.hmm_estep(nat)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(5):
+                HK.hmm_estep(nat)
+            b_.record(); torch.cuda.synchronize()
+            extra["hmm_estep_K32_T500_B2048_seq_per_s"] = 2048 / (a.elapsed_time(b_) / 5 * 1e-3)
+        except Exception as e:  # pragma: no cover
+            extra["error"] = repr(e)
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        ab = alg_bytes_per_seq(n, T) * B
+        ab = alg_bytes_per_seq(n, T) * B + 8 * T * S * n * B     # + injected noise read
         achieved = ab / (kern_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
@@ -314,17 +339,17 @@ def run_ours(args):
                         global_batch=world * B, parallelism="dp%d" % world,
                         l2="inputs per step (196 MB node potentials+noise, 1.4 GB stash) exceed the 126 MB L2; "
                            "%d input sets rotated" % NSETS,
-                        step="fused filter+smoother+sampler kernel, minibatch reduction of global stats"
+                        step="fused filter+smoother+sampler kernel, 2-stage minibatch reduction of the global statistics"
                              + (", NCCL all-reduce of the %d-double accumulator" % (4 * n * n + n + 1) if world > 1 else "")),
             e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                     ms_per_step=e2e_ms),
+                     ms_per_step=e2e_ms, note="pinned host buffers, 8 chunks pipelined over 3 streams; noise drawn on device"),
             gpu_launches=int(launches),
             clocks=clk.summary(),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                          traffic=traffic, peak_source=peak_src, kernel="lds_estep_fwd_kernel<10,16>",
+                          traffic=traffic, peak_source=peak_src, kernel="lds_estep_fwd_kernel<10,16,false>",
                           kernel_ms=kern_ms, algorithmic_bytes_per_launch=ab,
-                          note="fp64 ALU/latency-bound at ~31 flop/B (SURVEY.md §8d); see DESIGN.md"),
-            cpu_baseline=cpu)
+                          note="fp64 ALU / shared-memory bound at ~30 flop/B, not HBM bound (SURVEY.md 8d, DESIGN.md 3)"),
+            cpu_baseline=cpu, extra=extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -337,6 +362,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-core baseline (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary (fwd+VJP, HMM) timings")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

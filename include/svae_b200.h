@@ -127,6 +127,18 @@ int svae_lds_estep_bwd(
     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Minibatch reduction of the LDS global expected statistics: out[4n^2+n+1] =
+ *   sum_b [ E_init_xx | E_init_x | E_pair_xx | E_pair_xxn | E_pair_xnxn | lognorm ]   (deterministic order).
+ * This is flat(stats) of svae/svae.py:33-34 for a minibatch of B sequences, and the payload of the single
+ * all-reduce per SVI step when the minibatch is sharded over GPUs.
+ */
+size_t svae_lds_reduce_stats_workspace_bytes(int n);
+int svae_lds_reduce_stats(int B, int n, const double* E_init_xx, const double* E_init_x,
+                          const double* E_pair_xx, const double* E_pair_xxn, const double* E_pair_xnxn,
+                          const double* lognorm, double* out, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * HMM local E-step for B sequences: log-normaliser and expected statistics by scaled forward-backward.
  * Replaces hmm_logZ / hmm_logZ_grad (svae/hmm/cython_hmm_inference.pyx:93-166; with cotangent 1 the
  * gradient IS the E-step, svae/hmm/hmm_inference.py:65) and hmm_estep (hmm_inference.py:21-41, pyhsmm).

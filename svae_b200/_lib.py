@@ -33,6 +33,8 @@ _SIGNATURES = {
     "svae_lds_estep_workspace_bytes": (_SZ, [_I] * 5),
     "svae_lds_estep_fwd": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 15 + [_P, _P, _SZ, _P]),
     "svae_lds_estep_bwd": (_I, [_I] * 5 + [_P] * 16 + [_P, _SZ, _P]),
+    "svae_lds_reduce_stats_workspace_bytes": (_SZ, [_I]),
+    "svae_lds_reduce_stats": (_I, [_I] * 2 + [_P] * 7 + [_P, _SZ, _P]),
     "svae_hmm_estep": (_I, [_I] * 4 + [_P] * 7 + [_P]),
     "svae_hmm_viterbi_workspace_bytes": (_SZ, [_I] * 3),
     "svae_hmm_viterbi": (_I, [_I] * 3 + [_P] * 4 + [_P, _SZ, _P]),

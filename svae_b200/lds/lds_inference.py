@@ -158,6 +158,65 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
     return out
 
 
+def lds_reduce_global_stats(o):
+    """sum over the minibatch of [E_init_xx | E_init_x | E_pair_xx | E_pair_xxn | E_pair_xnxn | lognorm]
+    (flat(stats) of svae.py:33-34 plus the normaliser) with the deterministic two-stage CUDA reduction."""
+    B, n = o["B"], o["n"]
+    dev = o["lognorm"].device
+    L = _lib.lib()
+    out = torch.empty(4 * n * n + n + 1, dtype=torch.float64, device=dev)
+    wbytes = L.svae_lds_reduce_stats_workspace_bytes(n)
+    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    P = _lib.ptr
+    code = L.svae_lds_reduce_stats(B, n, P(o["E_init_xx"]), P(o["E_init_x"]), P(o["E_pair_xx"]), P(o["E_pair_xxn"]),
+                                   P(o["E_pair_xnxn"]), P(o["lognorm"]), P(out), ctypes.c_void_p(work.data_ptr()),
+                                   wbytes, _lib.stream_ptr(dev))
+    _lib.check(code, "svae_lds_reduce_stats")
+    return out
+
+
+def lds_estep_host(natparam, node_host, num_samples, out_host, chunks=4, generator=None, device=None):
+    """End-to-end E-step for HOST-resident minibatches: the public call a data loader would make.
+
+    node_host = (J_node, h_node) pinned CPU tensors (B,T,n); out_host = dict of pinned CPU tensors
+    {"samples" (B,T,S,n), "E_node_xx" (B,T,n), "E_node_x" (B,T,n), "lognorm" (B)} that are filled in place.
+    The batch is cut into `chunks` pieces that flow H2D copy -> fused E-step kernel -> D2H copy on rotating
+    streams, so PCIe transfers in both directions overlap the kernels of neighbouring chunks.  Returns the
+    device tensor sum_b [E_init | E_pair | lognorm] (see lds_reduce_global_stats)."""
+    init_params, pair_params = natparam
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    J_h, h_h = node_host
+    B, T, n = h_h.shape
+    S = int(num_samples) if num_samples else 0
+    bounds = [(B * k) // chunks for k in range(chunks + 1)]
+    streams = [torch.cuda.Stream(device=device) for _ in range(min(3, chunks))]
+    cur = torch.cuda.current_stream(device)
+    acc = torch.zeros(4 * n * n + n + 1, dtype=torch.float64, device=device)
+    parts = []
+    for k in range(chunks):
+        lo, hi = bounds[k], bounds[k + 1]
+        if hi == lo:
+            continue
+        st = streams[k % len(streams)]
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            dJ = J_h[lo:hi].to(device, non_blocking=True)
+            dh = h_h[lo:hi].to(device, non_blocking=True)
+            o = lds_estep_forward(init_params, pair_params, (dJ, dh), S, None, generator=generator)
+            parts.append((st, lds_reduce_global_stats(o)))
+            if S:
+                out_host["samples"][lo:hi].copy_(o["samples"], non_blocking=True)
+            out_host["E_node_xx"][lo:hi].copy_(o["E_node_xx"], non_blocking=True)
+            out_host["E_node_x"][lo:hi].copy_(o["E_node_x"], non_blocking=True)
+            out_host["lognorm"][lo:hi].copy_(o["lognorm"], non_blocking=True)
+            for t_ in (dJ, dh, o["E_node_xx"], o["E_node_x"], o["lognorm"]) + ((o["samples"],) if S else ()):
+                t_.record_stream(st)
+    for st, part in parts:
+        cur.wait_stream(st)
+        acc += part
+    return acc
+
+
 def lds_estep_backward(o, g):
     """VJP w.r.t. (node_J, node_h): one launch of the reverse-mode kernel.
 

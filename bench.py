@@ -79,11 +79,23 @@ def _cpu_port_worker(args):
     return time.perf_counter() - t0
 
 
+def usable_cores():
+    """Host threads this process can actually use: CPU affinity capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference_rate(n, T, S, target_seconds=4.0, cores=None):
     """sequences/s of the reference CPU path using all host cores (one sequence stream per process)."""
     import multiprocessing as mp
     from oracle import ref
-    cores = cores or (len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()) or 1
+    cores = cores or usable_cores()
     kind = "reference" if ref.available() else "port"
     worker = _cpu_worker if kind == "reference" else _cpu_port_worker
     ctx = mp.get_context("spawn")

@@ -61,7 +61,7 @@ extern "C" int svae_lds_estep_fwd(
   if (workspace_bytes < svae_lds_estep_workspace_bytes(B, T, n, S, flags)) return SVAE_ERR_WORKSPACE;
 
   svae::LdsFwdParams p;
-  p.B = B; p.T = T; p.S = S; p.flags = flags;
+  p.B = B; p.T = T; p.S = S; p.flags = flags; p.const_slot = 0;
   p.init_J = init_J; p.init_h = init_h; p.init_logZ = init_logZ;
   p.J11 = J11; p.J12 = J12; p.J22 = J22; p.pair_logZ = pair_logZ;
   p.pair_stride_t = pair_stride_t; p.pair_stride_b = pair_stride_b;

@@ -44,7 +44,7 @@
 namespace svae {
 
 struct LdsFwdParams {
-  int B, T, S, flags;
+  int B, T, S, flags, const_slot;
   const double *init_J, *init_h, *init_logZ;
   const double *J11, *J12, *J22, *pair_logZ;
   long long pair_stride_t, pair_stride_b;
@@ -85,7 +85,9 @@ __host__ __device__ inline int lds_tile_doubles(int N, int S, bool inhomog) {
 
 // homogeneous J12 (natural form, row-major n x n) lives in the constant bank so the prediction's
 // multiply-adds take it as an immediate-offset constant operand: no shared-memory traffic at all.
-static __constant__ double c_J12[SVAE_LDS_CONST_NN];
+// (a small pool of slots so launches on different streams do not serialise on one bank)
+#define SVAE_LDS_CONST_SLOTS 8
+static __constant__ double c_J12[SVAE_LDS_CONST_SLOTS][SVAE_LDS_CONST_NN];
 
 // register budget: one warp per CTA; SVAE_LDS_MAXREG caps registers/thread (144 -> 14 CTAs per SM)
 #if defined(SVAE_LDS_MAXREG)
@@ -356,10 +358,11 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
           }
         } else {
           // information-form J12 = -(natural J12):  a -= J12_info' r  ==  a += J12_nat' r
+          const double* cj12 = c_J12[p.const_slot];
 #pragma unroll
           for (int k = 0; k < N; ++k) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) a[i] = fma(c_J12[k * N + i], r[k], a[i]);
+            for (int i = 0; i < N; ++i) a[i] = fma(cj12[k * N + i], r[k], a[i]);
           }
         }
       }

@@ -17,25 +17,30 @@
 
 namespace svae {
 
-// The homogeneous J12 is handed to the kernel through this translation unit's __constant__ array.
-// One array per latent dimension: uses from different streams are ordered with an event so a copy
-// never overwrites the bank while an earlier launch on another stream may still read it.
+// The homogeneous J12 is handed to the kernel through this translation unit's __constant__ slots.
+// Slots rotate; a slot is re-used from a different stream only after the event recorded behind its last
+// kernel, so a copy never overwrites a bank another stream's launch may still read.
 static std::mutex g_const_mu;
-static cudaEvent_t g_const_ev = nullptr;
-static cudaStream_t g_const_stream = nullptr;
-static bool g_const_used = false;
+static cudaEvent_t g_const_ev[SVAE_LDS_CONST_SLOTS] = {};
+static cudaStream_t g_const_stream[SVAE_LDS_CONST_SLOTS] = {};
+static bool g_const_used[SVAE_LDS_CONST_SLOTS] = {};
+static int g_const_next = 0;
 
 template <int N>
-static cudaError_t stage_const_J12(const double* J12, cudaStream_t stream) {
-  if (!g_const_ev) {
-    cudaError_t e = cudaEventCreateWithFlags(&g_const_ev, cudaEventDisableTiming);
+static cudaError_t stage_const_J12(const double* J12, cudaStream_t stream, int* slot_out) {
+  const int slot = g_const_next;
+  g_const_next = (g_const_next + 1) % SVAE_LDS_CONST_SLOTS;
+  if (!g_const_ev[slot]) {
+    cudaError_t e = cudaEventCreateWithFlags(&g_const_ev[slot], cudaEventDisableTiming);
     if (e != cudaSuccess) return e;
   }
-  if (g_const_used && g_const_stream != stream) {
-    cudaError_t e = cudaStreamWaitEvent(stream, g_const_ev, 0);
+  if (g_const_used[slot] && g_const_stream[slot] != stream) {
+    cudaError_t e = cudaStreamWaitEvent(stream, g_const_ev[slot], 0);
     if (e != cudaSuccess) return e;
   }
-  return cudaMemcpyToSymbolAsync(c_J12, J12, sizeof(double) * N * N, 0, cudaMemcpyDeviceToDevice, stream);
+  *slot_out = slot;
+  return cudaMemcpyToSymbolAsync(c_J12, J12, sizeof(double) * N * N, sizeof(double) * SVAE_LDS_CONST_NN * slot,
+                                 cudaMemcpyDeviceToDevice, stream);
 }
 
 template <int N, int LPS, bool INHOMOG>
@@ -62,14 +67,17 @@ static cudaError_t launch_one(const LdsFwdParams& p, cudaStream_t stream) {
   }
   if (!INHOMOG && p.T > 1) {
     std::lock_guard<std::mutex> lock(g_const_mu);
-    cudaError_t e = stage_const_J12<N>(p.J12, stream);
+    LdsFwdParams q = p;
+    int slot = 0;
+    cudaError_t e = stage_const_J12<N>(p.J12, stream, &slot);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)grid, warps_per_cta * 32, smem, stream>>>(p);
+    q.const_slot = slot;
+    kern<<<(unsigned)grid, warps_per_cta * 32, smem, stream>>>(q);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    g_const_used = true;
-    g_const_stream = stream;
-    return cudaEventRecord(g_const_ev, stream);
+    g_const_used[slot] = true;
+    g_const_stream[slot] = stream;
+    return cudaEventRecord(g_const_ev[slot], stream);
   }
   kern<<<(unsigned)grid, warps_per_cta * 32, smem, stream>>>(p);
   return cudaGetLastError();

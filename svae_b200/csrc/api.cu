@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" boundary of libsvae_b200.so (see include/svae_b200.h).
 #include <atomic>
+#include <cstdlib>
 #include "svae_b200.h"
 #include "launch.h"
 
@@ -9,7 +10,7 @@ extern "C" const char* svae_b200_version(void) { return "svae_b200 0.1 sm_100a";
 extern "C" uint64_t svae_b200_launch_count(void) { return g_svae_launches.load(); }
 
 namespace {
-typedef cudaError_t (*lds_fwd_fn)(const svae::LdsFwdParams&, int, bool, cudaStream_t);
+typedef cudaError_t (*lds_fwd_fn)(const svae::LdsFwdParams&, int, int, bool, cudaStream_t);
 const lds_fwd_fn kLdsFwd[SVAE_LDS_MAX_N + 1] = {
     nullptr,
     svae::lds_fwd_launch_n1, svae::lds_fwd_launch_n2, svae::lds_fwd_launch_n3, svae::lds_fwd_launch_n4,
@@ -25,10 +26,24 @@ const lds_bwd_fn kLdsBwd[SVAE_LDS_MAX_N + 1] = {
     svae::lds_bwd_launch_n9, svae::lds_bwd_launch_n10, svae::lds_bwd_launch_n11, svae::lds_bwd_launch_n12,
     svae::lds_bwd_launch_n13, svae::lds_bwd_launch_n14, svae::lds_bwd_launch_n15, svae::lds_bwd_launch_n16};
 
-int pick_lps(int n, int S) {
+int pick_lps(int n, int S) {   // one column per lane (VJP kernel; forward kernel with SVAE_LDS_CPL=1)
   if (n + 1 + S <= 16) return 16;
   if (n + 1 + S <= 32) return 32;
   return 0;
+}
+// forward kernel: two column slots per lane, the smallest tile that holds n + 1 + S slots
+int pick_lps2(int n, int S) {
+  for (int lps = 4; lps <= 32; lps *= 2)
+    if (2 * lps >= n + 1 + S) return lps;
+  return 0;
+}
+int forward_cpl() {
+#ifdef SVAE_LDS_ENABLE_CPL2
+  static int cpl = [] { const char* e = getenv("SVAE_LDS_CPL"); return (e && atoi(e) == 2) ? 2 : 1; }();
+  return cpl;
+#else
+  return 1;
+#endif
 }
 }  // namespace
 
@@ -56,7 +71,8 @@ extern "C" int svae_lds_estep_fwd(
   if (T > 1 && (!J11 || !J12 || !J22)) return SVAE_ERR_BAD_ARG;
   if (S > 0 && !eps) return SVAE_ERR_BAD_ARG;
   if (n > SVAE_LDS_MAX_N) return SVAE_ERR_UNSUPPORTED;
-  const int lps = pick_lps(n, S);
+  const int cpl = forward_cpl();
+  const int lps = cpl == 2 ? pick_lps2(n, S) : pick_lps(n, S);
   if (!lps) return SVAE_ERR_UNSUPPORTED;
   if (workspace_bytes < svae_lds_estep_workspace_bytes(B, T, n, S, flags)) return SVAE_ERR_WORKSPACE;
 
@@ -76,7 +92,7 @@ extern "C" int svae_lds_estep_fwd(
   p.status = status;
   p.stash = static_cast<double*>(workspace);
   const bool inhomog = (pair_stride_t != 0 || pair_stride_b != 0) && T > 1;
-  cudaError_t e = kLdsFwd[n](p, lps, inhomog, static_cast<cudaStream_t>(stream));
+  cudaError_t e = kLdsFwd[n](p, cpl, lps, inhomog, static_cast<cudaStream_t>(stream));
   g_svae_launches.fetch_add(1);
   return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
 }

@@ -43,8 +43,11 @@ __device__ __forceinline__ float tile_maxf(float v) {
 }
 
 // flags: bit0 = forward only (logZ), else full E-step
+#ifndef SVAE_HMM_MINB32
+#define SVAE_HMM_MINB32 8
+#endif
 template <int LPS>
-__global__ void __launch_bounds__(32) hmm_estep_kernel(const HmmParams p) {
+__global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_estep_kernel(const HmmParams p) {
   constexpr int SPW = 32 / LPS;
   constexpr int LP = (LPS + 1) & ~1;
   __shared__ __align__(16) double sbuf[SPW][2][LP < 2 ? 2 : LP];

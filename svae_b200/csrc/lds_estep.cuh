@@ -9,10 +9,11 @@
 //   per-step kernels svae/lds/cython_gaussian_grads.pxd:38-82,125-144,167-188,208-296,431-508
 //
 // B200 design (not a translation):
-//   * one sub-warp tile of LPS lanes per sequence (LPS = 16 -> 2 sequences per warp, or 32);
-//     lane c < N owns COLUMN c of every n x n matrix in registers, lane N owns the mean/potential
-//     vector, lanes N+1..N+S own one sample path each.  All register arrays are fully unrolled over
-//     the compile-time N; cross-lane traffic is 16-byte broadcast reads from shared memory.
+//   * one sub-warp tile of LPS lanes per sequence, each lane owning CPL "column slots" (CPL = 2, LPS = 8:
+//     FOUR sequences per warp at n <= 14).  Slot c < N is COLUMN c of every n x n matrix, held in
+//     registers; slot N is the mean/potential vector, slots N+1..N+S one sample path each.  All register
+//     arrays are fully unrolled over the compile-time N; cross-lane traffic is 16-byte broadcast reads from
+//     shared memory, and with CPL = 2 every broadcast element feeds two multiply-adds per lane.
 //   * filter step t (same arithmetic result as _natural_condition_diag + _natural_predict):
 //       M_t = J_pred + diag(J_node) + J11        (information form)
 //       M_t = L~ D L~'                           square-root-free LDL' (N reciprocals, no sqrt chain)
@@ -89,30 +90,41 @@ __host__ __device__ inline int lds_tile_doubles(int N, int S, bool inhomog) {
 #define SVAE_LDS_CONST_SLOTS 8
 static __constant__ double c_J12[SVAE_LDS_CONST_SLOTS][SVAE_LDS_CONST_NN];
 
-// register budget: one warp per CTA; SVAE_LDS_MAXREG caps registers/thread (144 -> 14 CTAs per SM)
-#if defined(SVAE_LDS_MAXREG)
-#define SVAE_LDS_BOUNDS __maxnreg__(SVAE_LDS_MAXREG)
-#else
+// register budget (one warp per CTA).  CPL = 1, n <= 10: 128 registers so that 16 CTAs fit per SM (the whole
+// metric batch in one wave); CPL = 2 keeps two columns per lane in registers and needs the full file, with
+// four sequences per warp only 7 CTAs per SM are needed.
 #ifndef SVAE_LDS_MINB
-#define SVAE_LDS_MINB 8
+#define SVAE_LDS_MINB(N, CPL) (((CPL) == 1 && (N) <= 10) ? 16 : 7)
 #endif
-#define SVAE_LDS_BOUNDS __launch_bounds__(32, SVAE_LDS_MINB)
-#endif
-template <int N, int LPS, bool INHOMOG>
-__global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
+#define SVAE_LDS_BOUNDS(N, CPL) __launch_bounds__(32, SVAE_LDS_MINB(N, CPL))
+
+template <int N, int CPL, int LPS, bool INHOMOG>
+__global__ void SVAE_LDS_BOUNDS(N, CPL) lds_estep_fwd_kernel(const LdsFwdParams p) {
   constexpr int SPW = 32 / LPS;
   constexpr int NP = lds_np(N);
   constexpr int NN = N * N;
+  static_assert(CPL == 1 || CPL == 2, "one or two column slots per lane");
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int sub = lane / LPS, c = lane % LPS;
+  const int sub = lane / LPS, l = lane % LPS;
   const int S = p.S, T = p.T;
   const long long seq = ((long long)blockIdx.x * nwarps + warp) * SPW + sub;
   const bool valid = seq < p.B;
   const long long b = valid ? seq : (long long)p.B - 1;
-  const bool mat = c < N, vec = c == N, smp = (c > N) && (c <= N + S);
-  const int s = smp ? c - N - 1 : 0;
-  const int cm = mat ? c : 0;   // safe column index for lanes that do not own a matrix column
+  // the column slots of this lane
+  int c[CPL], sx[CPL], cm[CPL];
+  bool mat[CPL], vec[CPL], smp[CPL];
+#pragma unroll
+  for (int cl = 0; cl < CPL; ++cl) {
+    c[cl] = l * CPL + cl;
+    mat[cl] = c[cl] < N;
+    vec[cl] = c[cl] == N;
+    smp[cl] = (c[cl] > N) && (c[cl] <= N + S);
+    sx[cl] = smp[cl] ? c[cl] - N - 1 : 0;
+    cm[cl] = mat[cl] ? c[cl] : 0;   // safe column index for slots that do not own a matrix column
+  }
+  const bool anymat = mat[0];                     // slots are ordered: slot 0 is a matrix column iff any is
+  const bool pairmat = mat[CPL - 1];              // every slot of this lane is a matrix column
   const int SS = lds_stash_stride(N, S);               // fetched prefix of a record
   const bool save = (p.flags & SVAE_LDS_FLAG_SAVE) != 0;
   const int RS = lds_record_stride(N, S, save);         // record stride in HBM
@@ -131,7 +143,7 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
   double* uni = xs + S * NP;      // ---- phase-shared storage ----
   // filter sweep
   double* Lr = uni;               // Lr[k*NP+i]: raw LDL' column k (i >= k), Lr[k*NP+k] = d_k - node
-  double* Lt = Lr + N * NP;       // Lt[k*NP+i]: unit-lower L~[i][k] (i > k)
+  double* Lt = Lr + N * NP;       // Lt[i*NP+k]: unit-lower L~[i][k] (k < i), row-major
   double* nring = Lt + N * NP;    // 2 x { J_node row | h_node row | eps rows }
   double* tJ12 = nring + 2 * NODE;  // per-tile pair parameters (INHOMOG only)
   double* tJ22 = tJ12 + N * NP;
@@ -151,7 +163,7 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
       shJ22[i * NP + j] = -2.0 * p.J22[e];
     }
   }
-  if (c == 0) {
+  if (l == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_fence_init();
@@ -165,37 +177,47 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
 
   // stage the node potentials (+ noise) of time t into node-ring slot t&1 with cp.async
   auto stage_node = [&](int t) {
-    if (mat) {
-      double* dst = nring + (t & 1) * NODE;
-      cp_async8(dst + c, nJ + (size_t)t * N + c);
-      cp_async8(dst + NP + c, nh + (size_t)t * N + c);
-      for (int ss = 0; ss < S; ++ss) cp_async8(dst + (2 + ss) * NP + c, eps + ((size_t)t * S + ss) * N + c);
+#pragma unroll
+    for (int cl = 0; cl < CPL; ++cl) {
+      if (mat[cl]) {
+        double* dst = nring + (t & 1) * NODE;
+        cp_async8(dst + c[cl], nJ + (size_t)t * N + c[cl]);
+        cp_async8(dst + NP + c[cl], nh + (size_t)t * N + c[cl]);
+        for (int ss = 0; ss < S; ++ss)
+          cp_async8(dst + (2 + ss) * NP + c[cl], eps + ((size_t)t * S + ss) * N + c[cl]);
+      }
     }
     cp_async_commit();
   };
 
   double lacc = 0.0;   // per-lane partial of lognorm (reduced over the tile at the end)
-  double dprod = 1.0;  // running product of this lane's pivots (log taken every 8 steps)
-  bool bad = false;
+  double lq[CPL];      // sum_t sum_k z_k^2 / d_k accumulated by every slot, only the vec slot's is used
+#pragma unroll
+  for (int cl = 0; cl < CPL; ++cl) lq[cl] = 0.0;
+  int badbits = 0;     // OR of the pivots' high words: the sign bit flags a non-positive-definite M_t
+  double dprod = 1.0;  // running product of this lane's pivots (log taken every few steps)
 
   stage_node(0);
   if (T > 1) stage_node(1); else cp_async_commit();
   cp_async_wait<1>();
   __syncwarp();
 
-  // a: mat lanes -- column c of M_t = J_pred + J11 (the node precision is added at the pivot);
-  //    vec lane  -- h_filtered = h_pred + h_node.   Information form.
-  double a[N];
+  // a: mat slots -- column c of M_t = J_pred + J11 (the node precision is added at the pivot);
+  //    vec slot  -- h_filtered = h_pred + h_node.   Information form.
+  double a[CPL][N];
   const bool init_per_seq = (p.flags & SVAE_LDS_FLAG_INIT_PER_SEQ) != 0;
   const double* iJ = p.init_J + (init_per_seq ? (size_t)b * NN : 0);
   const double* ih = p.init_h + (init_per_seq ? (size_t)b * N : 0);
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-    if (mat) {
-      a[i] = -2.0 * iJ[i * N + c];
-      if (!INHOMOG && T > 1) a[i] -= 2.0 * p.J11[i * N + c];
-    } else {
-      a[i] = vec ? ih[i] + nring[NP + i] : 0.0;
+  for (int cl = 0; cl < CPL; ++cl) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (mat[cl]) {
+        a[cl][i] = -2.0 * iJ[i * N + c[cl]];
+        if (!INHOMOG && T > 1) a[cl][i] -= 2.0 * p.J11[i * N + c[cl]];
+      } else {
+        a[cl][i] = vec[cl] ? ih[i] + nring[NP + i] : 0.0;
+      }
     }
   }
 
@@ -204,13 +226,15 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
     const bool last = (t == T - 1);
     if (INHOMOG && !last) {
       const size_t off = (size_t)t * p.pair_stride_t + (size_t)b * p.pair_stride_b;
-      if (mat) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          const double j11 = -2.0 * p.J11[off + i * N + c];
-          a[i] += j11;
-          tJ12[i * NP + c] = -p.J12[off + i * N + c];
-          tJ22[i * NP + c] = -2.0 * p.J22[off + i * N + c];
+      for (int cl = 0; cl < CPL; ++cl) {
+        if (mat[cl]) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            a[cl][i] += -2.0 * p.J11[off + i * N + c[cl]];
+            tJ12[i * NP + c[cl]] = -p.J12[off + i * N + c[cl]];
+            tJ22[i * NP + c[cl]] = -2.0 * p.J22[off + i * N + c[cl]];
+          }
         }
       }
       __syncwarp();
@@ -218,19 +242,28 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
     const double* nd = nring + (t & 1) * NODE;
 
     // right-hand sides: r = J12 column (mat), q = identity column (mat -> M^-1 column)
-    double r[N], q[N];
+    double r[CPL][N], q[CPL][N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      r[i] = last ? 0.0 : J12s[i * NP + cm];
-      q[i] = (i == c) ? 1.0 : 0.0;
+      if (CPL == 2) {
+        const double2 v = last ? make_double2(0.0, 0.0) : ld2(&J12s[i * NP + cm[0]]);   // cm[0] is even
+        r[0][i] = v.x;
+        r[CPL - 1][i] = v.y;
+      } else {
+        r[0][i] = last ? 0.0 : J12s[i * NP + cm[0]];
+      }
+#pragma unroll
+      for (int cl = 0; cl < CPL; ++cl) q[cl][i] = (i == c[cl]) ? 1.0 : 0.0;
     }
 
     // ---- square-root-free LDL' of M_t fused with the forward substitution of all right-hand
-    //      sides: lanes = rows; the pivot column is broadcast through Lr; the vec lane's `a`
+    //      sides: slots = rows; the pivot column is broadcast through Lr; the vec slot's `a`
     //      rides along as a bordered row, which IS its forward substitution ----------------------
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      if (mat) Lr[k * NP + c] = a[k];
+#pragma unroll
+      for (int cl = 0; cl < CPL; ++cl)
+        if (mat[cl]) Lr[k * NP + c[cl]] = a[cl][k];
       __syncwarp();
       double row[NP];
 #pragma unroll
@@ -240,95 +273,117 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
         row[2 * q2 + 1] = v.y;
       }
       const double piv = fma(-2.0, nd[k], row[k]);     // + node precision on the diagonal
-      bad |= !(piv > 0.0);
+      badbits |= __double2hiint(piv);
       const double ik = fast_rcp(piv);
-      const double ta = a[k] * ik, tr = r[k] * ik, tq = q[k] * ik;
-      if (mat) Lt[k * NP + c] = ta;                      // unit-lower factor, column k
-      if (vec) lacc = fma(0.5 * a[k], ta, lacc);         // 1/2 z_k^2 / d_k
 #pragma unroll
-      for (int j = k + 1; j < N; ++j) {
-        a[j] = fma(-ta, row[j], a[j]);
-        r[j] = fma(-tr, row[j], r[j]);
-        q[j] = fma(-tq, row[j], q[j]);
+      for (int cl = 0; cl < CPL; ++cl) {
+        const double ta = a[cl][k] * ik, tr = r[cl][k] * ik, tq = q[cl][k] * ik;
+        if (mat[cl]) Lt[c[cl] * NP + k] = ta;                   // unit-lower factor L~[c][k], row-major
+        lq[cl] = fma(a[cl][k], ta, lq[cl]);                     // z_k^2 / d_k (meaningful in the vec slot)
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) {
+          a[cl][j] = fma(-ta, row[j], a[cl][j]);
+          r[cl][j] = fma(-tr, row[j], r[cl][j]);
+          q[cl][j] = fma(-tq, row[j], q[cl][j]);
+        }
+        a[cl][k] = ta;
+        r[cl][k] = tr;
+        q[cl][k] = tq;
       }
-      a[k] = ta;
-      r[k] = tr;
-      q[k] = tq;
     }
-    if (mat) {
-      const double dc = fma(-2.0, nd[c], Lr[c * NP + c]);
-      dprod *= dc;
-      const double rs = rsqrt(dc);
-      sq[c] = rs;
-      if (save) mbuf[c] = dc * rs;   // sqrt(d_c), consumed below (mbuf is free until m_t is published)
+#pragma unroll
+    for (int cl = 0; cl < CPL; ++cl) {
+      if (mat[cl]) {
+        const double dc = fma(-2.0, nd[c[cl]], Lr[c[cl] * NP + c[cl]]);
+        dprod *= dc;
+        const double rs = rsqrt(dc);
+        sq[c[cl]] = rs;
+        if (save) mbuf[c[cl]] = dc * rs;   // sqrt(d_c), consumed below (mbuf is free until m_t is published)
+      }
+      if (vec[cl]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[cl][i] = a[cl][i];
+      }
     }
-    if ((t & 7) == 7 || last) {
+    if ((t & 3) == 3 || last) {
       lacc -= 0.5 * log(dprod);
       dprod = 1.0;
     }
-    if (vec) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) r[i] = a[i];
-    }
     __syncwarp();
-    if (smp) {
-      const double* ep = nd + (2 + s) * NP;
 #pragma unroll
-      for (int k = 0; k < N; ++k) r[k] = ep[k] * sq[k];   // D^-1/2 eps
+    for (int cl = 0; cl < CPL; ++cl) {
+      if (smp[cl]) {
+        const double* ep = nd + (2 + sx[cl]) * NP;
+#pragma unroll
+        for (int k = 0; k < N; ++k) r[cl][k] = ep[k] * sq[k];   // D^-1/2 eps
+      }
     }
     if (save) {
       // K = L^-1 column c: (L~^-1 e_c)_i / sqrt(d_i) = q_i sqrt(d_i)   (q is D^-1 L~^-1 e_c here)
-      if (mat && valid) {
-        double* kt = stash + (size_t)t * RS + (2 * N + 1 + S) * NP;
+      double* kt = stash + (size_t)t * RS + (2 * N + 1 + S) * NP;
 #pragma unroll
-        for (int i = 0; i < N; ++i) kt[i * NP + c] = q[i] * mbuf[i];
+      for (int cl = 0; cl < CPL; ++cl) {
+        if (mat[cl] && valid) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) kt[i * NP + c[cl]] = q[cl][i] * mbuf[i];
+        }
       }
       __syncwarp();   // mbuf is rewritten with m_t below
     }
-    // ---- backward substitution with the unit-upper factor L~' (in place) ----------------------
+    // ---- backward substitution with the unit-upper factor L~' (in place), column-oriented: once y_i is
+    //      final, r[k] -= L~[i][k] y_i for all k < i -- independent accumulators, chain of one FMA per i ----
 #pragma unroll
-    for (int k = N - 2; k >= 0; --k) {
-      double accr = 0.0, accq = 0.0;
+    for (int i = N - 1; i >= 1; --i) {
 #pragma unroll
-      for (int q2 = (k + 1) / 2; q2 < NP / 2; ++q2) {
-        const double2 v = ld2(&Lt[k * NP + 2 * q2]);
-        if (2 * q2 > k && 2 * q2 < N) {
-          accr = fma(v.x, r[2 * q2], accr);
-          accq = fma(v.x, q[2 * q2], accq);
-        }
-        if (2 * q2 + 1 > k && 2 * q2 + 1 < N) {
-          accr = fma(v.y, r[2 * q2 + 1], accr);
-          accq = fma(v.y, q[2 * q2 + 1], accq);
+      for (int q2 = 0; q2 < (i + 1) / 2; ++q2) {
+        const double2 v = ld2(&Lt[i * NP + 2 * q2]);          // L~[i][2q2], L~[i][2q2+1]
+#pragma unroll
+        for (int cl = 0; cl < CPL; ++cl) {
+          r[cl][2 * q2] = fma(-v.x, r[cl][i], r[cl][2 * q2]);
+          q[cl][2 * q2] = fma(-v.x, q[cl][i], q[cl][2 * q2]);
+          if (2 * q2 + 1 < i) {
+            r[cl][2 * q2 + 1] = fma(-v.y, r[cl][i], r[cl][2 * q2 + 1]);
+            q[cl][2 * q2 + 1] = fma(-v.y, q[cl][i], q[cl][2 * q2 + 1]);
+          }
         }
       }
-      r[k] -= accr;
-      q[k] -= accq;
     }
     // mat: r = M^-1 J12[:,c] = -G[:,c], q = M^-1[:,c];  vec: r = m;  smp: r = L^-T eps
-    if (vec) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) mbuf[i] = r[i];
+    for (int cl = 0; cl < CPL; ++cl) {
+      if (vec[cl]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) mbuf[i] = r[cl][i];
+      }
     }
     __syncwarp();
-    if (smp) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) r[i] += mbuf[i];   // b_t = m_t + L^-T eps_t
+    for (int cl = 0; cl < CPL; ++cl) {
+      if (smp[cl]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[cl][i] += mbuf[i];   // b_t = m_t + L^-T eps_t
+      }
     }
 
     if (!last || save) {
       // ---- stash record for the backward sweep (and, when saving, for the VJP kernel) ---------
       double* st = stash + (size_t)t * RS;
       if (valid) {
-        if (mat) {
+        // G is stored TRANSPOSED (Gt[k*NP+i] = G[i][k]): slot c owns the contiguous row c, and the smoother's
+        // C = G z becomes an axpy over k with independent accumulators.  M^-1 is symmetric: same trick.
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            st[i * NP + c] = -r[i];
-            st[N * NP + i * NP + c] = q[i];
+        for (int cl = 0; cl < CPL; ++cl) {
+          if (mat[cl]) {
+#pragma unroll
+            for (int q2 = 0; q2 < NP / 2; ++q2) {
+              st2(&st[c[cl] * NP + 2 * q2], -r[cl][2 * q2], (2 * q2 + 1 < N) ? -r[cl][2 * q2 + 1] : 0.0);
+              st2(&st[N * NP + c[cl] * NP + 2 * q2], q[cl][2 * q2], (2 * q2 + 1 < N) ? q[cl][2 * q2 + 1] : 0.0);
+            }
+            st[2 * N * NP + c[cl]] = mbuf[c[cl]];
+          } else if (smp[cl]) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) st[(2 * N + 1 + sx[cl]) * NP + i] = r[cl][i];
           }
-          st[2 * N * NP + c] = mbuf[c];
-        } else if (smp) {
-#pragma unroll
-          for (int i = 0; i < N; ++i) st[(2 * N + 1 + s) * NP + i] = r[i];
         }
       }
     }
@@ -342,18 +397,24 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
       {
         const double* ndn = nring + ((t + 1) & 1) * NODE;
         const double* pm = INHOMOG ? J22s : ((t + 1 == T - 1) ? shJ22 : shJ11);
-        const double* pinit = mat ? pm + c : ndn + NP;
-        const int pstr = mat ? NP : 1;
 #pragma unroll
-        for (int i = 0; i < N; ++i) a[i] = pinit[i * pstr];
+        for (int cl = 0; cl < CPL; ++cl) {
+          const double* pinit = mat[cl] ? pm + c[cl] : ndn + NP;
+          const int pstr = mat[cl] ? NP : 1;
+#pragma unroll
+          for (int i = 0; i < N; ++i) a[cl][i] = pinit[i * pstr];
+        }
         if (INHOMOG) {
 #pragma unroll
           for (int k = 0; k < N; ++k) {
 #pragma unroll
             for (int q2 = 0; q2 < NP / 2; ++q2) {
               const double2 v = ld2(&J12s[k * NP + 2 * q2]);
-              a[2 * q2] = fma(-v.x, r[k], a[2 * q2]);
-              if (2 * q2 + 1 < N) a[2 * q2 + 1] = fma(-v.y, r[k], a[2 * q2 + 1]);
+#pragma unroll
+              for (int cl = 0; cl < CPL; ++cl) {
+                a[cl][2 * q2] = fma(-v.x, r[cl][k], a[cl][2 * q2]);
+                if (2 * q2 + 1 < N) a[cl][2 * q2 + 1] = fma(-v.y, r[cl][k], a[cl][2 * q2 + 1]);
+              }
             }
           }
         } else {
@@ -362,26 +423,36 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
 #pragma unroll
           for (int k = 0; k < N; ++k) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) a[i] = fma(cj12[k * N + i], r[k], a[i]);
+            for (int i = 0; i < N; ++i) {
+              const double j = cj12[k * N + i];
+#pragma unroll
+              for (int cl = 0; cl < CPL; ++cl) a[cl][i] = fma(j, r[cl][k], a[cl][i]);
+            }
           }
         }
       }
     } else {
       // terminal step: the smoothed marginal at T-1 is the filtered one
 #pragma unroll
-      for (int i = 0; i < N; ++i) a[i] = mat ? q[i] : r[i];
+      for (int cl = 0; cl < CPL; ++cl) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[cl][i] = mat[cl] ? q[cl][i] : r[cl][i];
+      }
     }
     __syncwarp();
   }
-  // backward-sweep state: column of [Sigma | mu | x]  (reuses the registers of a)
-  double (&z)[N] = a;
+  // backward-sweep state: columns of [Sigma | mu | x]  (reuses the registers of a)
+  double (&z)[CPL][N] = a;
 
   // lognorm: reduce the per-lane partials over the tile, add the constant terms
   {
     double tot = lacc;
 #pragma unroll
+    for (int cl = 0; cl < CPL; ++cl)
+      if (vec[cl]) tot = fma(0.5, lq[cl], tot);
+#pragma unroll
     for (int o = LPS / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o, LPS);
-    if (c == 0 && valid && p.lognorm) {
+    if (l == 0 && valid && p.lognorm) {
       double konst = p.init_logZ ? p.init_logZ[init_per_seq ? b : 0] : 0.0;
       if (p.pair_logZ) {
         if (!INHOMOG) {
@@ -396,7 +467,8 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
       p.lognorm[b] = tot + konst;
     }
   }
-  if (bad && p.status) atomicMax(p.status, (int)b + 1);
+  // negative pivot (sign bit) or a NaN that reached the normaliser
+  if ((badbits < 0 || !(lacc == lacc)) && p.status) atomicMax(p.status, (int)b + 1);
 
   // =========================== backward in time: smoother + sampler ==========================
   // stash records were written through the generic proxy; order them before the async-proxy reads
@@ -405,23 +477,27 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
   __syncwarp();
   auto fetch = [&](int t, int j) {   // j-th backward step (t = T-2-j) -> ring slot j&1
 #if SVAE_LDS_TMA
-    if (c == 0) {
+    if (l == 0) {
       mbar_arrive_expect_tx(&bars[j & 1], (uint32_t)(SS * sizeof(double)));
       tma_load_1d(ring + (j & 1) * SS, stash + (size_t)t * RS, (uint32_t)(SS * sizeof(double)), &bars[j & 1]);
     }
 #else
     double* dst = ring + (j & 1) * SS;
     const double* src = stash + (size_t)t * RS;
-    for (int e = c; e < SS; e += LPS) dst[e] = src[e];
+    for (int e = l; e < SS; e += LPS) dst[e] = src[e];
 #endif
   };
   if (T >= 2) fetch(T - 2, 0);
   if (T >= 3) fetch(T - 3, 1);
 
-  double acc_mid[N], acc_xxn[N];
+  double acc_mid[CPL][N], acc_xxn[CPL][N];
+  double mun_c[CPL];
 #pragma unroll
-  for (int i = 0; i < N; ++i) acc_mid[i] = acc_xxn[i] = 0.0;
-  double mun_c = 0.0;
+  for (int cl = 0; cl < CPL; ++cl) {
+    mun_c[cl] = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc_mid[cl][i] = acc_xxn[cl][i] = 0.0;
+  }
 
   for (int t = T - 1; t >= 0; --t) {
     if (t < T - 1) {
@@ -434,113 +510,144 @@ __global__ void SVAE_LDS_BOUNDS lds_estep_fwd_kernel(const LdsFwdParams p) {
 #endif
       const double* G = rec;
       const double* Minv = rec + N * NP;
-      // C = G z  for every column of [Sigma_{t+1} | mu_{t+1} | x_{t+1}]
+      // C = G z  for every column slot of [Sigma_{t+1} | mu_{t+1} | x_{t+1}]:  cc[:] += Gt[k][:] z[k]
       {
-        double cc[N];
+        double cc[CPL][N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          double acc = 0.0;
+        for (int cl = 0; cl < CPL; ++cl)
+#pragma unroll
+          for (int i = 0; i < N; ++i) cc[cl][i] = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
 #pragma unroll
           for (int q2 = 0; q2 < NP / 2; ++q2) {
-            const double2 g = ld2(&G[i * NP + 2 * q2]);
-            acc = fma(g.x, z[2 * q2], acc);
-            if (2 * q2 + 1 < N) acc = fma(g.y, z[2 * q2 + 1], acc);
+            const double2 g = ld2(&G[k * NP + 2 * q2]);
+#pragma unroll
+            for (int cl = 0; cl < CPL; ++cl) {
+              cc[cl][2 * q2] = fma(g.x, z[cl][k], cc[cl][2 * q2]);
+              if (2 * q2 + 1 < N) cc[cl][2 * q2 + 1] = fma(g.y, z[cl][k], cc[cl][2 * q2 + 1]);
+            }
           }
-          cc[i] = acc;
         }
-        if (mat) {
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            Cs[c * NP + i] = cc[i];
-            acc_xxn[i] += cc[i];     // Cov(x_t, x_{t+1})[i][c]; the mean outer product is added below
+        for (int cl = 0; cl < CPL; ++cl) {
+          if (mat[cl]) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              Cs[c[cl] * NP + i] = cc[cl][i];
+              acc_xxn[cl][i] += cc[cl][i];   // Cov(x_t, x_{t+1})[i][c]; the mean outer product is added below
+            }
+          } else if (vec[cl] || smp[cl]) {
+            const double* base = rec + (2 * N + (vec[cl] ? 0 : 1 + sx[cl])) * NP;
+#pragma unroll
+            for (int i = 0; i < N; ++i) z[cl][i] = base[i] + cc[cl][i];
           }
-        } else if (vec || smp) {
-          const double* base = rec + (2 * N + (vec ? 0 : 1 + s)) * NP;
-#pragma unroll
-          for (int i = 0; i < N; ++i) z[i] = base[i] + cc[i];
         }
       }
       __syncwarp();
-      if (mat) {
+      if (anymat) {
+        if (CPL == 2) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) z[i] = Minv[i * NP + c];
+          for (int i = 0; i < N; ++i) {
+            const double2 v = ld2(&Minv[i * NP + cm[0]]);
+            if (mat[0]) z[0][i] = v.x;
+            if (mat[CPL - 1]) z[CPL - 1][i] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < N; ++i) z[0][i] = Minv[i * NP + cm[0]];
+        }
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-          const double gk = G[c * NP + k];
+          double gk[CPL];
+#pragma unroll
+          for (int cl = 0; cl < CPL; ++cl) gk[cl] = G[k * NP + cm[cl]];   // G[c][k], transposed storage
 #pragma unroll
           for (int q2 = 0; q2 < NP / 2; ++q2) {
             const double2 v = ld2(&Cs[k * NP + 2 * q2]);
-            z[2 * q2] = fma(v.x, gk, z[2 * q2]);
-            if (2 * q2 + 1 < N) z[2 * q2 + 1] = fma(v.y, gk, z[2 * q2 + 1]);   // Sigma_t[:, c]
+#pragma unroll
+            for (int cl = 0; cl < CPL; ++cl) {
+              if (mat[cl]) {
+                z[cl][2 * q2] = fma(v.x, gk[cl], z[cl][2 * q2]);
+                if (2 * q2 + 1 < N) z[cl][2 * q2 + 1] = fma(v.y, gk[cl], z[cl][2 * q2 + 1]);   // Sigma_t[:, c]
+              }
+            }
           }
         }
       }
     }
     // ---- emit statistics for time t -----------------------------------------------------------
-    if (vec) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) mu_s[i] = z[i];
-    } else if (smp) {
+    for (int cl = 0; cl < CPL; ++cl) {
+      if (vec[cl]) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) xs[s * NP + i] = z[i];
+        for (int i = 0; i < N; ++i) mu_s[i] = z[cl][i];
+      } else if (smp[cl]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) xs[sx[cl] * NP + i] = z[cl][i];
+      }
     }
     __syncwarp();
-    if (mat && save && valid) {
-      double* sg = stash + (size_t)t * RS + (3 * N + 1 + S) * NP;
+    const size_t bt = (size_t)b * T + t;
+    const bool first = (t == 0), lastt = (t == T - 1);
 #pragma unroll
-      for (int i = 0; i < N; ++i) sg[i * NP + c] = z[i];   // Sigma_t[:, c]
-    }
-    if (mat) {
-      const double mu_c = mu_s[c];
-      const size_t bt = (size_t)b * T + t;
-      const bool first = (t == 0), lastt = (t == T - 1);
-      // hot path: running sums only
-      double diag = 0.0;
-      if (!first && !lastt) {
+    for (int cl = 0; cl < CPL; ++cl) {
+      if (mat[cl] && save && valid) {
+        double* sg = stash + (size_t)t * RS + (3 * N + 1 + S) * NP;
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          const double mi = mu_s[i];
-          const double exx = fma(mi, mu_c, z[i]);           // E[x_t x_t'][i][c]
-          if (i == c) diag = exx;
-          acc_xxn[i] = fma(mi, mun_c, acc_xxn[i]);
-          acc_mid[i] += exx;
+        for (int i = 0; i < N; ++i) sg[i * NP + c[cl]] = z[cl][i];   // Sigma_t[:, c]
+      }
+      if (mat[cl]) {
+        const int cc_ = c[cl];
+        const double mu_c = mu_s[cc_];
+        // hot path: running sums only
+        double diag = 0.0;
+        if (!first && !lastt) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            const double mi = mu_s[i];
+            const double exx = fma(mi, mu_c, z[cl][i]);           // E[x_t x_t'][i][c]
+            if (i == cc_) diag = exx;
+            acc_xxn[cl][i] = fma(mi, mun_c[cl], acc_xxn[cl][i]);
+            acc_mid[cl][i] += exx;
+          }
+        } else {
+          // first / last time step: E_init, the end corrections of the pair sums
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            const double mi = mu_s[i];
+            const double exx = fma(mi, mu_c, z[cl][i]);
+            if (i == cc_) diag = exx;
+            if (!lastt) acc_xxn[cl][i] = fma(mi, mun_c[cl], acc_xxn[cl][i]);
+            if (valid) {
+              const size_t o = (size_t)b * NN + i * N + cc_;
+              if (lastt && p.E_pair_xnxn) p.E_pair_xnxn[o] = (T > 1) ? exx : 0.0;
+              if (first) {
+                if (p.E_init_xx) p.E_init_xx[o] = exx;
+                if (p.E_pair_xx) p.E_pair_xx[o] = (T > 1) ? acc_mid[cl][i] + exx : 0.0;
+                if (p.E_pair_xxn) p.E_pair_xxn[o] = acc_xxn[cl][i];
+                if (p.E_pair_xnxn && T > 1) p.E_pair_xnxn[o] = (lastt ? 0.0 : p.E_pair_xnxn[o]) + acc_mid[cl][i];
+              }
+            }
+          }
+          if (first && valid && p.E_init_x) p.E_init_x[(size_t)b * N + cc_] = mu_c;
         }
-      } else {
-        // first / last time step: E_init, the end corrections of the pair sums
+        if (valid) {
+          if (p.E_node_x) p.E_node_x[bt * N + cc_] = mu_c;
+          if (p.E_node_xx) p.E_node_xx[bt * N + cc_] = diag;
+          if (p.samples)
+            for (int ss = 0; ss < S; ++ss) p.samples[(bt * S + ss) * N + cc_] = xs[ss * NP + cc_];
+          if (p.Exx_t) {   // per-time second moments (inhomogeneous E_pair): cold path
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          const double mi = mu_s[i];
-          const double exx = fma(mi, mu_c, z[i]);
-          if (i == c) diag = exx;
-          if (!lastt) acc_xxn[i] = fma(mi, mun_c, acc_xxn[i]);
-          if (valid) {
-            const size_t o = (size_t)b * NN + i * N + c;
-            if (lastt && p.E_pair_xnxn) p.E_pair_xnxn[o] = (T > 1) ? exx : 0.0;
-            if (first) {
-              if (p.E_init_xx) p.E_init_xx[o] = exx;
-              if (p.E_pair_xx) p.E_pair_xx[o] = (T > 1) ? acc_mid[i] + exx : 0.0;
-              if (p.E_pair_xxn) p.E_pair_xxn[o] = acc_xxn[i];
-              if (p.E_pair_xnxn && T > 1) p.E_pair_xnxn[o] = (lastt ? 0.0 : p.E_pair_xnxn[o]) + acc_mid[i];
+            for (int i = 0; i < N; ++i) {
+              p.Exx_t[bt * NN + i * N + cc_] = fma(mu_s[i], mu_c, z[cl][i]);
+              if (!lastt && p.Exxn_t)
+                p.Exxn_t[((size_t)b * (T - 1) + t) * NN + i * N + cc_] = fma(mu_s[i], mun_c[cl], Cs[cc_ * NP + i]);
             }
           }
         }
-        if (first && valid && p.E_init_x) p.E_init_x[(size_t)b * N + c] = mu_c;
+        mun_c[cl] = mu_c;
       }
-      if (valid) {
-        if (p.E_node_x) p.E_node_x[bt * N + c] = mu_c;
-        if (p.E_node_xx) p.E_node_xx[bt * N + c] = diag;
-        if (p.samples)
-          for (int ss = 0; ss < S; ++ss) p.samples[(bt * S + ss) * N + c] = xs[ss * NP + c];
-        if (p.Exx_t) {   // per-time second moments (inhomogeneous E_pair): cold path
-#pragma unroll
-          for (int i = 0; i < N; ++i) {
-            p.Exx_t[bt * NN + i * N + c] = fma(mu_s[i], mu_c, z[i]);
-            if (!lastt && p.Exxn_t)
-              p.Exxn_t[((size_t)b * (T - 1) + t) * NN + i * N + c] = fma(mu_s[i], mun_c, Cs[c * NP + i]);
-          }
-        }
-      }
-      mun_c = mu_c;
     }
     __syncwarp();
     if (t >= 2 && t < T - 1) fetch(t - 2, T - t);   // the slot just consumed is free: prefetch

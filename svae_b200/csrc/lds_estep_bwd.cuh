@@ -54,7 +54,7 @@ __host__ __device__ inline int lds_bwd_tile_doubles(int N, int S) {
 }
 
 template <int N, int LPS>
-__global__ void __launch_bounds__(32, 6) lds_estep_bwd_kernel(const LdsBwdParams p) {
+__global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams p) {
   constexpr int SPW = 32 / LPS;
   constexpr int NP = lds_np(N);
   constexpr int NN = N * N;
@@ -67,7 +67,6 @@ __global__ void __launch_bounds__(32, 6) lds_estep_bwd_kernel(const LdsBwdParams
   const long long b = valid ? seq : (long long)p.B - 1;
   const bool mat = c < N, vec = c == N, smp = (c > N) && (c <= N + S);
   const int s = smp ? c - N - 1 : 0;
-  const int cm = mat ? c : 0;
   const int RS = lds_record_stride(N, S, true);
   const int REC = (3 * N + 1 + S) * NP;
   const int SLOT = REC + N * NP;
@@ -211,17 +210,17 @@ __global__ void __launch_bounds__(32, 6) lds_estep_bwd_kernel(const LdsBwdParams
         double C[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) sig[i] = SigN[i * NP + c];   // Sigma_{t+1}[:, c] (symmetric)
-        // C[:,c] = G Sigma_{t+1}[:,c]
+        // C[:,c] = G Sigma_{t+1}[:,c]   (G is stored transposed: G[k*NP+i] = G_t[i][k])
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          double acc = 0.0;
+        for (int i = 0; i < N; ++i) C[i] = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
 #pragma unroll
           for (int q2 = 0; q2 < NP / 2; ++q2) {
-            const double2 g = ld2(&G[i * NP + 2 * q2]);
-            acc = fma(g.x, sig[2 * q2], acc);
-            if (2 * q2 + 1 < N) acc = fma(g.y, sig[2 * q2 + 1], acc);
+            const double2 g = ld2(&G[k * NP + 2 * q2]);
+            C[2 * q2] = fma(g.x, sig[k], C[2 * q2]);
+            if (2 * q2 + 1 < N) C[2 * q2 + 1] = fma(g.y, sig[k], C[2 * q2 + 1]);
           }
-          C[i] = acc;
         }
         // Cb[:,c] = B[:,c] + Sb G[:,c]
 #pragma unroll
@@ -229,7 +228,7 @@ __global__ void __launch_bounds__(32, 6) lds_estep_bwd_kernel(const LdsBwdParams
           Cb[i] = per_t ? p.g_Exxn_t[((size_t)b * (T - 1) + t) * NN + i * N + c] : Bm[i * NP + c];
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-          const double gk = G[k * NP + c];
+          const double gk = G[c * NP + k];   // G_t[k][c]
 #pragma unroll
           for (int q2 = 0; q2 < NP / 2; ++q2) {
             const double2 v = ld2(&SbS[k * NP + 2 * q2]);
@@ -277,22 +276,24 @@ __global__ void __launch_bounds__(32, 6) lds_estep_bwd_kernel(const LdsBwdParams
 #pragma unroll
         for (int i = 0; i < N; ++i) GbS[c * NP + i] = Gb[i];
       }
-      // carry: (G' Cb)[:,c] / (G' vb)
+      // carry: (G' Cb)[i] = sum_k G_t[k][i] Cb[k] = sum_k G[i*NP+k] Cb[k]   (two partial sums per output)
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
+      for (int i = 0; i < N; ++i) {
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int q2 = 0; q2 < NP / 2; ++q2) {
-          const double2 g = ld2(&G[k * NP + 2 * q2]);
-          Sbn[2 * q2] = fma(g.x, Cb[k], Sbn[2 * q2]);
-          if (2 * q2 + 1 < N) Sbn[2 * q2 + 1] = fma(g.y, Cb[k], Sbn[2 * q2 + 1]);
+          const double2 g = ld2(&G[i * NP + 2 * q2]);
+          s0 = fma(g.x, Cb[2 * q2], s0);
+          if (2 * q2 + 1 < N) s1 = fma(g.y, Cb[2 * q2 + 1], s1);
         }
+        Sbn[i] = s0 + s1;
       }
       __syncwarp();   // GbS visible
       if (mat) {
         // inner[:,c] = (Gb G')[:,c] = sum_k Gb[:,k] G[c][k]
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-          const double gck = G[c * NP + k];
+          const double gck = G[k * NP + c];   // G_t[c][k]
 #pragma unroll
           for (int q2 = 0; q2 < NP / 2; ++q2) {
             const double2 v = ld2(&GbS[k * NP + 2 * q2]);
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(32, 6) lds_estep_bwd_kernel(const LdsBwdParams
         for (int i = 0; i < N; ++i) T1[i] = 0.0;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-          const double gck = G[c * NP + k];
+          const double gck = G[k * NP + c];   // G_t[c][k]
 #pragma unroll
           for (int q2 = 0; q2 < NP / 2; ++q2) {
             const double2 v = ld2(&PbS[k * NP + 2 * q2]);
@@ -439,22 +440,28 @@ __global__ void __launch_bounds__(32, 6) lds_estep_bwd_kernel(const LdsBwdParams
           }
         }
         const double m_c = mrow[c];
+        // (G T1)[i] = sum_k G_t[i][k] T1[k] and (G hb)[i]: axpy over k on the transposed storage
+        double gt1[N], ghb[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          double acc = 0.0, ghb = 0.0;
+        for (int i = 0; i < N; ++i) gt1[i] = ghb[i] = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const double hk = hbS[k];
 #pragma unroll
           for (int q2 = 0; q2 < NP / 2; ++q2) {
-            const double2 g = ld2(&G[i * NP + 2 * q2]);
-            const double2 h2 = ld2(&hbS[2 * q2]);
-            acc = fma(g.x, T1[2 * q2], acc);
-            ghb = fma(g.x, h2.x, ghb);
+            const double2 g = ld2(&G[k * NP + 2 * q2]);
+            gt1[2 * q2] = fma(g.x, T1[k], gt1[2 * q2]);
+            ghb[2 * q2] = fma(g.x, hk, ghb[2 * q2]);
             if (2 * q2 + 1 < N) {
-              acc = fma(g.y, T1[2 * q2 + 1], acc);
-              ghb = fma(g.y, h2.y, ghb);
+              gt1[2 * q2 + 1] = fma(g.y, T1[k], gt1[2 * q2 + 1]);
+              ghb[2 * q2 + 1] = fma(g.y, hk, ghb[2 * q2 + 1]);
             }
           }
-          Pn[i] += acc - ghb * m_c;          // Q + G Pb G' - (G hb) m'
-          if (i == c) hn_c += ghb;           // f + G hb
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          Pn[i] += gt1[i] - ghb[i] * m_c;          // Q + G Pb G' - (G hb) m'
+          if (i == c) hn_c += ghb[i];               // f + G hb
         }
       }
 #pragma unroll

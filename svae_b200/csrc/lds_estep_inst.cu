@@ -1,10 +1,5 @@
 // One translation unit per latent dimension: compiled with -DSVAE_N=<n> for n = 1..SVAE_LDS_MAX_N so
 // the fully-unrolled kernels build in parallel.  Exposes svae::lds_fwd_launch_n<n>().
-// register cap: for n <= 10 the whole metric batch (2048 one-warp CTAs at B = 4096) is resident in ONE
-// wave at 128 registers/thread (16 CTAs/SM); larger n needs the registers more than the occupancy.
-#if !defined(SVAE_LDS_MAXREG) && !defined(SVAE_LDS_MINB) && SVAE_N <= 10
-#define SVAE_LDS_MAXREG 128
-#endif
 #include "lds_estep.cuh"
 #include "launch.h"
 
@@ -43,7 +38,7 @@ static cudaError_t stage_const_J12(const double* J12, cudaStream_t stream, int* 
                                  cudaMemcpyDeviceToDevice, stream);
 }
 
-template <int N, int LPS, bool INHOMOG>
+template <int N, int CPL, int LPS, bool INHOMOG>
 static cudaError_t launch_one(const LdsFwdParams& p, cudaStream_t stream) {
   constexpr int SPW = 32 / LPS;
   const int warps_per_cta = 1;
@@ -51,7 +46,7 @@ static cudaError_t launch_one(const LdsFwdParams& p, cudaStream_t stream) {
   const long long grid = (tiles + warps_per_cta - 1) / warps_per_cta;
   const size_t smem = sizeof(double) *
       (3 * N * lds_np(N) + (size_t)warps_per_cta * SPW * lds_tile_doubles(N, p.S, INHOMOG));
-  auto kern = lds_estep_fwd_kernel<N, LPS, INHOMOG>;
+  auto kern = lds_estep_fwd_kernel<N, CPL, LPS, INHOMOG>;
   {
     // many small CTAs per SM: optional shared-memory carve-out hint (percent), SVAE_LDS_CARVEOUT
     static bool carved = false;
@@ -86,16 +81,32 @@ static cudaError_t launch_one(const LdsFwdParams& p, cudaStream_t stream) {
 #define SVAE_CAT_(a, b) a##b
 #define SVAE_CAT(a, b) SVAE_CAT_(a, b)
 
-cudaError_t SVAE_CAT(lds_fwd_launch_n, SVAE_N)(const LdsFwdParams& p, int lps, bool inhomog, cudaStream_t stream) {
+template <int N, int CPL, int LPS>
+static cudaError_t launch_if_fits(const LdsFwdParams& p, bool inhomog, cudaStream_t stream) {
+  if constexpr (CPL * LPS >= N + 1) {
+    return inhomog ? launch_one<N, CPL, LPS, true>(p, stream) : launch_one<N, CPL, LPS, false>(p, stream);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+}
+
+// cpl: columns per lane (1 or 2); lps: lanes per sequence tile, with cpl * lps >= n + 1 + S
+cudaError_t SVAE_CAT(lds_fwd_launch_n, SVAE_N)(const LdsFwdParams& p, int cpl, int lps, bool inhomog, cudaStream_t stream) {
   constexpr int N = SVAE_N;
-  if (lps == 16) {
-    if constexpr (N + 1 <= 16) {
-      return inhomog ? launch_one<N, 16, true>(p, stream) : launch_one<N, 16, false>(p, stream);
-    } else {
-      return cudaErrorInvalidValue;
+#ifdef SVAE_LDS_ENABLE_CPL2   // two column slots per lane: measured slower than CPL = 1 on B200
+  if (cpl == 2) {
+    switch (lps) {
+      case 4: return launch_if_fits<N, 2, 4>(p, inhomog, stream);
+      case 8: return launch_if_fits<N, 2, 8>(p, inhomog, stream);
+      case 16: return launch_if_fits<N, 2, 16>(p, inhomog, stream);
+      default: return launch_if_fits<N, 2, 32>(p, inhomog, stream);
     }
   }
-  return inhomog ? launch_one<N, 32, true>(p, stream) : launch_one<N, 32, false>(p, stream);
+#else
+  if (cpl == 2) return cudaErrorInvalidValue;
+#endif
+  if (lps == 16) return launch_if_fits<N, 1, 16>(p, inhomog, stream);
+  return launch_if_fits<N, 1, 32>(p, inhomog, stream);
 }
 
 }  // namespace svae

@@ -88,7 +88,7 @@ def _canonical_pair_params(pair_params, B, T, n, device):
 
 def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=None,
                       per_t_pair_stats=False, want_stats=True, generator=None, check_status=False,
-                      save_for_bwd=False):
+                      save_for_bwd=False, buffers=None):
     """One launch of the fused filter + smoother + sampler kernel.  Returns a dict of raw tensors.
     With save_for_bwd the workspace keeps what lds_estep_backward needs (returned as out["workspace"])."""
     h_any = node_params[1]
@@ -119,19 +119,30 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
     L = _lib.lib()
     flags = (_lib.SVAE_LDS_PER_T_PAIR_STATS if per_t_pair_stats else 0) | (_lib.SVAE_LDS_SAVE_FOR_BWD if save_for_bwd else 0) \
         | (_lib.SVAE_LDS_INIT_PER_SEQ if init_per_seq else 0)
-    new = lambda *shape: torch.empty(shape, dtype=torch.float64, device=device)
+    _pool = dict(buffers) if buffers else {}
+
+    def new(*shape, name=None):
+        t = _pool.get(name) if name else None
+        if t is not None and tuple(t.shape) == tuple(shape):
+            return t
+        return torch.empty(shape, dtype=torch.float64, device=device)
     out = dict(B=B, T=T, n=n, S=S, batched=batched, eps=eps)
-    out["lognorm"] = new(B)
-    out["E_node_xx"], out["E_node_x"] = new(B, T, n), new(B, T, n)
-    out["samples"] = new(B, T, S, n) if S > 0 else None
+    out["lognorm"] = new(B, name="lognorm")
+    out["E_node_xx"], out["E_node_x"] = new(B, T, n, name="E_node_xx"), new(B, T, n, name="E_node_x")
+    out["samples"] = new(B, T, S, n, name="samples") if S > 0 else None
     if want_stats:
-        out["E_init_xx"], out["E_init_x"] = new(B, n, n), new(B, n)
-        out["E_pair_xx"], out["E_pair_xxn"], out["E_pair_xnxn"] = new(B, n, n), new(B, n, n), new(B, n, n)
+        out["E_init_xx"], out["E_init_x"] = new(B, n, n, name="E_init_xx"), new(B, n, name="E_init_x")
+        out["E_pair_xx"], out["E_pair_xxn"], out["E_pair_xnxn"] = \
+            new(B, n, n, name="E_pair_xx"), new(B, n, n, name="E_pair_xxn"), new(B, n, n, name="E_pair_xnxn")
     if per_t_pair_stats:
         out["Exx_t"], out["Exxn_t"] = new(B, T, n, n), new(B, max(T - 1, 0), n, n)
-    status = torch.zeros(1, dtype=torch.int32, device=device)
+    status = _pool.get("status")
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=device)
     wbytes = L.svae_lds_estep_workspace_bytes(B, T, n, S, flags)
-    work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=device)
+    work = _pool.get("workspace")
+    if work is None or work.numel() < wbytes:
+        work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=device)
     g = out.get
     P = _lib.ptr
     code = L.svae_lds_estep_fwd(
@@ -158,15 +169,17 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
     return out
 
 
-def lds_reduce_global_stats(o):
+def lds_reduce_global_stats(o, out=None, work=None):
     """sum over the minibatch of [E_init_xx | E_init_x | E_pair_xx | E_pair_xxn | E_pair_xnxn | lognorm]
     (flat(stats) of svae.py:33-34 plus the normaliser) with the deterministic two-stage CUDA reduction."""
     B, n = o["B"], o["n"]
     dev = o["lognorm"].device
     L = _lib.lib()
-    out = torch.empty(4 * n * n + n + 1, dtype=torch.float64, device=dev)
+    if out is None:
+        out = torch.empty(4 * n * n + n + 1, dtype=torch.float64, device=dev)
     wbytes = L.svae_lds_reduce_stats_workspace_bytes(n)
-    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    if work is None:
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
     P = _lib.ptr
     code = L.svae_lds_reduce_stats(B, n, P(o["E_init_xx"]), P(o["E_init_x"]), P(o["E_pair_xx"]), P(o["E_pair_xxn"]),
                                    P(o["E_pair_xnxn"]), P(o["lognorm"]), P(out), ctypes.c_void_p(work.data_ptr()),
@@ -175,46 +188,80 @@ def lds_reduce_global_stats(o):
     return out
 
 
-def lds_estep_host(natparam, node_host, num_samples, out_host, chunks=4, generator=None, device=None):
+class LdsHostPipeline:
     """End-to-end E-step for HOST-resident minibatches: the public call a data loader would make.
 
-    node_host = (J_node, h_node) pinned CPU tensors (B,T,n); out_host = dict of pinned CPU tensors
-    {"samples" (B,T,S,n), "E_node_xx" (B,T,n), "E_node_x" (B,T,n), "lognorm" (B)} that are filled in place.
-    The batch is cut into `chunks` pieces that flow H2D copy -> fused E-step kernel -> D2H copy on rotating
-    streams, so PCIe transfers in both directions overlap the kernels of neighbouring chunks.  Returns the
-    device tensor sum_b [E_init | E_pair | lognorm] (see lds_reduce_global_stats)."""
-    init_params, pair_params = natparam
-    device = device or torch.device("cuda", torch.cuda.current_device())
-    J_h, h_h = node_host
-    B, T, n = h_h.shape
+    All device buffers (inputs, noise, outputs, stash workspace) and the streams are allocated ONCE for a
+    given (B, T, n, S); each call cuts the batch into `chunks` pieces that flow
+        pinned host -> H2D copy -> fused E-step kernel -> statistics reduction -> D2H copy -> pinned host
+    on rotating streams, so PCIe transfers in both directions overlap the kernels of neighbouring chunks.
+    """
+
+    def __init__(self, B, T, n, S, chunks=3, device=None):
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.B, self.T, self.n, self.S, self.chunks = B, T, n, S, chunks
+        self.bounds = [(B * k) // chunks for k in range(chunks + 1)]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(min(3, chunks))]
+        new = lambda *s: torch.empty(s, dtype=torch.float64, device=self.device)
+        L = _lib.lib()
+        self.bufs = []
+        for k in range(chunks):
+            b = self.bounds[k + 1] - self.bounds[k]
+            d = dict(J=new(b, T, n), h=new(b, T, n), eps=new(b, T, S, n) if S else None,
+                     lognorm=new(b), E_node_xx=new(b, T, n), E_node_x=new(b, T, n),
+                     samples=new(b, T, S, n) if S else None, E_init_xx=new(b, n, n), E_init_x=new(b, n),
+                     E_pair_xx=new(b, n, n), E_pair_xxn=new(b, n, n), E_pair_xnxn=new(b, n, n),
+                     status=torch.zeros(1, dtype=torch.int32, device=self.device),
+                     workspace=torch.empty(max(L.svae_lds_estep_workspace_bytes(b, T, n, S, 0), 16), dtype=torch.uint8,
+                                           device=self.device),
+                     acc=new(4 * n * n + n + 1),
+                     rwork=torch.empty(L.svae_lds_reduce_stats_workspace_bytes(n), dtype=torch.uint8, device=self.device))
+            self.bufs.append(d)
+        self.acc = new(4 * n * n + n + 1)
+
+    def run(self, natparam, node_host, out_host, generator=None):
+        """node_host = (J_node, h_node) pinned CPU tensors (B,T,n); out_host = dict of pinned CPU tensors
+        {"samples", "E_node_xx", "E_node_x", "lognorm"} filled in place.  Returns the device tensor
+        sum_b [E_init | E_pair | lognorm] (see lds_reduce_global_stats)."""
+        init_params, pair_params = natparam
+        J_h, h_h = node_host
+        cur = torch.cuda.current_stream(self.device)
+        S = self.S
+        for k, d in enumerate(self.bufs):
+            lo, hi = self.bounds[k], self.bounds[k + 1]
+            if hi == lo:
+                continue
+            st = self.streams[k % len(self.streams)]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                d["J"].copy_(J_h[lo:hi], non_blocking=True)
+                d["h"].copy_(h_h[lo:hi], non_blocking=True)
+                if S:
+                    d["eps"].normal_(generator=generator)
+                o = lds_estep_forward(init_params, pair_params, (d["J"], d["h"]), S, d["eps"], buffers=d)
+                lds_reduce_global_stats(o, out=d["acc"], work=d["rwork"])
+                if S:
+                    out_host["samples"][lo:hi].copy_(o["samples"], non_blocking=True)
+                out_host["E_node_xx"][lo:hi].copy_(o["E_node_xx"], non_blocking=True)
+                out_host["E_node_x"][lo:hi].copy_(o["E_node_x"], non_blocking=True)
+                out_host["lognorm"][lo:hi].copy_(o["lognorm"], non_blocking=True)
+        self.acc.zero_()
+        for k, d in enumerate(self.bufs):
+            if self.bounds[k + 1] > self.bounds[k]:
+                cur.wait_stream(self.streams[k % len(self.streams)])
+                self.acc += d["acc"]
+        return self.acc
+
+
+def lds_estep_host(natparam, node_host, num_samples, out_host, chunks=3, generator=None, device=None, _plans={}):
+    """Functional wrapper around LdsHostPipeline (plans are cached per shape)."""
+    B, T, n = node_host[1].shape
     S = int(num_samples) if num_samples else 0
-    bounds = [(B * k) // chunks for k in range(chunks + 1)]
-    streams = [torch.cuda.Stream(device=device) for _ in range(min(3, chunks))]
-    cur = torch.cuda.current_stream(device)
-    acc = torch.zeros(4 * n * n + n + 1, dtype=torch.float64, device=device)
-    parts = []
-    for k in range(chunks):
-        lo, hi = bounds[k], bounds[k + 1]
-        if hi == lo:
-            continue
-        st = streams[k % len(streams)]
-        st.wait_stream(cur)
-        with torch.cuda.stream(st):
-            dJ = J_h[lo:hi].to(device, non_blocking=True)
-            dh = h_h[lo:hi].to(device, non_blocking=True)
-            o = lds_estep_forward(init_params, pair_params, (dJ, dh), S, None, generator=generator)
-            parts.append((st, lds_reduce_global_stats(o)))
-            if S:
-                out_host["samples"][lo:hi].copy_(o["samples"], non_blocking=True)
-            out_host["E_node_xx"][lo:hi].copy_(o["E_node_xx"], non_blocking=True)
-            out_host["E_node_x"][lo:hi].copy_(o["E_node_x"], non_blocking=True)
-            out_host["lognorm"][lo:hi].copy_(o["lognorm"], non_blocking=True)
-            for t_ in (dJ, dh, o["E_node_xx"], o["E_node_x"], o["lognorm"]) + ((o["samples"],) if S else ()):
-                t_.record_stream(st)
-    for st, part in parts:
-        cur.wait_stream(st)
-        acc += part
-    return acc
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    key = (B, T, n, S, chunks, str(device))
+    if key not in _plans:
+        _plans[key] = LdsHostPipeline(B, T, n, S, chunks, device)
+    return _plans[key].run(natparam, node_host, out_host, generator)
 
 
 def lds_estep_backward(o, g):

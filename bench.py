@@ -270,7 +270,7 @@ def run_ours(args):
     acc_host = torch.empty((4 * n * n + n + 1,), dtype=torch.float64).pin_memory()
 
     def e2e_step(i):
-        acc = K.lds_estep_host((gi, gp), (h_nJ, h_nh), S, out_host, chunks=3, generator=gen, device=dev)
+        acc = K.lds_estep_host((gi, gp), (h_nJ, h_nh), S, out_host, chunks=4, generator=gen, device=dev)
         if world > 1:
             dist.all_reduce(acc)
         acc_host.copy_(acc, non_blocking=True)
@@ -354,7 +354,7 @@ def run_ours(args):
                         step="fused filter+smoother+sampler kernel, 2-stage minibatch reduction of the global statistics"
                              + (", NCCL all-reduce of the %d-double accumulator" % (4 * n * n + n + 1) if world > 1 else "")),
             e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                     ms_per_step=e2e_ms, note="pinned host buffers, 3 chunks pipelined over 3 streams; noise drawn on device"),
+                     ms_per_step=e2e_ms, note="pinned host buffers, 4 chunks pipelined over 3 streams, persistent device buffers; noise drawn on device"),
             gpu_launches=int(launches),
             clocks=clk.summary(),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,

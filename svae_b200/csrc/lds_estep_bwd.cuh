@@ -50,7 +50,8 @@ __host__ __device__ inline int lds_bwd_tile_doubles(int N, int S) {
   const int NP = lds_np(N);
   const int REC = (3 * N + 1 + S) * NP;   // G | W | m | b | K   (Sigma_{t+1} is fetched separately)
   return 2 /*mbarriers*/ + 2 * (REC + N * NP) /*ring: record + Sigma_{t+1}*/ + 4 * N * NP /*XA XB X0 Bm*/ +
-         3 * N * NP /*SbS CbS GbS*/ + (4 + 2 * (1 + S)) * NP /*mean window(3), vtmp, vbS(1+S), xn(S) ~*/ + 2 * NP;
+         3 * N * NP /*SbS CbS GbS*/ + (4 + 1 + (1 + S) + 2) * NP /*mean window(4), vtmp, vbS, wm, us*/ +
+         2 * (2 + 3 * S) * NP /*input ring: g_node_x | g_node_xx | g_samples | x_{t+1} | eps*/;
 }
 
 template <int N, int LPS>
@@ -81,12 +82,13 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
   double* SbS = Bm + N * NP;             // SbS[k*NP+i] = Sb[i][k]
   double* CbS = SbS + N * NP;            // CbS[k*NP+i] = Cb[i][k]
   double* GbS = CbS + N * NP;            // GbS[k*NP+i] = Gb[i][k]   (sweep 2: Pb)
-  double* muw = GbS + N * NP;            // mean window: slot (t mod 3) holds mu_t
-  double* vtmp = muw + 3 * NP;           // per-lane scalars exchanged through smem
+  double* muw = GbS + N * NP;            // mean window: slot (t mod 4) holds mu_t
+  double* vtmp = muw + 4 * NP;           // per-lane scalars exchanged through smem
   double* vbS = vtmp + NP;               // vbS[v*NP+i]: vb of vector column v (0 = mu, 1+s = x^s)
-  double* xn = vbS + (1 + S) * NP;       // x_{t+1}[s][i]
-  double* wm = xn + S * NP;              // W mb
+  double* wm = vbS + (1 + S) * NP;       // W mb
   double* us = wm + NP;                  // u = K xb_s
+  const int IN = (2 + 3 * S) * NP;       // per-step inputs staged one step ahead by cp.async:
+  double* iring = us + NP;               //   2 x { g_node_x | g_node_xx | g_samples[S] | x_{t+1}[S] | eps_t[S] }
 
   if (c == 0) {
     mbar_init(&bars[0], 1);
@@ -125,11 +127,26 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
   fetch1(0);
   if (T > 1) fetch1(1);
 
-  // mean window
-  if (mat) {
-    muw[0 * NP + c] = Ex[c];
-    if (T > 1) muw[1 * NP + c] = Ex[N + c];
-  }
+  // per-step inputs (cotangents, next sample, noise) and the mean window arrive by cp.async one step ahead
+  for (int e = c; e < 2 * IN; e += LPS) iring[e] = 0.0;
+  __syncwarp();
+  auto stage_in = [&](int t) {    // inputs of step t -> input-ring slot t&1;  mu_{t+1} -> window slot (t+1)%4
+    if (mat && t < T) {
+      double* dst = iring + (t & 1) * IN;
+      const size_t bt = (size_t)b * T + t;
+      if (p.g_E_node_x) cp_async8(dst + c, p.g_E_node_x + bt * N + c);
+      if (p.g_E_node_xx) cp_async8(dst + NP + c, p.g_E_node_xx + bt * N + c);
+      for (int ss = 0; ss < S; ++ss) {
+        if (p.g_samples) cp_async8(dst + (2 + ss) * NP + c, p.g_samples + (bt * S + ss) * N + c);
+        if (t + 1 < T) cp_async8(dst + (2 + S + ss) * NP + c, p.samples + ((bt + 1) * S + ss) * N + c);
+        cp_async8(dst + (2 + 2 * S + ss) * NP + c, p.eps + (bt * S + ss) * N + c);
+      }
+      if (t + 1 < T) cp_async8(muw + ((t + 1) % 4) * NP + c, Ex + (size_t)(t + 1) * N + c);
+    }
+    cp_async_commit();
+  };
+  if (mat) cp_async8(muw + c, Ex + c);
+  stage_in(0);
 
   double Sb[N];    // mat: column c of Sb;  vec/smp: the vector cotangent vb
 #pragma unroll
@@ -144,17 +161,18 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
     const double* mrow = rec + 2 * N * NP;
     const double* K = rec + (2 * N + 1 + S) * NP;
     const double* SigN = rec + REC;
-    const double* mu_t = muw + (t % 3) * NP;
-    const double* mu_n = muw + ((t + 1) % 3) * NP;
-    const double* mu_p = muw + ((t + 2) % 3) * NP;
-    // stage x_{t+1}
-    if (mat && !last)
-      for (int ss = 0; ss < S; ++ss) xn[ss * NP + c] = p.samples[(((size_t)b * T + t + 1) * S + ss) * N + c];
+    const double* mu_t = muw + (t % 4) * NP;
+    const double* mu_n = muw + ((t + 1) % 4) * NP;
+    const double* mu_p = muw + ((t + 3) % 4) * NP;
+    const double* inp = iring + (t & 1) * IN;     // this step's staged inputs
+    const double* xn = inp + (2 + S) * NP;        // x_{t+1}[s][i]
+    cp_async_wait<0>();
     __syncwarp();
+    stage_in(t + 1);                               // lands while this step computes
 
     // ---- seeds -----------------------------------------------------------------------------
     if (mat) {
-      double seedv = p.g_E_node_x ? p.g_E_node_x[((size_t)b * T + t) * N + c] : 0.0;
+      double seedv = inp[c];
       if (first && p.g_E_init_x) seedv += p.g_E_init_x[(size_t)b * N + c];
       double am = 0.0, bn = 0.0, bp = 0.0;
 #pragma unroll
@@ -164,7 +182,7 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
           const size_t o = ((size_t)b * T + t) * NN;
           a_ic += 0.5 * (p.g_Exx_t[o + i * N + c] + p.g_Exx_t[o + c * N + i]);
         }
-        if (i == c && p.g_E_node_xx) a_ic += p.g_E_node_xx[((size_t)b * T + t) * N + c];
+        if (i == c) a_ic += inp[NP + c];
         Sb[i] += a_ic;
         am = fma(a_ic, mu_t[i], am);                                   // (A_s mu_t)_c
         double bm_ci = Bm[c * NP + i], bm_ic = Bm[i * NP + c];
@@ -179,10 +197,8 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
 #pragma unroll
       for (int i = 0; i < N; ++i) SbS[c * NP + i] = Sb[i];
     } else if (smp) {
-      if (p.g_samples) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) Sb[i] += p.g_samples[(((size_t)b * T + t) * S + s) * N + i];
-      }
+      for (int i = 0; i < N; ++i) Sb[i] += inp[(2 + s) * NP + i];
     }
     __syncwarp();
     if (vec) {
@@ -353,7 +369,7 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
       }
       __syncwarp();
       if (mat) {
-        const double* ep = p.eps + (((size_t)b * T + t) * S + ss) * N;
+        const double* ep = inp + (2 + 2 * S + ss) * NP;
         // y_i = -eps_i ( sum_{j<i} u_j K[j][c] + u_i K[i][c] / 2 ),  then  Q[:,c] += K' y
         double run = 0.0;
 #pragma unroll
@@ -383,8 +399,7 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
 #pragma unroll
     for (int i = 0; i < N; ++i) Sb[i] = Sbn[i];
     __syncwarp();
-    // mean window: slot of mu_{t-1} is now free -> mu_{t+2};  ring slot t&1 is free -> fetch t+2
-    if (mat && t + 2 < T) muw[((t + 2) % 3) * NP + c] = Ex[(size_t)(t + 2) * N + c];
+    // ring slot t&1 is free -> fetch t+2
     if (t + 2 < T) fetch1(t + 2);
     __syncwarp();
   }

@@ -91,14 +91,15 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
     if (t + 1 < T) xn = act ? node[(size_t)(t + 1) * K + j] : NEG;
     abuf[j] = alpha;
     __syncwarp();
-    double pj = 0.0;
+    // four independent partial sums: the K-term dot product is a chain of K/4 dependent FMAs, not K
+    double pa[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int i2 = 0; i2 < LPS / 2; ++i2) {
       const double2 a2 = *reinterpret_cast<const double2*>(&abuf[2 * i2]);
-      pj = fma(a2.x, Pc[2 * i2], pj);
-      pj = fma(a2.y, Pc[2 * i2 + 1], pj);
+      pa[(2 * i2) & 3] = fma(a2.x, Pc[2 * i2], pa[(2 * i2) & 3]);
+      pa[(2 * i2 + 1) & 3] = fma(a2.y, Pc[2 * i2 + 1], pa[(2 * i2 + 1) & 3]);
     }
-    if (LPS == 1) pj = abuf[0] * Pc[0];
+    const double pj = (pa[0] + pa[1]) + (pa[2] + pa[3]);
     mf = tile_maxf<LPS>((float)x);
     e = act ? pj * exp(x - (double)mf) : 0.0;
     c = tile_sum<LPS>(e);
@@ -138,14 +139,14 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
     xc = act ? node[(size_t)t * K + j] : NEG;
     if (t > 0) an = act ? Ez[(size_t)(t - 1) * K + j] : 0.0;
     __syncwarp();
-    double bu = 0.0;
+    double pb[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int i2 = 0; i2 < LPS / 2; ++i2) {
       const double2 w2 = *reinterpret_cast<const double2*>(&wbuf[2 * i2]);
-      bu = fma(w2.x, Pr[2 * i2], bu);
-      bu = fma(w2.y, Pr[2 * i2 + 1], bu);
+      pb[(2 * i2) & 3] = fma(w2.x, Pr[2 * i2], pb[(2 * i2) & 3]);
+      pb[(2 * i2 + 1) & 3] = fma(w2.y, Pr[2 * i2 + 1], pb[(2 * i2 + 1) & 3]);
     }
-    if (LPS == 1) bu = wbuf[0] * Pr[0];
+    const double bu = (pb[0] + pb[1]) + (pb[2] + pb[3]);
     const double s = tile_sum<LPS>(at * bu);
     const double invs = 1.0 / s;
     if (act && valid) Ez[(size_t)t * K + j] = at * bu * invs;
@@ -157,7 +158,6 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
       O[2 * i2] = fma(a2.x, w, O[2 * i2]);
       O[2 * i2 + 1] = fma(a2.y, w, O[2 * i2 + 1]);
     }
-    if (LPS == 1) O[0] = fma(abuf[0], w, O[0]);
     beta = bu * invs;
     __syncwarp();
   }

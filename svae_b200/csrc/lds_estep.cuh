@@ -93,6 +93,9 @@ static __constant__ double c_J12[SVAE_LDS_CONST_SLOTS][SVAE_LDS_CONST_NN];
 // register budget (one warp per CTA).  CPL = 1, n <= 10: 128 registers so that 16 CTAs fit per SM (the whole
 // metric batch in one wave); CPL = 2 keeps two columns per lane in registers and needs the full file, with
 // four sequences per warp only 7 CTAs per SM are needed.
+#ifdef SVAE_LDS_MINB_OVERRIDE
+#define SVAE_LDS_MINB(N, CPL) SVAE_LDS_MINB_OVERRIDE
+#endif
 #ifndef SVAE_LDS_MINB
 #define SVAE_LDS_MINB(N, CPL) (((CPL) == 1 && (N) <= 10) ? 16 : 7)
 #endif

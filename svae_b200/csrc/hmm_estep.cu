@@ -42,7 +42,24 @@ __device__ __forceinline__ float tile_maxf(float v) {
   return v;
 }
 
-// flags: bit0 = forward only (logZ), else full E-step
+__device__ __forceinline__ double hmm_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// flags: bit0 = forward only (logZ), else full E-step.
+//
+// Latency structure: the per-step chain is  message -> shared memory -> K-term dot product -> next message.
+// Every normaliser is taken OFF that chain: the sum of the previous message is re-derived by each lane from the
+// very values it broadcasts for the dot product (no shuffle tree), is applied one step late (any positive
+// rescaling is legal, the logs are accounted exactly), and exp(node - max) of the NEXT step is computed while
+// the current dot product is in flight.  In the backward sweep E[z_t], the transition-count outer product and
+// the normaliser 1/s_t of step t are finished during step t-1.
 #ifndef SVAE_HMM_MINB32
 #define SVAE_HMM_MINB32 8
 #endif
@@ -50,7 +67,8 @@ template <int LPS>
 __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_estep_kernel(const HmmParams p) {
   constexpr int SPW = 32 / LPS;
   constexpr int LP = (LPS + 1) & ~1;
-  __shared__ __align__(16) double sbuf[SPW][2][LP < 2 ? 2 : LP];
+  constexpr int LQ = LP < 2 ? 2 : LP;
+  __shared__ __align__(16) double sbuf[SPW][8][LQ];
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPS, j = lane % LPS;
   const int K = p.K, T = p.T;
@@ -58,64 +76,73 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
   const bool valid = seq < p.B;
   const long long b = valid ? seq : (long long)p.B - 1;
   const bool act = j < K;
-  double* abuf = sbuf[sub][0];
-  double* wbuf = sbuf[sub][1];
   const bool fwd_only = (p.flags & 1) != 0;
+  const bool store = act && valid && !fwd_only;
 
   // global shift of log A so that P = exp(log A - gmax) <= 1
   float gmf = -INFINITY;
   for (int e = j; e < K * K; e += LPS) gmf = fmaxf(gmf, (float)p.log_A[e]);
   const double gmax = (double)tile_maxf<LPS>(gmf);
 
-  double Pc[LPS];   // column j of P (forward):  Pc[i] = P[i][j]
-#pragma unroll
-  for (int i = 0; i < LPS; ++i) Pc[i] = (act && i < K) ? exp(p.log_A[i * K + j] - gmax) : 0.0;
-
   const double* node = p.node + (size_t)b * T * K;
   double* Ez = p.Ez + (size_t)b * T * K;
   const double NEG = -1.0e300;
 
   // ------------------------------------ forward ---------------------------------------------
-  double x = act ? node[j] : NEG;
-  double xn = (act && T > 1) ? node[K + j] : NEG;
-  double a0 = act ? p.log_pi[j] + x : NEG;
-  float mf = tile_maxf<LPS>((float)a0);
-  double e = act ? exp(a0 - (double)mf) : 0.0;
-  double c = tile_sum<LPS>(e);
-  double alpha = e / c;
-  double logZ = (double)mf;
-  double cprod = c;
-  if (act && valid && !fwd_only) Ez[j] = alpha;
-  for (int t = 1; t < T; ++t) {
-    x = xn;
-    if (t + 1 < T) xn = act ? node[(size_t)(t + 1) * K + j] : NEG;
-    abuf[j] = alpha;
-    __syncwarp();
-    // four independent partial sums: the K-term dot product is a chain of K/4 dependent FMAs, not K
-    double pa[4] = {0.0, 0.0, 0.0, 0.0};
+  double logZ, cprod = 1.0, e, c, invc;
+  double x_last;   // node[T-1][j], reused by the backward sweep
+  {
+    double Pc[LPS];   // column j of P:  Pc[i] = P[i][j]
 #pragma unroll
-    for (int i2 = 0; i2 < LPS / 2; ++i2) {
-      const double2 a2 = *reinterpret_cast<const double2*>(&abuf[2 * i2]);
-      pa[(2 * i2) & 3] = fma(a2.x, Pc[2 * i2], pa[(2 * i2) & 3]);
-      pa[(2 * i2 + 1) & 3] = fma(a2.y, Pc[2 * i2 + 1], pa[(2 * i2 + 1) & 3]);
+    for (int i = 0; i < LPS; ++i) Pc[i] = (act && i < K) ? exp(p.log_A[i * K + j] - gmax) : 0.0;
+
+    const double x0 = act ? node[j] : NEG;
+    x_last = x0;
+    const double a0 = act ? p.log_pi[j] + x0 : NEG;
+    float mf = tile_maxf<LPS>((float)a0);
+    e = act ? exp(a0 - (double)mf) : 0.0;
+    logZ = (double)mf;
+    double x_nxt = (act && T > 1) ? node[K + j] : NEG;
+    float mfn = tile_maxf<LPS>((float)x_nxt);
+    double exn = act ? exp(x_nxt - (double)mfn) : 0.0;
+    for (int t = 1; t < T; ++t) {
+      double* buf = sbuf[sub][t & 1];
+      buf[j] = e;
+      const double x_pre = (act && t + 1 < T) ? node[(size_t)(t + 1) * K + j] : NEG;   // prefetch
+      __syncwarp();
+      double pa[4] = {0.0, 0.0, 0.0, 0.0}, sa[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int i2 = 0; i2 < LPS / 2; ++i2) {
+        const double2 a2 = *reinterpret_cast<const double2*>(&buf[2 * i2]);
+        pa[(2 * i2) & 3] = fma(a2.x, Pc[2 * i2], pa[(2 * i2) & 3]);
+        pa[(2 * i2 + 1) & 3] = fma(a2.y, Pc[2 * i2 + 1], pa[(2 * i2 + 1) & 3]);
+        sa[(2 * i2) & 3] += a2.x;
+        sa[(2 * i2 + 1) & 3] += a2.y;
+      }
+      const double pj = (pa[0] + pa[1]) + (pa[2] + pa[3]);
+      c = (sa[0] + sa[1]) + (sa[2] + sa[3]);          // sum of the previous message, same in every lane
+      invc = hmm_rcp(c);
+      if (store) Ez[(size_t)(t - 1) * K + j] = e * invc;          // alpha_{t-1}, normalised
+      logZ += (double)mfn;
+      cprod *= c;
+      if ((t & 7) == 7) {
+        logZ += log(cprod);
+        cprod = 1.0;
+      }
+      e = pj * invc * exn;                                       // message t (sums to c_t)
+      x_last = x_nxt;
+      x_nxt = x_pre;
+      mfn = tile_maxf<LPS>((float)x_nxt);
+      exn = act ? exp(x_nxt - (double)mfn) : 0.0;
     }
-    const double pj = (pa[0] + pa[1]) + (pa[2] + pa[3]);
-    mf = tile_maxf<LPS>((float)x);
-    e = act ? pj * exp(x - (double)mf) : 0.0;
     c = tile_sum<LPS>(e);
-    alpha = e / c;
-    logZ += (double)mf;
+    invc = 1.0 / c;
     cprod *= c;
-    if ((t & 7) == 7) {
-      logZ += log(cprod);
-      cprod = 1.0;
-    }
-    if (act && valid && !fwd_only) Ez[(size_t)t * K + j] = alpha;
-    __syncwarp();
+    logZ += log(cprod) + (double)(T - 1) * gmax;
+    if (j == 0 && valid && p.logZ) p.logZ[b] = logZ;
+    if (fwd_only) return;
+    if (store) Ez[(size_t)(T - 1) * K + j] = e * invc;            // alpha_{T-1} = E[z_{T-1}]
   }
-  logZ += log(cprod) + (double)(T - 1) * gmax;
-  if (j == 0 && valid && p.logZ) p.logZ[b] = logZ;
-  if (fwd_only) return;
 
   // ------------------------------------ backward --------------------------------------------
   double Pr[LPS];   // row j of P:  Pr[i] = P[j][i]
@@ -124,45 +151,87 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
   double O[LPS];    // column j of sum_t alpha_t (x) w_{t+1} / s_t
 #pragma unroll
   for (int i = 0; i < LPS; ++i) O[i] = 0.0;
-  double beta = act ? 1.0 : 0.0;
-  // x currently holds node[T-1]; alpha holds alpha_{T-1} (= E[z_{T-1}], already stored)
-  double xc = x;
-  double an = (act && T > 1) ? 0.0 : 0.0;
-  if (T > 1) an = act ? Ez[(size_t)(T - 2) * K + j] : 0.0;   // visible: same thread wrote it
+  __syncwarp();
+  double bet = act ? 1.0 : 0.0;     // beta_{t+1}, arbitrary positive scale
+  double kb = 1.0;                  // lagged rescaling of beta
+  double exl;                       // exp(node_{t+1} - max)
+  {
+    const float mfl = tile_maxf<LPS>((float)x_last);
+    exl = act ? exp(x_last - (double)mfl) : 0.0;
+  }
+  double at = (act && T > 1) ? Ez[(size_t)(T - 2) * K + j] : 0.0;     // alpha_t (same thread wrote it)
+  double x_pre = (act && T > 1) ? node[(size_t)(T - 2) * K + j] : NEG;
+  double prd_prev = 0.0, at_prev = 0.0, w_prev = 0.0;                 // finished one step late
   for (int t = T - 2; t >= 0; --t) {
-    // w = exp(node_{t+1} - max) * beta_{t+1}
-    mf = tile_maxf<LPS>((float)xc);
-    const double w = act ? exp(xc - (double)mf) * beta : 0.0;
-    wbuf[j] = w;
-    const double at = an;
-    // prefetch for the next iteration
-    xc = act ? node[(size_t)t * K + j] : NEG;
-    if (t > 0) an = act ? Ez[(size_t)(t - 1) * K + j] : 0.0;
+    const int sl = 2 + 3 * (t & 1);
+    double* wb = sbuf[sub][sl];
+    double* pbf = sbuf[sub][sl + 1];
+    double* ab = sbuf[sub][sl + 2];
+    const double w = exl * bet * kb;          // w_{t+1}[j]
+    wb[j] = w;
+    pbf[j] = prd_prev;                        // alpha_{t+1} .* (P w_{t+2})
+    ab[j] = at_prev;                          // alpha_{t+1}
+    const double at_next = (act && t > 0) ? Ez[(size_t)(t - 1) * K + j] : 0.0;   // prefetch
+    const double x_next = (act && t > 0) ? node[(size_t)(t - 1) * K + j] : NEG;
     __syncwarp();
-    double pb[4] = {0.0, 0.0, 0.0, 0.0};
+    double pb[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int i2 = 0; i2 < LPS / 2; ++i2) {
-      const double2 w2 = *reinterpret_cast<const double2*>(&wbuf[2 * i2]);
+      const double2 w2 = *reinterpret_cast<const double2*>(&wb[2 * i2]);
+      const double2 p2 = *reinterpret_cast<const double2*>(&pbf[2 * i2]);
       pb[(2 * i2) & 3] = fma(w2.x, Pr[2 * i2], pb[(2 * i2) & 3]);
       pb[(2 * i2 + 1) & 3] = fma(w2.y, Pr[2 * i2 + 1], pb[(2 * i2 + 1) & 3]);
+      ss[(2 * i2) & 3] += p2.x;
+      ss[(2 * i2 + 1) & 3] += p2.y;
     }
-    const double bu = (pb[0] + pb[1]) + (pb[2] + pb[3]);
-    const double s = tile_sum<LPS>(at * bu);
-    const double invs = 1.0 / s;
-    if (act && valid) Ez[(size_t)t * K + j] = at * bu * invs;
-    abuf[j] = at * invs;
+    const double bu = (pb[0] + pb[1]) + (pb[2] + pb[3]);       // (P w_{t+1})[j]
+    if (t < T - 2) {
+      // finish step t+1: s_{t+1} = <alpha_{t+1}, P w_{t+2}>
+      const double invs = hmm_rcp((ss[0] + ss[1]) + (ss[2] + ss[3]));
+      if (act && valid) Ez[(size_t)(t + 1) * K + j] = prd_prev * invs;
+      const double wsc = w_prev * invs;
+#pragma unroll
+      for (int i2 = 0; i2 < LPS / 2; ++i2) {
+        const double2 a2 = *reinterpret_cast<const double2*>(&ab[2 * i2]);
+        O[2 * i2] = fma(a2.x, wsc, O[2 * i2]);
+        O[2 * i2 + 1] = fma(a2.y, wsc, O[2 * i2 + 1]);
+      }
+      kb = invs;
+    }
+    prd_prev = at * bu;
+    at_prev = at;
+    w_prev = w;
+    bet = bu;
+    at = at_next;
+    {
+      // exp factor of node[t] (prefetched one iteration ago) for the next iteration
+      const double xv = act ? x_pre : NEG;
+      const float mfl = tile_maxf<LPS>((float)xv);
+      exl = act ? exp(xv - (double)mfl) : 0.0;
+    }
+    x_pre = x_next;
+  }
+  double ez0 = e * invc;     // T == 1: alpha_0
+  if (T > 1) {
+    // finish step 0
+    const double s0 = tile_sum<LPS>(prd_prev);
+    const double invs = 1.0 / s0;
+    ez0 = prd_prev * invs;
+    if (act && valid) Ez[j] = ez0;
+    double* ab = sbuf[sub][0];
+    ab[j] = at_prev;
     __syncwarp();
+    const double wsc = w_prev * invs;
 #pragma unroll
     for (int i2 = 0; i2 < LPS / 2; ++i2) {
-      const double2 a2 = *reinterpret_cast<const double2*>(&abuf[2 * i2]);
-      O[2 * i2] = fma(a2.x, w, O[2 * i2]);
-      O[2 * i2 + 1] = fma(a2.y, w, O[2 * i2 + 1]);
+      const double2 a2 = *reinterpret_cast<const double2*>(&ab[2 * i2]);
+      O[2 * i2] = fma(a2.x, wsc, O[2 * i2]);
+      O[2 * i2 + 1] = fma(a2.y, wsc, O[2 * i2 + 1]);
     }
-    beta = bu * invs;
-    __syncwarp();
   }
+  __syncwarp();
   if (act && valid) {
-    if (p.Ez0) p.Ez0[(size_t)b * K + j] = Ez[j];
+    if (p.Ez0) p.Ez0[(size_t)b * K + j] = ez0;
     if (p.Etrans) {
 #pragma unroll
       for (int i = 0; i < LPS; ++i)

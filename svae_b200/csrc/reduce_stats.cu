@@ -44,13 +44,17 @@ __global__ void reduce_stage1(const ReduceParams p) {
   }
 }
 
+// one warp per output element: lanes stride over the partials, then a fixed-order shuffle tree
 __global__ void reduce_stage2(const ReduceParams p, int parts) {
   const int E = 4 * p.n * p.n + p.n + 1;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
-    double acc = 0.0;
-    for (int g = 0; g < parts; ++g) acc += p.partial[(size_t)g * E + e];
-    p.out[e] = acc;
-  }
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (e >= E) return;
+  double acc = 0.0;
+  for (int g = lane; g < parts; g += 32) acc += p.partial[(size_t)g * E + e];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) p.out[e] = acc;
 }
 
 }  // namespace
@@ -76,7 +80,8 @@ extern "C" int svae_lds_reduce_stats(int B, int n, const double* E_init_xx, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int parts = B < kStage1Ctas ? B : kStage1Ctas;
   reduce_stage1<<<parts, 256, 0, s>>>(p);
-  reduce_stage2<<<4, 256, 0, s>>>(p, parts);
+  const int E = 4 * n * n + n + 1;
+  reduce_stage2<<<(E + 7) / 8, 256, 0, s>>>(p, parts);
   g_svae_launches.fetch_add(2);
   return cudaGetLastError() == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
 }

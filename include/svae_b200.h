@@ -43,6 +43,7 @@ extern "C" {
 
 #define SVAE_LDS_MAX_N 16           /* latent dimension range compiled into the library: 1..16    */
 #define SVAE_HMM_MAX_K 32           /* discrete states: 1..32 (lane = state)                       */
+#define SVAE_GMM_MAX_N 8            /* GMM latent dimension: 1..8                                  */
 
 /* flags for svae_lds_estep_fwd */
 #define SVAE_LDS_PER_T_PAIR_STATS 1 /* also write per-time second moments (inhomogeneous E_pair)   */
@@ -159,6 +160,23 @@ int svae_hmm_estep(int B, int T, int K, int flags, const double* log_pi, const d
 size_t svae_hmm_viterbi_workspace_bytes(int B, int T, int K);
 int svae_hmm_viterbi(int B, int T, int K, const double* log_pi, const double* log_A, const double* node,
                      int32_t* path, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GMM-SVAE local mean-field fixed point (svae/models/gmm.py:90-110 meanfield_fixed_point with
+ * gaussian_meanfield :112-117 and label_meanfield :119-124) for B independent minibatches of T points,
+ * the whole coordinate ascent inside one launch (one CTA per minibatch, no host round trip per iteration).
+ *   node_J, node_h (B,T,N): diagonal Gaussian node potentials (-1/2 precision, h)      [gaussian_info heads]
+ *   label_global (K) = E[log pi]  (dirichlet.expectedstats); gaussian_globals (K,N+2,N+2) = packed
+ *   niw.expectedstats (svae/distributions/gaussian.py:39-53 layout)
+ *   label_init (B,T,K): initial responsibilities (the reference draws them with npr.rand, gmm.py:126-128)
+ *   tol, max_iter: 1e-3 and 100 in the reference
+ * outputs: label_stats (B,T,K) responsibilities at the fixed point; iters (B) iterations used; kl (B) the
+ * local KL of the last sweep.  The differentiable evaluation at the optimum stays with the caller.
+ */
+int svae_gmm_meanfield(int B, int T, int K, int N, const double* node_J, const double* node_h,
+                       const double* label_global, const double* gaussian_globals,
+                       const double* label_init, double tol, int max_iter, double* label_stats,
+                       int* iters, double* kl, void* stream);
 
 #ifdef __cplusplus
 }

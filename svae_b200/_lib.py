@@ -16,6 +16,7 @@ SVAE_LDS_PER_T_PAIR_STATS = 1
 SVAE_LDS_SAVE_FOR_BWD = 2
 SVAE_LDS_INIT_PER_SEQ = 4
 SVAE_HMM_MAX_K = 32
+SVAE_GMM_MAX_N = 8
 SVAE_HMM_LOGZ_ONLY = 1
 
 _ERR = {-1: "SVAE_ERR_BAD_ARG", -2: "SVAE_ERR_UNSUPPORTED", -3: "SVAE_ERR_WORKSPACE", -4: "SVAE_ERR_CUDA"}
@@ -36,6 +37,7 @@ _SIGNATURES = {
     "svae_lds_reduce_stats_workspace_bytes": (_SZ, [_I]),
     "svae_lds_reduce_stats": (_I, [_I] * 2 + [_P] * 7 + [_P, _SZ, _P]),
     "svae_hmm_estep": (_I, [_I] * 4 + [_P] * 7 + [_P]),
+    "svae_gmm_meanfield": (_I, [_I] * 4 + [_P] * 5 + [ctypes.c_double, _I] + [_P] * 3 + [_P]),
     "svae_hmm_viterbi_workspace_bytes": (_SZ, [_I] * 3),
     "svae_hmm_viterbi": (_I, [_I] * 3 + [_P] * 4 + [_P, _SZ, _P]),
 }

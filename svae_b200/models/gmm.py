@@ -69,11 +69,45 @@ def initialize_meanfield(label_global, node_potentials, generator=None):
     return normalize(torch.rand(T, K, dtype=torch.float64, generator=generator).to(node_potentials.device))
 
 
+def meanfield_fixed_point_cuda(label_global, gaussian_globals, node_J, node_h, label_init, tol=1e-3, max_iter=100):
+    """The whole coordinate ascent in ONE launch of csrc/gmm_meanfield.cu (one CTA per minibatch).
+    node_J, node_h: (T,N) or (B,T,N) diagonal potentials; label_init (T,K) or (B,T,K).  Returns (label_stats, iters, kl)."""
+    import ctypes
+    from .. import _lib
+    dev = node_h.device
+    batched = node_h.dim() == 3
+    nJ, nh, li = (_lib.f64(x, dev) for x in (node_J, node_h, label_init))
+    if not batched:
+        nJ, nh, li = nJ[None], nh[None], li[None]
+    B, T, N = nh.shape
+    K = label_global.shape[0]
+    lg, gg = _lib.f64(label_global, dev), _lib.f64(gaussian_globals, dev)
+    out = torch.empty((B, T, K), dtype=torch.float64, device=dev)
+    iters = torch.zeros(B, dtype=torch.int32, device=dev)
+    kl = torch.empty(B, dtype=torch.float64, device=dev)
+    P = _lib.ptr
+    code = _lib.lib().svae_gmm_meanfield(B, T, K, N, P(nJ.contiguous()), P(nh.contiguous()), P(lg), P(gg), P(li.contiguous()),
+                                         float(tol), int(max_iter), P(out), ctypes.c_void_p(iters.data_ptr()), P(kl),
+                                         _lib.stream_ptr(dev))
+    _lib.check(code, "svae_gmm_meanfield")
+    if not batched:
+        return out[0], iters[0], kl[0]
+    return out, iters, kl
+
+
 def meanfield_fixed_point(label_global, gaussian_globals, node_potentials, tol=1e-3, max_iter=100,
                           label_init=None, generator=None):
-    """gmm.py:90-110."""
+    """gmm.py:90-110.  On a CUDA device with diagonal node precisions the loop runs inside one kernel launch."""
     kl = float('inf')
     label_stats = initialize_meanfield(label_global, node_potentials, generator) if label_init is None else label_init
+    if node_potentials.is_cuda:
+        N = node_potentials.shape[-1] - 2
+        A = node_potentials[..., :N, :N]
+        diag = torch.diagonal(A, dim1=-1, dim2=-2)
+        from .. import _lib
+        if N <= _lib.SVAE_GMM_MAX_N and bool((A - torch.diag_embed(diag)).abs().max() == 0):
+            return meanfield_fixed_point_cuda(label_global, gaussian_globals, diag, node_potentials[..., :N, N],
+                                              label_stats, tol, max_iter)[0]
     for _ in range(max_iter):
         gaussian_natparam, gaussian_stats, gaussian_kl = gaussian_meanfield(gaussian_globals, node_potentials, label_stats)
         label_natparam, label_stats, label_kl = label_meanfield(label_global, gaussian_globals, gaussian_stats)

@@ -323,6 +323,21 @@ def run_ours(args):
                 HK.hmm_estep(nat)
             b_.record(); torch.cuda.synchronize()
             extra["hmm_estep_K32_T500_B2048_seq_per_s"] = 2048 / (a.elapsed_time(b_) / 5 * 1e-3)
+            # the other LDS shapes BASELINE.json lists (parity-test cases; reported for context only)
+            for (n2, T2, B2) in ((8, 50, 256), (16, 200, 4096)):
+                i2, p2 = O.rand_lds_natparam(n2, rng)
+                gi2, gp2 = tuple(g(x) for x in i2), tuple(g(x) for x in p2)
+                J2 = -0.5 * torch.nn.functional.softplus(torch.randn(B2, T2, n2, dtype=torch.float64, device=dev, generator=gen))
+                h2 = torch.randn(B2, T2, n2, dtype=torch.float64, device=dev, generator=gen)
+                e2 = torch.randn(B2, T2, 1, n2, dtype=torch.float64, device=dev, generator=gen)
+                for _ in range(2):
+                    K.lds_estep_forward(gi2, gp2, (J2, h2), 1, e2)
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(5):
+                    K.lds_estep_forward(gi2, gp2, (J2, h2), 1, e2)
+                b_.record(); torch.cuda.synchronize()
+                extra["lds_estep_d%d_T%d_B%d_seq_per_s" % (n2, T2, B2)] = B2 / (a.elapsed_time(b_) / 5 * 1e-3)
         except Exception as e:  # pragma: no cover
             extra["error"] = repr(e)
 

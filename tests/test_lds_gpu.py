@@ -150,3 +150,53 @@ def test_unbatched_like_the_reference():
     with pytest.raises(ValueError):
         K.natural_lds_inference_general((tuple(_gpu(x) for x in init), tuple(_gpu(x) for x in pair)),
                                         (_gpu(np.zeros((T, n, n))), _gpu(node[1][0])), 1)
+
+
+def test_long_sequence_no_drift():
+    """T = 1000 steps of the information-form recursion: no accumulated drift against the oracle."""
+    n, T, B, S = 4, 1000, 3, 1
+    rng = np.random.default_rng(99)
+    init, pair = O.rand_lds_natparam(n, rng)
+    node = O.rand_node_potentials(B, T, n, rng)
+    eps = rng.standard_normal((B, T, S, n))
+    want = O.natural_lds_inference_general((init, pair), node, eps)
+    _compare(_run(init, pair, node, eps, S), want)
+
+
+def test_many_samples_wide_tile():
+    """S = 20 sample paths force the 32-lane tile even at n = 6."""
+    n, T, B, S = 6, 9, 4, 20
+    rng = np.random.default_rng(98)
+    init, pair = O.rand_lds_natparam(n, rng)
+    node = O.rand_node_potentials(B, T, n, rng)
+    eps = rng.standard_normal((B, T, S, n))
+    want = O.natural_lds_inference_general((init, pair), node, eps)
+    _compare(_run(init, pair, node, eps, S), want)
+
+
+def test_minibatch_reduction_and_host_pipeline():
+    """svae_lds_reduce_stats == column sums; LdsHostPipeline (pinned host in/out, chunked) == the direct call."""
+    from svae_b200.lds import lds_inference as K
+    n, T, B, S = 5, 11, 37, 1
+    rng = np.random.default_rng(97)
+    init, pair = O.rand_lds_natparam(n, rng)
+    node = O.rand_node_potentials(B, T, n, rng)
+    gi, gp = tuple(_gpu(x) for x in init), tuple(_gpu(x) for x in pair)
+    eps = _gpu(rng.standard_normal((B, T, S, n)))
+    o = K.lds_estep_forward(gi, gp, (_gpu(node[0]), _gpu(node[1])), S, eps)
+    acc = K.lds_reduce_global_stats(o)
+    want = torch.cat([o["E_init_xx"].sum(0).reshape(-1), o["E_init_x"].sum(0), o["E_pair_xx"].sum(0).reshape(-1),
+                      o["E_pair_xxn"].sum(0).reshape(-1), o["E_pair_xnxn"].sum(0).reshape(-1), o["lognorm"].sum().reshape(1)])
+    assert rel_err(acc.cpu().numpy(), want.cpu().numpy()) < 1e-12
+    # host pipeline: statistics and normalisers do not depend on the noise
+    pin = lambda x: torch.as_tensor(x, dtype=torch.float64).pin_memory()
+    out_host = dict(samples=torch.empty(B, T, S, n, dtype=torch.float64).pin_memory(),
+                    E_node_xx=torch.empty(B, T, n, dtype=torch.float64).pin_memory(),
+                    E_node_x=torch.empty(B, T, n, dtype=torch.float64).pin_memory(),
+                    lognorm=torch.empty(B, dtype=torch.float64).pin_memory())
+    acc2 = K.lds_estep_host((gi, gp), (pin(node[0]), pin(node[1])), S, out_host, chunks=3)
+    torch.cuda.synchronize()
+    assert rel_err(acc2.cpu().numpy(), want.cpu().numpy()) < 1e-12
+    assert rel_err(out_host["E_node_x"].numpy(), o["E_node_x"].cpu().numpy()) < 1e-12
+    assert rel_err(out_host["lognorm"].numpy(), o["lognorm"].cpu().numpy()) < 1e-12
+    assert torch.isfinite(out_host["samples"]).all()

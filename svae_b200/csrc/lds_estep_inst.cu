@@ -16,24 +16,34 @@ namespace svae {
 // Slots rotate; a slot is re-used from a different stream only after the event recorded behind its last
 // kernel, so a copy never overwrites a bank another stream's launch may still read.
 static std::mutex g_const_mu;
-static cudaEvent_t g_const_ev[SVAE_LDS_CONST_SLOTS] = {};
-static cudaStream_t g_const_stream[SVAE_LDS_CONST_SLOTS] = {};
-static bool g_const_used[SVAE_LDS_CONST_SLOTS] = {};
-static int g_const_next = 0;
+constexpr int kMaxDevices = 32;     // per-device state: __constant__ symbols and events belong to one device
+struct ConstSlots {
+  cudaEvent_t ev[SVAE_LDS_CONST_SLOTS] = {};
+  cudaStream_t stream[SVAE_LDS_CONST_SLOTS] = {};
+  bool used[SVAE_LDS_CONST_SLOTS] = {};
+  int next = 0;
+};
+static ConstSlots g_const[kMaxDevices];
 
 template <int N>
-static cudaError_t stage_const_J12(const double* J12, cudaStream_t stream, int* slot_out) {
-  const int slot = g_const_next;
-  g_const_next = (g_const_next + 1) % SVAE_LDS_CONST_SLOTS;
-  if (!g_const_ev[slot]) {
-    cudaError_t e = cudaEventCreateWithFlags(&g_const_ev[slot], cudaEventDisableTiming);
+static cudaError_t stage_const_J12(const double* J12, cudaStream_t stream, int* slot_out, ConstSlots** st_out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  ConstSlots& cs = g_const[dev];
+  const int slot = cs.next;
+  cs.next = (cs.next + 1) % SVAE_LDS_CONST_SLOTS;
+  if (!cs.ev[slot]) {
+    e = cudaEventCreateWithFlags(&cs.ev[slot], cudaEventDisableTiming);
     if (e != cudaSuccess) return e;
   }
-  if (g_const_used[slot] && g_const_stream[slot] != stream) {
-    cudaError_t e = cudaStreamWaitEvent(stream, g_const_ev[slot], 0);
+  if (cs.used[slot] && cs.stream[slot] != stream) {
+    e = cudaStreamWaitEvent(stream, cs.ev[slot], 0);
     if (e != cudaSuccess) return e;
   }
   *slot_out = slot;
+  *st_out = &cs;
   return cudaMemcpyToSymbolAsync(c_J12, J12, sizeof(double) * N * N, sizeof(double) * SVAE_LDS_CONST_NN * slot,
                                  cudaMemcpyDeviceToDevice, stream);
 }
@@ -64,15 +74,16 @@ static cudaError_t launch_one(const LdsFwdParams& p, cudaStream_t stream) {
     std::lock_guard<std::mutex> lock(g_const_mu);
     LdsFwdParams q = p;
     int slot = 0;
-    cudaError_t e = stage_const_J12<N>(p.J12, stream, &slot);
+    ConstSlots* cs = nullptr;
+    cudaError_t e = stage_const_J12<N>(p.J12, stream, &slot, &cs);
     if (e != cudaSuccess) return e;
     q.const_slot = slot;
     kern<<<(unsigned)grid, warps_per_cta * 32, smem, stream>>>(q);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    g_const_used[slot] = true;
-    g_const_stream[slot] = stream;
-    return cudaEventRecord(g_const_ev[slot], stream);
+    cs->used[slot] = true;
+    cs->stream[slot] = stream;
+    return cudaEventRecord(cs->ev[slot], stream);
   }
   kern<<<(unsigned)grid, warps_per_cta * 32, smem, stream>>>(p);
   return cudaGetLastError();

@@ -70,9 +70,13 @@ def get_var_lds_local_natparam(lds_global_natparams, hmm_expected_stats):
     """slds_svae.py:92-103: mix the per-mode parameters with E[z_t] -> per-sequence init, time-inhomogeneous pair."""
     _, _, Ez = hmm_expected_stats                                     # (B,T,K)
     dense_init, dense_pair = get_all_lds_local_natparams(lds_global_natparams)
-    mix = lambda w, p: torch.tensordot(w, p, dims=1)
+    B, T, K = Ez.shape
+
+    def mix(w, p):   # (R,K) @ (K,M): a plain tall-skinny GEMM (cuBLAS), reshaped back
+        return (w.reshape(-1, K) @ p.reshape(K, -1)).reshape(w.shape[:-1] + p.shape[1:])
     init_param = tuple(mix(Ez[:, 0], p) for p in dense_init)          # (B,n,n), (B,n), (B,), (B,)
-    pair_params = tuple(mix(Ez[:, 1:], p).contiguous() for p in dense_pair)   # (B,T-1,n,n) x3, (B,T-1)
+    w = Ez[:, 1:].contiguous()
+    pair_params = tuple(mix(w, p) for p in dense_pair)                # (B,T-1,n,n) x3, (B,T-1)
     return init_param, pair_params
 
 
@@ -97,10 +101,14 @@ def get_arhmm_local_nodeparams(lds_global_natparam, lds_expected_stats):
     init_stats, pair_stats = lds_expected_stats[:2]
     (J, h, a, b), (J11, J12, J22, logZ) = get_all_lds_local_natparams(lds_global_natparam)
     ExxT0, Ex0 = init_stats[0], init_stats[1]
-    init_node = torch.einsum('bij,kij->bk', ExxT0, J) + torch.einsum('bi,ki->bk', Ex0, h) + (a + b)[None]
+    K = J.shape[0]
+    flatK = lambda p: p.reshape(K, -1).T                              # (M,K)
+    init_node = ExxT0.reshape(ExxT0.shape[0], -1) @ flatK(J) + Ex0 @ h.T + (a + b)[None]
     Exx, Exxn, Exnxn = pair_stats[0], pair_stats[1], pair_stats[2]    # (B,T-1,n,n)
-    rest = torch.einsum('btij,kij->btk', Exx, J11) + torch.einsum('btij,kij->btk', Exxn, J12) \
-        + torch.einsum('btij,kij->btk', Exnxn, J22) + logZ[None, None]
+    B, Tm = Exx.shape[0], Exx.shape[1]
+    # three tall-skinny GEMMs (R, n^2) @ (n^2, K) instead of einsum's batched path
+    rest = (Exx.reshape(B * Tm, -1) @ flatK(J11) + Exxn.reshape(B * Tm, -1) @ flatK(J12)
+            + Exnxn.reshape(B * Tm, -1) @ flatK(J22)).reshape(B, Tm, K) + logZ[None, None]
     return torch.cat((init_node[:, None], rest), 1)                   # (B,T,K)
 
 

@@ -66,10 +66,10 @@ def get_all_lds_local_natparams(lds_global_natparams):
     return dense_init, dense_pair
 
 
-def get_var_lds_local_natparam(lds_global_natparams, hmm_expected_stats):
+def get_var_lds_local_natparam(lds_global_natparams, hmm_expected_stats, dense=None):
     """slds_svae.py:92-103: mix the per-mode parameters with E[z_t] -> per-sequence init, time-inhomogeneous pair."""
     _, _, Ez = hmm_expected_stats                                     # (B,T,K)
-    dense_init, dense_pair = get_all_lds_local_natparams(lds_global_natparams)
+    dense_init, dense_pair = dense if dense is not None else get_all_lds_local_natparams(lds_global_natparams)
     B, T, K = Ez.shape
 
     def mix(w, p):   # (R,K) @ (K,M): a plain tall-skinny GEMM (cuBLAS), reshaped back
@@ -80,9 +80,9 @@ def get_var_lds_local_natparam(lds_global_natparams, hmm_expected_stats):
     return init_param, pair_params
 
 
-def lds_meanfield(lds_global_natparams, node_potentials, hmm_expected_stats):
+def lds_meanfield(lds_global_natparams, node_potentials, hmm_expected_stats, dense=None):
     """slds_svae.py:80-83."""
-    local_natparam = get_var_lds_local_natparam(lds_global_natparams, hmm_expected_stats)
+    local_natparam = get_var_lds_local_natparam(lds_global_natparams, hmm_expected_stats, dense)
     vlb, expected_stats = natural_lds_estep_general(local_natparam, node_potentials)
     return local_natparam, expected_stats, vlb
 
@@ -96,10 +96,10 @@ def hmm_prior_expectedstats(natparam):
 get_hmm_local_natparam = hmm_prior_expectedstats
 
 
-def get_arhmm_local_nodeparams(lds_global_natparam, lds_expected_stats):
+def get_arhmm_local_nodeparams(lds_global_natparam, lds_expected_stats, dense=None):
     """slds_svae.py:131-147: HMM node potential (t,k) = <expected LDS statistics at t, mode-k parameters>."""
     init_stats, pair_stats = lds_expected_stats[:2]
-    (J, h, a, b), (J11, J12, J22, logZ) = get_all_lds_local_natparams(lds_global_natparam)
+    (J, h, a, b), (J11, J12, J22, logZ) = dense if dense is not None else get_all_lds_local_natparams(lds_global_natparam)
     ExxT0, Ex0 = init_stats[0], init_stats[1]
     K = J.shape[0]
     flatK = lambda p: p.reshape(K, -1).T                              # (M,K)
@@ -112,19 +112,19 @@ def get_arhmm_local_nodeparams(lds_global_natparam, lds_expected_stats):
     return torch.cat((init_node[:, None], rest), 1)                   # (B,T,K)
 
 
-def hmm_meanfield(hmm_global_natparam, lds_global_natparam, lds_expected_stats):
+def hmm_meanfield(hmm_global_natparam, lds_global_natparam, lds_expected_stats, dense=None, hmm_local=None):
     """slds_svae.py:108-115."""
-    init_params, pair_params = get_hmm_local_natparam(hmm_global_natparam)
-    node_params = get_arhmm_local_nodeparams(lds_global_natparam, lds_expected_stats)
+    init_params, pair_params = hmm_local if hmm_local is not None else get_hmm_local_natparam(hmm_global_natparam)
+    node_params = get_arhmm_local_nodeparams(lds_global_natparam, lds_expected_stats, dense)
     local_natparam = (init_params, pair_params, node_params)
     vlb, stats = hmm_estep(local_natparam)
     return local_natparam, stats, vlb
 
 
-def get_hmm_vlb(lds_global_natparam, hmm_local_natparam, lds_expected_stats):
+def get_hmm_vlb(lds_global_natparam, hmm_local_natparam, lds_expected_stats, dense=None):
     """slds_svae.py:150-154."""
     init_params, pair_params, _ = hmm_local_natparam
-    node_params = get_arhmm_local_nodeparams(lds_global_natparam, lds_expected_stats)
+    node_params = get_arhmm_local_nodeparams(lds_global_natparam, lds_expected_stats, dense)
     return hmm_logZ((init_params, pair_params, node_params))
 
 
@@ -145,14 +145,18 @@ def initialize_local_meanfield(node_potentials, eps=None, generator=None):
     return init_stats, pair_stats
 
 
-def optimize_local_meanfield(global_natparam, node_potentials, tol=1e-2, max_iter=100, init_eps=None, generator=None):
-    """slds_svae.py:159-175."""
+def optimize_local_meanfield(global_natparam, node_potentials, tol=1e-2, max_iter=100, init_eps=None, generator=None,
+                             dense=None):
+    """slds_svae.py:159-175.  The per-mode expected parameters (K small NIW/MNIW maps, loop-invariant) are
+    evaluated once per call instead of once per sweep."""
     hmm_global, lds_global = global_natparam
+    dense = dense if dense is not None else get_all_lds_local_natparams(lds_global)
+    hmm_local = get_hmm_local_natparam(hmm_global)
     lds_stats = initialize_local_meanfield(node_potentials, init_eps, generator)
     local_vlb = None
     for _ in range(max_iter):
-        hmm_natparam, hmm_stats, hmm_vlb = hmm_meanfield(hmm_global, lds_global, lds_stats)
-        lds_natparam, lds_stats, lds_vlb = lds_meanfield(lds_global, node_potentials, hmm_stats)
+        hmm_natparam, hmm_stats, hmm_vlb = hmm_meanfield(hmm_global, lds_global, lds_stats, dense, hmm_local)
+        lds_natparam, lds_stats, lds_vlb = lds_meanfield(lds_global, node_potentials, hmm_stats, dense)
         local_vlb, prev = hmm_vlb + lds_vlb, local_vlb
         if prev is not None and float((local_vlb - prev).abs().max()) < tol:   # the one host sync per sweep
             break
@@ -206,12 +210,13 @@ def run_inference(prior_natparam, global_natparam, nn_potentials, num_samples, e
     hmm_global_natparam, lds_global_natparam = global_natparam
     batched = nn_potentials[1].dim() == 3
     pots = tuple(nn_potentials[:2]) if batched else tuple(p[None] for p in nn_potentials[:2])
+    dense = get_all_lds_local_natparams(lds_global_natparam)
     with torch.no_grad():
         (hmm_stats, _), (hmm_local_natparam, lds_local_natparam), _ = \
-            optimize_local_meanfield(global_natparam, unbox(pots), init_eps=init_eps, generator=generator)
+            optimize_local_meanfield(global_natparam, unbox(pots), init_eps=init_eps, generator=generator, dense=dense)
     samples, lds_stats, lds_normalizer = natural_lds_inference_general(lds_local_natparam, pots, num_samples, eps=eps,
                                                                        generator=generator)
-    hmm_vlb = get_hmm_vlb(lds_global_natparam, hmm_local_natparam, lds_stats)
+    hmm_vlb = get_hmm_vlb(lds_global_natparam, hmm_local_natparam, lds_stats, dense)
     global_lds_stats, local_lds_stats = lds_stats[:-1], lds_stats[-1]
     expected_stats = get_global_stats(hmm_stats, global_lds_stats)
     global_vlb = slds_prior_vlb(global_natparam, prior_natparam)

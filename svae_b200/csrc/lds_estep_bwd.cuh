@@ -54,7 +54,9 @@ __host__ __device__ inline int lds_bwd_tile_doubles(int N, int S) {
          2 * (2 + 3 * S) * NP /*input ring: g_node_x | g_node_xx | g_samples | x_{t+1} | eps*/;
 }
 
-template <int N, int LPS>
+// PER_T: cotangents arrive for the per-time second moments (inhomogeneous / SLDS use); the homogeneous
+// instantiation carries none of that code.
+template <int N, int LPS, bool PER_T>
 __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams p) {
   constexpr int SPW = 32 / LPS;
   constexpr int NP = lds_np(N);
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
     mbar_init(&bars[1], 1);
     mbar_fence_init();
   }
-  const bool per_t = p.g_Exx_t != nullptr;
+  constexpr bool per_t = PER_T;
   // stage the (symmetrised) cotangents of the global statistics
   if (mat) {
 #pragma unroll
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         double a_ic = (last ? 0.0 : XA[i * NP + c]) + (first ? X0[i * NP + c] : XB[i * NP + c]);
-        if (per_t) {
+        if (per_t && p.g_Exx_t) {
           const size_t o = ((size_t)b * T + t) * NN;
           a_ic += 0.5 * (p.g_Exx_t[o + i * N + c] + p.g_Exx_t[o + c * N + i]);
         }
@@ -187,6 +189,9 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
         am = fma(a_ic, mu_t[i], am);                                   // (A_s mu_t)_c
         double bm_ci = Bm[c * NP + i], bm_ic = Bm[i * NP + c];
         if (per_t) {
+          bm_ci = bm_ic = 0.0;
+        }
+        if (per_t && p.g_Exxn_t) {
           bm_ci = last ? 0.0 : p.g_Exxn_t[((size_t)b * (T - 1) + t) * NN + c * N + i];
           bm_ic = first ? 0.0 : p.g_Exxn_t[((size_t)b * (T - 1) + t - 1) * NN + i * N + c];
         }
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
         // Cb[:,c] = B[:,c] + Sb G[:,c]
 #pragma unroll
         for (int i = 0; i < N; ++i)
-          Cb[i] = per_t ? p.g_Exxn_t[((size_t)b * (T - 1) + t) * NN + i * N + c] : Bm[i * NP + c];
+          Cb[i] = per_t ? (p.g_Exxn_t ? p.g_Exxn_t[((size_t)b * (T - 1) + t) * NN + i * N + c] : 0.0) : Bm[i * NP + c];
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           const double gk = G[c * NP + k];   // G_t[k][c]

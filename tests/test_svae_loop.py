@@ -150,3 +150,14 @@ def test_lds_run_inference_matches_oracle_composition():
     w_kl = (node[0] * wn[0]).sum() + (node[1] * wn[1]).sum() - w_ln.sum()
     assert abs(float(local_kl) - w_kl) < 1e-9 * abs(w_kl)
     assert torch.isfinite(global_kl)
+
+
+def test_optimizers_on_nested_tuples():
+    from svae_b200.optimizers import sgd, adam
+    target = (torch.tensor([1., -2.], dtype=torch.float64), (torch.tensor(3., dtype=torch.float64),))
+    p0 = (torch.zeros(2, dtype=torch.float64), (torch.zeros((), dtype=torch.float64),))
+    gradfun = lambda p, i: (2 * (p[0] - target[0]), (2 * (p[1][0] - target[1][0]),))
+    ps = sgd(gradfun, p0, num_iters=400, step_size=0.1)
+    pa = adam(gradfun, p0, num_iters=2000, step_size=0.01)
+    for q in (ps, pa):
+        assert torch.allclose(q[0], target[0], atol=1e-3) and torch.allclose(q[1][0], target[1][0], atol=1e-3)

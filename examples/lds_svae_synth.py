@@ -35,12 +35,16 @@ def main():
     ap.add_argument("-T", type=int, default=50)
     ap.add_argument("-n", type=int, default=8)
     ap.add_argument("-p", type=int, default=12)
+    ap.add_argument("--pgm-on-device", dest="pgm_on_host", action="store_false")
     a = ap.parse_args()
     dev = "cuda"
     gen = torch.Generator().manual_seed(0)
     data = make_data(a.seq, a.T, a.n, a.p, gen, dev)
-    prior = lds.make_prior_natparam(a.n, device=dev)
-    pgm = lds.make_prior_natparam(a.n, scaling=2., device=dev)
+    # the global (PGM) block stays on the host: its NIW/MNIW maps are two n x n matrices, microseconds on a CPU
+    # core and launch-latency-bound on a GPU; only the ~4n^2 local natural parameters cross PCIe per step
+    pgm_dev = "cpu" if a.pgm_on_host else dev
+    prior = lds.make_prior_natparam(a.n, device=pgm_dev)
+    pgm = lds.make_prior_natparam(a.n, scaling=2., device=pgm_dev)
     recognize, recogn_params = nnet.init_gresnet(a.p, [(32, torch.tanh), (2 * a.n, nnet.gaussian_info)], generator=gen, device=dev)
     decode, loglike_params = nnet.init_gresnet(a.n, [(32, torch.tanh), (2 * a.p, nnet.gaussian_mean)], generator=gen, device=dev)
     loglike = nnet.make_loglike(decode)

@@ -53,6 +53,7 @@ def make_gradfun(run_inference, recognize, loglike, pgm_prior, data, batch_size,
         grads = torch.autograd.grad(val, nn_leaves, allow_unused=True)
         grads = [torch.zeros_like(l) if g is None else g for g, l in zip(grads, nn_leaves)]
         stats_flat = flat(unbox(stats))
+        pgm_flat = flat(unbox(pgm_params))
         if dist is not None and dist.get_world_size() > 1:
             # data-parallel minibatch: one all-reduce of [expected statistics | NN gradients | objective]
             buf = torch.cat([stats_flat] + [g.reshape(-1) for g in grads] + [val.detach().reshape(1)])
@@ -66,8 +67,10 @@ def make_gradfun(run_inference, recognize, loglike, pgm_prior, data, batch_size,
             val = buf[-1] / dist.get_world_size()
         loglike_grad, recogn_grad = _rebuild((loglike_params, recogn_params), iter(grads))
         # natural gradient of the PGM parameters (svae.py:31-34)
+        # (the PGM block may live on the host -- its exp-family maps are K tiny matrices -- while the statistics
+        #  come back from the device: one small copy, the same payload as the all-reduce)
         pgm_natgrad = -natgrad_scale / num_datapoints * \
-            (flat(pgm_prior) + num_batches * stats_flat - flat(unbox(pgm_params)))
+            (flat(pgm_prior).to(pgm_flat.device) + num_batches * stats_flat.to(pgm_flat.device) - pgm_flat)
         grad = unflat(pgm_natgrad), loglike_grad, recogn_grad
         if callback:
             callback(i, float(val.detach()), params, grad)

@@ -375,7 +375,13 @@ def run_ours(args):
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                           traffic=traffic, peak_source=peak_src, kernel="lds_estep_fwd_kernel<10,16,false>",
                           kernel_ms=kern_ms, algorithmic_bytes_per_launch=ab,
-                          note="fp64 ALU / shared-memory bound at ~30 flop/B, not HBM bound (SURVEY.md 8d, DESIGN.md 3)"),
+                          note="fp64 ALU / shared-memory bound at ~30 flop/B, not HBM bound (SURVEY.md 8d, DESIGN.md 3)",
+                          # the second roofline SURVEY.md 8d asks for: algorithmic flops T(12n^3+10n^2) per sequence
+                          # (the REFERENCE's operation count; this kernel's own formulation needs ~30% fewer) over the
+                          # fp64 FMA peak 148 SMs x 64 FMA/clk x 2 x 1.965 GHz
+                          fp64=dict(achieved_tflops=T * (12 * n ** 3 + 10 * n ** 2) * B / (kern_ms * 1e-3) / 1e12,
+                                    peak_tflops=148 * 64 * 2 * 1.965e9 / 1e12,
+                                    frac=T * (12 * n ** 3 + 10 * n ** 2) * B / (kern_ms * 1e-3) / (148 * 64 * 2 * 1.965e9))),
             cpu_baseline=cpu, extra=extra)
         print(json.dumps(line))
     if world > 1:

@@ -64,3 +64,25 @@ def test_hmm_unbatched_like_reference():
     logZ, (E0, Et, Ez) = K.hmm_estep((_g(lp), _g(lA), _g(node)))
     assert logZ.dim() == 0 and E0.shape == (4,) and Et.shape == (4, 4) and Ez.shape == (9, 4)
     assert K.hmm_viterbi((_g(lp), _g(lA), _g(node))).shape == (9,)
+
+
+def test_hmm_forbidden_transitions():
+    """Left-to-right chain: log A has -inf entries (zero-probability transitions) and log pi forbids all but state 0."""
+    from svae_b200.hmm import hmm_inference as K
+    rng = np.random.default_rng(11)
+    K_, T, B = 6, 25, 4
+    A = np.triu(rng.random((K_, K_)) + 0.1)
+    A = A / A.sum(1, keepdims=True)
+    with np.errstate(divide="ignore"):
+        lA = np.log(A)
+        lp = np.log(np.eye(K_)[0])
+    node = rng.standard_normal((B, T, K_))
+    w_logZ, (wE0, wEt, wEz) = H.hmm_estep((lp, lA, node))
+    nat = (_g(lp), _g(lA), _g(node))
+    logZ, (Ez0, Etrans, Ez) = K.hmm_estep(nat)
+    assert rel_err(logZ.cpu().numpy(), w_logZ) < RTOL
+    assert rel_err(Ez.cpu().numpy(), wEz) < RTOL and rel_err(Etrans.cpu().numpy(), wEt) < RTOL
+    assert float(Etrans.cpu().numpy()[:, np.tril_indices(K_, -1)[0], np.tril_indices(K_, -1)[1]].max()) == 0.0
+    path = K.hmm_viterbi(nat).cpu().numpy()
+    assert np.array_equal(path, H.hmm_viterbi((lp, lA, node)))
+    assert (np.diff(path, axis=1) >= 0).all() and (path[:, 0] == 0).all()

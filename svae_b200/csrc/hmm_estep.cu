@@ -105,10 +105,15 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
     double x_nxt = (act && T > 1) ? node[K + j] : NEG;
     float mfn = tile_maxf<LPS>((float)x_nxt);
     double exn = act ? exp(x_nxt - (double)mfn) : 0.0;
+    // node potentials are prefetched three steps ahead (a step is shorter than one DRAM round trip)
+    double xq1 = (act && T > 2) ? node[(size_t)2 * K + j] : NEG;
+    double xq2 = (act && T > 3) ? node[(size_t)3 * K + j] : NEG;
     for (int t = 1; t < T; ++t) {
       double* buf = sbuf[sub][t & 1];
       buf[j] = e;
-      const double x_pre = (act && t + 1 < T) ? node[(size_t)(t + 1) * K + j] : NEG;   // prefetch
+      const double x_pre = xq1;                                                          // node[t+1]
+      xq1 = xq2;
+      xq2 = (act && t + 3 < T) ? node[(size_t)(t + 3) * K + j] : NEG;
       __syncwarp();
       double pa[4] = {0.0, 0.0, 0.0, 0.0}, sa[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -161,6 +166,9 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
   }
   double at = (act && T > 1) ? Ez[(size_t)(T - 2) * K + j] : 0.0;     // alpha_t (same thread wrote it)
   double x_pre = (act && T > 1) ? node[(size_t)(T - 2) * K + j] : NEG;
+  // three-deep prefetch queues for alpha_{t-1}, node[t-1]
+  double aq1 = (act && T > 2) ? Ez[(size_t)(T - 3) * K + j] : 0.0, aq2 = (act && T > 3) ? Ez[(size_t)(T - 4) * K + j] : 0.0;
+  double nq1 = (act && T > 2) ? node[(size_t)(T - 3) * K + j] : NEG, nq2 = (act && T > 3) ? node[(size_t)(T - 4) * K + j] : NEG;
   double prd_prev = 0.0, at_prev = 0.0, w_prev = 0.0;                 // finished one step late
   for (int t = T - 2; t >= 0; --t) {
     const int sl = 2 + 3 * (t & 1);
@@ -171,8 +179,11 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
     wb[j] = w;
     pbf[j] = prd_prev;                        // alpha_{t+1} .* (P w_{t+2})
     ab[j] = at_prev;                          // alpha_{t+1}
-    const double at_next = (act && t > 0) ? Ez[(size_t)(t - 1) * K + j] : 0.0;   // prefetch
-    const double x_next = (act && t > 0) ? node[(size_t)(t - 1) * K + j] : NEG;
+    const double at_next = aq1, x_next = nq1;                                       // alpha_{t-1}, node[t-1]
+    aq1 = aq2;
+    nq1 = nq2;
+    aq2 = (act && t > 2) ? Ez[(size_t)(t - 3) * K + j] : 0.0;
+    nq2 = (act && t > 2) ? node[(size_t)(t - 3) * K + j] : NEG;
     __syncwarp();
     double pb[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll

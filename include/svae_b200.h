@@ -99,6 +99,34 @@ int svae_lds_estep_fwd(
     double* Exx_t, double* Exxn_t,
     int* status, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same kernel behind the reference's three-primitive interface (svae/lds/lds_inference.py:18-39):
+ *   msg_J_pred (B,T,n,n), msg_h_pred (B,T,n): OUTPUT the prediction messages of natural_filter_forward_general
+ *       (cython_lds_inference.pyx:83-86; the filtered messages are J_pred + diag(node_J), h_pred + node_h);
+ *   in_J_filt (B,T,n,n), in_h_filt (B,T,n): run the smoother / sampler sweeps from GIVEN filtered messages
+ *       (natural_smoother_general, natural_sample_backward: pyx:149-195, 310-355) -- pass node_J = node_h = 0;
+ *       `lognorm` is then meaningless;
+ *   node_J_dense (B,T,n,n): dense node precisions, natural form (-1/2 J), ADDED to the diagonal node_J -- the
+ *       reference's pure-Python option (svae/lds/lds_inference.py:65-80, svae/lds/gaussian.py:46-49) that its Cython
+ *       path rejects (pyx:43).  With it E_node_stats[0] is the full E[x_t x_t'] = Exx_t (lds_inference.py:164-167):
+ *       pass SVAE_LDS_PER_T_PAIR_STATS and Exx_t (Exxn_t may stay NULL).
+ * Any of the five may be NULL.
+ */
+int svae_lds_estep_fwd_ex(
+    int B, int T, int n, int S, int flags,
+    const double* init_J, const double* init_h, const double* init_logZ,
+    const double* J11, const double* J12, const double* J22, const double* pair_logZ,
+    long long pair_stride_t, long long pair_stride_b,
+    const double* node_J, const double* node_h, const double* node_logZ,
+    const double* eps,
+    double* E_init_xx, double* E_init_x,
+    double* E_pair_xx, double* E_pair_xxn, double* E_pair_xnxn,
+    double* E_node_xx, double* E_node_x,
+    double* samples, double* lognorm,
+    double* Exx_t, double* Exxn_t,
+    double* msg_J_pred, double* msg_h_pred, const double* in_J_filt, const double* in_h_filt,
+    const double* node_J_dense,
+    int* status, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * LDS local E-step, backward: the VJP of svae_lds_estep_fwd with respect to the node potentials
  * (node_J, node_h), given cotangents of every output.  Replaces the composition
@@ -125,6 +153,20 @@ int svae_lds_estep_bwd(
     const double* g_Exx_t, const double* g_Exxn_t,
     const double* g_E_node_xx, const double* g_E_node_x, const double* g_lognorm,
     double* g_node_J, double* g_node_h,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* As above plus g_node_J_dense (B,T,n,n): the un-symmetrised cotangent Pbar_t of the filtered precision at every
+ * step; the gradient w.r.t. a dense natural-form node precision is -(Pbar_t + Pbar_t') (g_node_J may then be NULL).
+ * In this entry point the homogeneous-sum cotangents (g_E_pair_*) and the per-time ones (g_Exx_t, g_Exxn_t) ADD. */
+int svae_lds_estep_bwd_ex(
+    int B, int T, int n, int S, int flags,
+    const double* E_node_x, const double* samples, const double* eps,
+    const double* g_samples,
+    const double* g_E_init_xx, const double* g_E_init_x,
+    const double* g_E_pair_xx, const double* g_E_pair_xxn, const double* g_E_pair_xnxn,
+    const double* g_Exx_t, const double* g_Exxn_t,
+    const double* g_E_node_xx, const double* g_E_node_x, const double* g_lognorm,
+    double* g_node_J, double* g_node_h, double* g_node_J_dense,
     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -72,7 +72,8 @@ def _pair_at(pair_params, t):
 
 
 def natural_lds_inference_general(natparam, node_params, eps):
-    """lds_inference.py:185-202, batched; node J diagonal (B,T,n).  Everything differentiable."""
+    """lds_inference.py:185-202, batched; node J diagonal (B,T,n) or dense (B,T,n,n) (gaussian.py:46-49; the
+    dense case returns the full E[x x'] as E_node_stats[0], lds_inference.py:159-167).  Everything differentiable."""
     (J0, h0, logZ0), pair_params = natparam
     Jn, hn = node_params[0], node_params[1]
     logZn = node_params[2] if len(node_params) > 2 else torch.zeros(hn.shape[:2], dtype=hn.dtype)
@@ -83,7 +84,7 @@ def natural_lds_inference_general(natparam, node_params, eps):
     Jp, hp, Jf, hf = [], [], [], []
     for t in range(T):                                            # lds_inference.py:86-106
         Jp.append(J); hp.append(h)
-        J, h = J + Jn[:, t, :, None] * eye, h + hn[:, t]
+        J, h = J + (Jn[:, t] if Jn.dim() == 4 else Jn[:, t, :, None] * eye), h + hn[:, t]
         lognorm = lognorm + logZn[:, t]
         Jf.append(J); hf.append(h)
         if t < T - 1:
@@ -111,7 +112,7 @@ def natural_lds_inference_general(natparam, node_params, eps):
     else:
         z = torch.zeros(B, n, n, dtype=hn.dtype)
         E_pair = (z, z, z)
-    E_node = (torch.diagonal(ExxT, dim1=-1, dim2=-2), Ex)
+    E_node = (ExxT if Jn.dim() == 4 else torch.diagonal(ExxT, dim1=-1, dim2=-2), Ex)
     # sampler                                                        lds_inference.py:109-124
     S = eps.shape[2]
     x = natural_sample(Jf[-1], hf[-1][:, None, :].expand(B, S, n), eps[:, -1])

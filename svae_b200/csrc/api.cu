@@ -53,7 +53,7 @@ extern "C" size_t svae_lds_estep_workspace_bytes(int B, int T, int n, int S, int
   return sizeof(double) * (size_t)B * (size_t)T * (size_t)svae::lds_record_stride(n, S, save);
 }
 
-extern "C" int svae_lds_estep_fwd(
+extern "C" int svae_lds_estep_fwd_ex(
     int B, int T, int n, int S, int flags,
     const double* init_J, const double* init_h, const double* init_logZ,
     const double* J11, const double* J12, const double* J22, const double* pair_logZ,
@@ -65,6 +65,8 @@ extern "C" int svae_lds_estep_fwd(
     double* E_node_xx, double* E_node_x,
     double* samples, double* lognorm,
     double* Exx_t, double* Exxn_t,
+    double* msg_J_pred, double* msg_h_pred, const double* in_J_filt, const double* in_h_filt,
+    const double* node_J_dense,
     int* status, void* workspace, size_t workspace_bytes, void* stream) {
   if (B <= 0 || T <= 0 || n <= 0 || S < 0) return SVAE_ERR_BAD_ARG;
   if (!init_J || !init_h || !node_J || !node_h || !workspace) return SVAE_ERR_BAD_ARG;
@@ -89,10 +91,63 @@ extern "C" int svae_lds_estep_fwd(
   p.samples = samples; p.lognorm = lognorm;
   const bool per_t = (flags & SVAE_LDS_PER_T_PAIR_STATS) != 0;
   p.Exx_t = per_t ? Exx_t : nullptr; p.Exxn_t = per_t ? Exxn_t : nullptr;
+  p.msg_J_pred = msg_J_pred; p.msg_h_pred = msg_h_pred; p.in_J_filt = in_J_filt; p.in_h_filt = in_h_filt;
+  p.node_J_dense = node_J_dense;
   p.status = status;
   p.stash = static_cast<double*>(workspace);
   const bool inhomog = (pair_stride_t != 0 || pair_stride_b != 0) && T > 1;
   cudaError_t e = kLdsFwd[n](p, cpl, lps, inhomog, static_cast<cudaStream_t>(stream));
+  g_svae_launches.fetch_add(1);
+  return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
+}
+
+extern "C" int svae_lds_estep_fwd(
+    int B, int T, int n, int S, int flags,
+    const double* init_J, const double* init_h, const double* init_logZ,
+    const double* J11, const double* J12, const double* J22, const double* pair_logZ,
+    long long pair_stride_t, long long pair_stride_b,
+    const double* node_J, const double* node_h, const double* node_logZ,
+    const double* eps,
+    double* E_init_xx, double* E_init_x,
+    double* E_pair_xx, double* E_pair_xxn, double* E_pair_xnxn,
+    double* E_node_xx, double* E_node_x,
+    double* samples, double* lognorm,
+    double* Exx_t, double* Exxn_t,
+    int* status, void* workspace, size_t workspace_bytes, void* stream) {
+  return svae_lds_estep_fwd_ex(B, T, n, S, flags, init_J, init_h, init_logZ, J11, J12, J22, pair_logZ, pair_stride_t,
+                               pair_stride_b, node_J, node_h, node_logZ, eps, E_init_xx, E_init_x, E_pair_xx, E_pair_xxn,
+                               E_pair_xnxn, E_node_xx, E_node_x, samples, lognorm, Exx_t, Exxn_t, nullptr, nullptr, nullptr,
+                               nullptr, nullptr, status, workspace, workspace_bytes, stream);
+}
+
+extern "C" int svae_lds_estep_bwd_ex(
+    int B, int T, int n, int S, int flags,
+    const double* E_node_x, const double* samples, const double* eps,
+    const double* g_samples,
+    const double* g_E_init_xx, const double* g_E_init_x,
+    const double* g_E_pair_xx, const double* g_E_pair_xxn, const double* g_E_pair_xnxn,
+    const double* g_Exx_t, const double* g_Exxn_t,
+    const double* g_E_node_xx, const double* g_E_node_x, const double* g_lognorm,
+    double* g_node_J, double* g_node_h, double* g_node_J_dense,
+    void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || T <= 0 || n <= 0 || S < 0) return SVAE_ERR_BAD_ARG;
+  if (!E_node_x || !workspace || (!g_node_J && !g_node_J_dense) || !g_node_h) return SVAE_ERR_BAD_ARG;
+  if (S > 0 && (!samples || !eps)) return SVAE_ERR_BAD_ARG;
+  if (n > SVAE_LDS_MAX_N) return SVAE_ERR_UNSUPPORTED;
+  const int lps = pick_lps(n, S);
+  if (!lps) return SVAE_ERR_UNSUPPORTED;
+  if (workspace_bytes < svae_lds_estep_workspace_bytes(B, T, n, S, flags | SVAE_LDS_SAVE_FOR_BWD)) return SVAE_ERR_WORKSPACE;
+  svae::LdsBwdParams p;
+  p.B = B; p.T = T; p.S = S; p.flags = flags;
+  p.E_node_x = E_node_x; p.samples = samples; p.eps = eps;
+  p.g_samples = g_samples;
+  p.g_E_init_xx = g_E_init_xx; p.g_E_init_x = g_E_init_x;
+  p.g_E_pair_xx = g_E_pair_xx; p.g_E_pair_xxn = g_E_pair_xxn; p.g_E_pair_xnxn = g_E_pair_xnxn;
+  p.g_Exx_t = g_Exx_t; p.g_Exxn_t = g_Exxn_t;
+  p.g_E_node_xx = g_E_node_xx; p.g_E_node_x = g_E_node_x; p.g_lognorm = g_lognorm;
+  p.g_node_J = g_node_J; p.g_node_h = g_node_h; p.g_node_J_dense = g_node_J_dense;
+  p.stash = static_cast<double*>(workspace);
+  cudaError_t e = kLdsBwd[n](p, lps, static_cast<cudaStream_t>(stream));
   g_svae_launches.fetch_add(1);
   return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
 }
@@ -107,24 +162,8 @@ extern "C" int svae_lds_estep_bwd(
     const double* g_E_node_xx, const double* g_E_node_x, const double* g_lognorm,
     double* g_node_J, double* g_node_h,
     void* workspace, size_t workspace_bytes, void* stream) {
-  if (B <= 0 || T <= 0 || n <= 0 || S < 0) return SVAE_ERR_BAD_ARG;
-  if (!E_node_x || !workspace || !g_node_J || !g_node_h) return SVAE_ERR_BAD_ARG;
-  if (S > 0 && (!samples || !eps)) return SVAE_ERR_BAD_ARG;
-  if (n > SVAE_LDS_MAX_N) return SVAE_ERR_UNSUPPORTED;
-  const int lps = pick_lps(n, S);
-  if (!lps) return SVAE_ERR_UNSUPPORTED;
-  if (workspace_bytes < svae_lds_estep_workspace_bytes(B, T, n, S, flags | SVAE_LDS_SAVE_FOR_BWD)) return SVAE_ERR_WORKSPACE;
-  svae::LdsBwdParams p;
-  p.B = B; p.T = T; p.S = S; p.flags = flags;
-  p.E_node_x = E_node_x; p.samples = samples; p.eps = eps;
-  p.g_samples = g_samples;
-  p.g_E_init_xx = g_E_init_xx; p.g_E_init_x = g_E_init_x;
-  p.g_E_pair_xx = g_E_pair_xx; p.g_E_pair_xxn = g_E_pair_xxn; p.g_E_pair_xnxn = g_E_pair_xnxn;
-  p.g_Exx_t = g_Exx_t; p.g_Exxn_t = g_Exxn_t;
-  p.g_E_node_xx = g_E_node_xx; p.g_E_node_x = g_E_node_x; p.g_lognorm = g_lognorm;
-  p.g_node_J = g_node_J; p.g_node_h = g_node_h;
-  p.stash = static_cast<double*>(workspace);
-  cudaError_t e = kLdsBwd[n](p, lps, static_cast<cudaStream_t>(stream));
-  g_svae_launches.fetch_add(1);
-  return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
+  if (!g_node_J) return SVAE_ERR_BAD_ARG;
+  return svae_lds_estep_bwd_ex(B, T, n, S, flags, E_node_x, samples, eps, g_samples, g_E_init_xx, g_E_init_x, g_E_pair_xx,
+                               g_E_pair_xxn, g_E_pair_xnxn, g_Exx_t, g_Exxn_t, g_E_node_xx, g_E_node_x, g_lognorm, g_node_J,
+                               g_node_h, nullptr, workspace, workspace_bytes, stream);
 }

@@ -53,6 +53,9 @@ struct LdsFwdParams {
   const double* eps;
   double *E_init_xx, *E_init_x, *E_pair_xx, *E_pair_xxn, *E_pair_xnxn;
   double *E_node_xx, *E_node_x, *samples, *lognorm, *Exx_t, *Exxn_t;
+  double *msg_J_pred, *msg_h_pred;          // optional outputs: prediction messages, natural form (B,T,n,n), (B,T,n)
+  const double *in_J_filt, *in_h_filt;      // optional inputs: run the backward sweeps from GIVEN filtered messages
+  const double *node_J_dense;               // optional input: dense node precisions (B,T,n,n), natural form (added to node_J)
   int* status;
   double* stash;
 };
@@ -243,6 +246,28 @@ __global__ void SVAE_LDS_BOUNDS(N, CPL) lds_estep_fwd_kernel(const LdsFwdParams 
       __syncwarp();
     }
     const double* nd = nring + (t & 1) * NODE;
+
+    if (p.msg_J_pred || p.in_J_filt || p.node_J_dense) {
+      // cold path: the three-primitive interface of the reference (messages out / messages in)
+      const size_t off = (size_t)t * p.pair_stride_t + (size_t)b * p.pair_stride_b;
+      const size_t bt = (size_t)b * T + t;
+#pragma unroll
+      for (int cl = 0; cl < CPL; ++cl) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          if (mat[cl]) {
+            const double j11 = last ? 0.0 : (INHOMOG ? -2.0 * p.J11[off + i * N + c[cl]]
+                                                     : shJ11[i * NP + c[cl]] - shJ22[i * NP + c[cl]]);
+            if (p.msg_J_pred && valid) p.msg_J_pred[bt * NN + i * N + c[cl]] = -0.5 * (a[cl][i] - j11);
+            if (p.in_J_filt) a[cl][i] = -2.0 * p.in_J_filt[bt * NN + i * N + c[cl]] + j11;
+            if (p.node_J_dense) a[cl][i] -= 2.0 * p.node_J_dense[bt * NN + i * N + c[cl]];
+          } else if (vec[cl]) {
+            if (p.msg_h_pred && valid) p.msg_h_pred[bt * N + i] = a[cl][i] - nd[NP + i];
+            if (p.in_h_filt) a[cl][i] = p.in_h_filt[bt * N + i];
+          }
+        }
+      }
+    }
 
     // right-hand sides: r = J12 column (mat), q = identity column (mat -> M^-1 column)
     double r[CPL][N], q[CPL][N];

@@ -42,6 +42,7 @@ struct LdsBwdParams {
   const double *g_lognorm;                                 // (B)
   // outputs
   double *g_node_J, *g_node_h;                             // (B,T,n)
+  double *g_node_J_dense;                                  // optional (B,T,n,n): raw Pbar_t, caller symmetrises
   double* stash;                                           // forward workspace (SAVE layout); overwritten
 };
 
@@ -187,13 +188,10 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
         if (i == c) a_ic += inp[NP + c];
         Sb[i] += a_ic;
         am = fma(a_ic, mu_t[i], am);                                   // (A_s mu_t)_c
-        double bm_ci = Bm[c * NP + i], bm_ic = Bm[i * NP + c];
-        if (per_t) {
-          bm_ci = bm_ic = 0.0;
-        }
-        if (per_t && p.g_Exxn_t) {
-          bm_ci = last ? 0.0 : p.g_Exxn_t[((size_t)b * (T - 1) + t) * NN + c * N + i];
-          bm_ic = first ? 0.0 : p.g_Exxn_t[((size_t)b * (T - 1) + t - 1) * NN + i * N + c];
+        double bm_ci = Bm[c * NP + i], bm_ic = Bm[i * NP + c];   // homogeneous sums' cotangent (zeros if absent)
+        if (per_t && p.g_Exxn_t) {                                // plus the per-time one
+          bm_ci += last ? 0.0 : p.g_Exxn_t[((size_t)b * (T - 1) + t) * NN + c * N + i];
+          bm_ic += first ? 0.0 : p.g_Exxn_t[((size_t)b * (T - 1) + t - 1) * NN + i * N + c];
         }
         if (!last) bn = fma(bm_ci, mu_n[i], bn);                       // (B mu_{t+1})_c
         if (!first) bp = fma(bm_ic, mu_p[i], bp);                      // (B' mu_{t-1})_c
@@ -246,7 +244,7 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
         // Cb[:,c] = B[:,c] + Sb G[:,c]
 #pragma unroll
         for (int i = 0; i < N; ++i)
-          Cb[i] = per_t ? (p.g_Exxn_t ? p.g_Exxn_t[((size_t)b * (T - 1) + t) * NN + i * N + c] : 0.0) : Bm[i * NP + c];
+          Cb[i] = Bm[i * NP + c] + ((per_t && p.g_Exxn_t) ? p.g_Exxn_t[((size_t)b * (T - 1) + t) * NN + i * N + c] : 0.0);
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           const double gk = G[c * NP + k];   // G_t[k][c]
@@ -495,6 +493,10 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
         const size_t bt = ((size_t)b * T + t) * N + c;
         if (p.g_node_J) p.g_node_J[bt] = -2.0 * diag;
         if (p.g_node_h) p.g_node_h[bt] = hb_c;
+        if (p.g_node_J_dense) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) p.g_node_J_dense[((size_t)b * T + t) * NN + i * N + c] = Pb[i];
+        }
       }
     }
     __syncwarp();   // everyone is done with PbS / hbS of t+1 and with the ring slot

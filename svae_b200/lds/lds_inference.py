@@ -33,18 +33,18 @@ def _canonical_init_params(init_params, device):
 
 
 def _canonical_node_params(node_params, device):
-    """Accepts (J,h) or (J,h,logZ) with J diagonal; shapes (T,n) or (B,T,n)  (lds_inference.py:65-80).
-
-    Dense (T,n,n) node precisions -- accepted by the reference's pure-Python path only, never by its
-    Cython path (cython_lds_inference.pyx:43) -- are rejected with ValueError like any other bad shape.
+    """Accepts (J,h) or (J,h,logZ); h (T,n) or (B,T,n); J diagonal (same shape as h) or dense (...,T,n,n)
+    (lds_inference.py:65-80: ndims (3,2,1),(3,2),(2,2,1),(2,2)).  The reference's Cython path is diag-only
+    (cython_lds_inference.pyx:43); dense potentials follow its pure-Python path (lds/gaussian.py:46-49) and
+    make E_node_stats[0] the full E[x x'] (lds_inference.py:159-167).  Other shapes: ValueError (:80).
     """
     if not isinstance(node_params, (tuple, list)) or len(node_params) not in (2, 3):
         raise ValueError("node_params must be (J, h) or (J, h, logZ)")
     J = _lib.f64(node_params[0], device)
     h = _lib.f64(node_params[1], device)
     batched = h.dim() == 3
-    if h.dim() not in (2, 3) or J.shape != h.shape:
-        raise ValueError("node_params shapes %s %s not supported (diagonal (T,n) or (B,T,n))"
+    if h.dim() not in (2, 3) or (J.shape != h.shape and J.shape != h.shape + h.shape[-1:]):
+        raise ValueError("node_params shapes %s %s not supported (h (T,n) or (B,T,n); J like h or dense)"
                          % (tuple(J.shape), tuple(h.shape)))
     if not batched:
         J, h = J[None], h[None]
@@ -88,13 +88,19 @@ def _canonical_pair_params(pair_params, B, T, n, device):
 
 def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=None,
                       per_t_pair_stats=False, want_stats=True, generator=None, check_status=False,
-                      save_for_bwd=False, buffers=None):
+                      save_for_bwd=False, buffers=None, messages_out=False, from_messages=None):
     """One launch of the fused filter + smoother + sampler kernel.  Returns a dict of raw tensors.
-    With save_for_bwd the workspace keeps what lds_estep_backward needs (returned as out["workspace"])."""
+    With save_for_bwd the workspace keeps what lds_estep_backward needs (returned as out["workspace"]).
+    messages_out: also return the prediction messages (out["J_pred"], out["h_pred"]).
+    from_messages = (J_filt (B,T,n,n), h_filt (B,T,n)): run the backward sweeps from these filtered messages
+    instead of the kernel's own (node_params must then be zero)."""
     h_any = node_params[1]
     device = h_any.device if torch.is_tensor(h_any) and h_any.is_cuda else torch.device("cuda", torch.cuda.current_device())
     nJ, nh, nlogZ, batched = _canonical_node_params(node_params, device)
     B, T, n = nh.shape
+    dense, nJd = nJ.dim() == 4, None
+    if dense:                      # dense precisions ride the cold port; the diagonal port gets zeros
+        nJd, nJ = nJ, torch.zeros_like(nh)
     if n > _lib.SVAE_LDS_MAX_N:
         raise ValueError("latent dimension %d > %d" % (n, _lib.SVAE_LDS_MAX_N))
     iJ, ih, ilogZ = _canonical_init_params(init_params, device)
@@ -117,7 +123,7 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
         eps = torch.randn((B, T, S, n), dtype=torch.float64, device=device, generator=generator)
 
     L = _lib.lib()
-    flags = (_lib.SVAE_LDS_PER_T_PAIR_STATS if per_t_pair_stats else 0) | (_lib.SVAE_LDS_SAVE_FOR_BWD if save_for_bwd else 0) \
+    flags = (_lib.SVAE_LDS_PER_T_PAIR_STATS if (per_t_pair_stats or dense) else 0) | (_lib.SVAE_LDS_SAVE_FOR_BWD if save_for_bwd else 0) \
         | (_lib.SVAE_LDS_INIT_PER_SEQ if init_per_seq else 0)
     _pool = dict(buffers) if buffers else {}
 
@@ -134,8 +140,17 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
         out["E_init_xx"], out["E_init_x"] = new(B, n, n, name="E_init_xx"), new(B, n, name="E_init_x")
         out["E_pair_xx"], out["E_pair_xxn"], out["E_pair_xnxn"] = \
             new(B, n, n, name="E_pair_xx"), new(B, n, n, name="E_pair_xxn"), new(B, n, n, name="E_pair_xnxn")
+    if per_t_pair_stats or dense:
+        out["Exx_t"] = new(B, T, n, n)
     if per_t_pair_stats:
-        out["Exx_t"], out["Exxn_t"] = new(B, T, n, n), new(B, max(T - 1, 0), n, n)
+        out["Exxn_t"] = new(B, max(T - 1, 0), n, n)
+    if messages_out:
+        out["J_pred"], out["h_pred"] = new(B, T, n, n), new(B, T, n)
+    inJ = inh = None
+    if from_messages is not None:
+        inJ, inh = (_lib.f64(x, device).contiguous() for x in from_messages)
+        if inJ.shape != (B, T, n, n) or inh.shape != (B, T, n):
+            raise ValueError("from_messages must be ((B,T,n,n), (B,T,n))")
     status = _pool.get("status")
     if status is None:
         status = torch.zeros(1, dtype=torch.int32, device=device)
@@ -145,7 +160,7 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
         work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=device)
     g = out.get
     P = _lib.ptr
-    code = L.svae_lds_estep_fwd(
+    code = L.svae_lds_estep_fwd_ex(
         B, T, n, S, flags,
         P(iJ), P(ih), P(ilogZ),
         P(J11), P(J12), P(J22), P(plogZ), st, sb,
@@ -155,10 +170,14 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
         P(out["E_node_xx"]), P(out["E_node_x"]),
         P(out["samples"]), P(out["lognorm"]),
         P(g("Exx_t")), P(g("Exxn_t")),
+        P(g("J_pred")), P(g("h_pred")), P(inJ), P(inh), P(nJd),
         ctypes.c_void_p(status.data_ptr()), ctypes.c_void_p(work.data_ptr()), wbytes,
         _lib.stream_ptr(device))
-    _lib.check(code, "svae_lds_estep_fwd")
+    _lib.check(code, "svae_lds_estep_fwd_ex")
     out["status"] = status
+    out["dense"] = dense
+    if dense:
+        out["E_node_xx"] = out["Exx_t"]      # full second moments (lds_inference.py:164-167)
     if save_for_bwd:
         out["workspace"], out["workspace_bytes"] = work, wbytes
     if check_status:
@@ -280,20 +299,30 @@ def lds_estep_backward(o, g):
     gp = lambda k: None if g.get(k) is None else _lib.f64(g[k], dev)
     keep = {k: gp(k) for k in ("samples", "E_init_xx", "E_init_x", "E_pair_xx", "E_pair_xxn", "E_pair_xnxn",
                                "Exx_t", "Exxn_t", "E_node_xx", "E_node_x", "lognorm")}
-    gJ = torch.empty((B, T, n), dtype=torch.float64, device=dev)
+    dense = bool(o.get("dense"))
+    gJd = None
+    if dense:     # cotangent of the full E[x_t x_t'] joins the per-time port; the result is a full matrix
+        a, b2 = keep["E_node_xx"], keep["Exx_t"]
+        keep["Exx_t"] = a if b2 is None else (b2 if a is None else a + b2)
+        keep["E_node_xx"] = None
+        gJd = torch.empty((B, T, n, n), dtype=torch.float64, device=dev)
+    keep = {k: (None if v is None else v.contiguous()) for k, v in keep.items()}
+    gJ = None if dense else torch.empty((B, T, n), dtype=torch.float64, device=dev)
     gh = torch.empty((B, T, n), dtype=torch.float64, device=dev)
     P = _lib.ptr
-    code = _lib.lib().svae_lds_estep_bwd(
+    code = _lib.lib().svae_lds_estep_bwd_ex(
         B, T, n, S, 0,
         P(o["E_node_x"]), P(o["samples"]), P(o["eps"]),
         P(keep["samples"]), P(keep["E_init_xx"]), P(keep["E_init_x"]),
         P(keep["E_pair_xx"]), P(keep["E_pair_xxn"]), P(keep["E_pair_xnxn"]),
         P(keep["Exx_t"]), P(keep["Exxn_t"]),
         P(keep["E_node_xx"]), P(keep["E_node_x"]), P(keep["lognorm"]),
-        P(gJ), P(gh),
+        P(gJ), P(gh), P(gJd),
         ctypes.c_void_p(o["workspace"].data_ptr()), o["workspace_bytes"], _lib.stream_ptr(dev))
-    _lib.check(code, "svae_lds_estep_bwd")
+    _lib.check(code, "svae_lds_estep_bwd_ex")
     o["workspace"] = None   # single use, like the reference's intermediates
+    if dense:               # d/dJ_node of a symmetric port: -2 sym(Pbar_t)
+        gJ = -(gJd + gJd.transpose(-1, -2))
     return gJ, gh
 
 
@@ -309,7 +338,10 @@ class _LDSEStepFn(torch.autograd.Function):
     def forward(ctx, nJ, nh, nlogZ, eps, init_params, pair_params, S, per_t):
         node = (nJ, nh) if nlogZ is None else (nJ, nh, nlogZ)
         o = lds_estep_forward(init_params, pair_params, node, S, eps, per_t_pair_stats=per_t, save_for_bwd=True)
-        ctx.o, ctx.names, ctx.has_logZ = o, (_OUT_PER_T if per_t else _OUT_HOMOG), nlogZ is not None
+        names = _OUT_PER_T if per_t else _OUT_HOMOG
+        if o["dense"] and per_t:      # E_node_xx IS Exx_t: hand autograd the tensor once
+            names = tuple(k for k in names if k != "E_node_xx")
+        ctx.o, ctx.names, ctx.has_logZ = o, names, nlogZ is not None
         ctx.set_materialize_grads(False)
         outs = tuple(o[k] for k in ctx.names)
         if o["samples"] is None:
@@ -347,8 +379,13 @@ def _estep(init_params, pair_params, node_params, S, eps, per_t, generator=None)
         eps = eps[None] if (not batched and eps.dim() == 3) else eps
     outs = _LDSEStepFn.apply(nJ, nh, nlogZ, eps, init_params, pair_params, S, per_t)
     names = _OUT_PER_T if per_t else _OUT_HOMOG
+    dense = nJ.dim() == 4
+    if dense and per_t:
+        names = tuple(k for k in names if k != "E_node_xx")
     o = dict(zip(names, outs))
-    o.update(B=B, T=T, n=n, S=S, batched=batched, eps=eps)
+    if dense and per_t:
+        o["E_node_xx"] = o["Exx_t"]
+    o.update(B=B, T=T, n=n, S=S, batched=batched, eps=eps, dense=dense)
     if S == 0:
         o["samples"] = None
     return o
@@ -422,3 +459,62 @@ def natural_lds_sample(natparam, node_params, num_samples=1, eps=None, generator
 
 
 cython_natural_lds_sample = natural_lds_sample
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's three primitives (lds_inference.py:18-39, cython_lds_inference.pyx:28,149,310), each one
+# launch of the same fused kernel with the message ports of svae_lds_estep_fwd_ex open.  Forward values
+# only: gradients flow through the fused natural_lds_* entry points above.
+# ------------------------------------------------------------------------------------------------
+
+def natural_filter_forward_general(init_params, pair_params, node_params):
+    """((prediction_messages, filtered_messages), lognorm) -- cython_lds_inference.pyx:28-90.
+
+    Messages are natural-parameter pairs (J (B,T,n,n), h (B,T,n)) [no B axis for unbatched node_params];
+    the filtered message is the prediction message conditioned on the node potential (pyx:64-66)."""
+    o = lds_estep_forward(init_params, pair_params, node_params, 0, None, want_stats=False, messages_out=True)
+    device = o["J_pred"].device
+    nJ, nh, _, _ = _canonical_node_params(node_params, device)
+    J_filt = o["J_pred"] + (torch.diag_embed(nJ) if nJ.dim() == 3 else nJ)
+    h_filt = o["h_pred"] + nh
+    msgs = ((o["J_pred"], o["h_pred"]), (J_filt, h_filt))
+    if not o["batched"]:
+        msgs = tuple(tuple(x[0] for x in m) for m in msgs)
+        return msgs, o["lognorm"][0]
+    return msgs, o["lognorm"]
+
+
+def _messages_run(forward_messages, pair_params, num_samples, eps, generator, want_stats):
+    _, (J_filt, h_filt) = forward_messages
+    device = h_filt.device if torch.is_tensor(h_filt) and h_filt.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    J_filt, h_filt = _lib.f64(J_filt, device), _lib.f64(h_filt, device)
+    batched = h_filt.dim() == 3
+    if not batched:
+        J_filt, h_filt = J_filt[None], h_filt[None]
+        if eps is not None and torch.as_tensor(eps).dim() == 3:
+            eps = torch.as_tensor(eps)[None]
+    B, T, n = h_filt.shape
+    zero = torch.zeros((B, T, n), dtype=torch.float64, device=device)
+    init = (-0.5 * torch.eye(n, dtype=torch.float64, device=device), zero[0, 0], 0.)   # overridden by the messages
+    homog = _is_homog(pair_params)
+    o = lds_estep_forward(init, pair_params, (zero, zero, None), num_samples, eps, per_t_pair_stats=not homog,
+                          want_stats=want_stats, generator=generator, from_messages=(J_filt, h_filt))
+    o["batched"] = batched
+    return o, homog
+
+
+def natural_smoother_general(forward_messages, pair_params):
+    """(E_init_stats, E_pair_stats, E_node_stats) from given forward messages -- pyx:149-195."""
+    o, homog = _messages_run(forward_messages, pair_params, 0, None, None, True)
+    return _pack_stats(o, homog)[1]
+
+
+def natural_sample_backward(forward_messages, pair_params, num_samples=1, eps=None, generator=None):
+    """samples (B,T,S,n) drawn backwards from given filtered messages -- pyx:310-355."""
+    o, _ = _messages_run(forward_messages, pair_params, num_samples, eps, generator, False)
+    return o["samples"] if o["batched"] else o["samples"][0]
+
+
+cython_natural_filter_forward = natural_filter_forward_general
+cython_natural_smoother_general = natural_smoother_general
+cython_natural_sample_backward = natural_sample_backward

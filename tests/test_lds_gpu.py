@@ -149,7 +149,7 @@ def test_unbatched_like_the_reference():
     assert samples.shape == (T, 2, n) and lognorm.dim() == 0 and E_pair[1].shape == (n, n)
     with pytest.raises(ValueError):
         K.natural_lds_inference_general((tuple(_gpu(x) for x in init), tuple(_gpu(x) for x in pair)),
-                                        (_gpu(np.zeros((T, n, n))), _gpu(node[1][0])), 1)
+                                        (_gpu(np.zeros((T, n + 1))), _gpu(node[1][0])), 1)   # lds_inference.py:80
 
 
 def test_long_sequence_no_drift():

@@ -109,7 +109,9 @@ int svae_lds_estep_fwd(
  *       reference's pure-Python option (svae/lds/lds_inference.py:65-80, svae/lds/gaussian.py:46-49) that its Cython
  *       path rejects (pyx:43).  With it E_node_stats[0] is the full E[x_t x_t'] = Exx_t (lds_inference.py:164-167):
  *       pass SVAE_LDS_PER_T_PAIR_STATS and Exx_t (Exxn_t may stay NULL).
- * Any of the five may be NULL.
+ *   term_J (B,n,n): a dense precision (natural form) added at the LAST step only -- how a chunk of a longer chain
+ *       receives the message from its future (parallel-in-time driver, svae_lds_compose_chunks below).
+ * Any of the six may be NULL.
  */
 int svae_lds_estep_fwd_ex(
     int B, int T, int n, int S, int flags,
@@ -124,8 +126,26 @@ int svae_lds_estep_fwd_ex(
     double* samples, double* lognorm,
     double* Exx_t, double* Exxn_t,
     double* msg_J_pred, double* msg_h_pred, const double* in_J_filt, const double* in_h_filt,
-    const double* node_J_dense,
+    const double* node_J_dense, const double* term_J,
     int* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Parallel-in-time stage 1 (small batch, long T).  Cuts every sequence into
+ * C = svae_lds_compose_num_chunks(T, chunk_len) chunks of chunk_len steps (the last may be shorter) and integrates the
+ * node and pair potentials of each chunk -- the factors natural_filter_forward_general eliminates one by one
+ * (svae/lds/lds_inference.py:86-106, svae/lds/gaussian.py:46-66) -- into ONE pair potential on the chunk's end states:
+ *   chunk_J11, chunk_J12, chunk_J22 (B,C,n,n), chunk_logZ (B,C): natural form, the layout svae_lds_estep_fwd takes as
+ *       per-sequence time-inhomogeneous pair parameters (pair_stride_t = n*n, pair_stride_b = C*n*n);
+ *   chunk_e1, chunk_e2 (B,C,n): linear terms on the chunk's first / last state (node_h of the boundary chain).
+ * Homogeneous pair parameters (n,n), diagonal node potentials (B,T,n); node_logZ (B,T) / pair_logZ (1) may be NULL.
+ * *status (may be NULL): 1 + index of the first sequence with a non-positive pivot.
+ */
+int svae_lds_compose_num_chunks(int T, int chunk_len);
+int svae_lds_compose_chunks(int B, int T, int n, int chunk_len, const double* J11, const double* J12,
+                            const double* J22, const double* pair_logZ, const double* node_J,
+                            const double* node_h, const double* node_logZ, double* chunk_J11,
+                            double* chunk_J12, double* chunk_J22, double* chunk_logZ, double* chunk_e1,
+                            double* chunk_e2, int* status, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * LDS local E-step, backward: the VJP of svae_lds_estep_fwd with respect to the node potentials

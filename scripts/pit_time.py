@@ -1,0 +1,34 @@
+"""Dev timing: sequential fused kernel vs parallel-in-time driver in the small-B / long-T regime."""
+import sys, os, time
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import numpy as np, torch
+from oracle import lds_numpy as O
+from svae_b200.lds import lds_inference as K, lds_pit
+
+
+def timeit(f, it=5):
+    f(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(it):
+        f()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / it
+
+
+g = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float64, device="cuda")
+for n, T, B, S in [(10, 20000, 1, 1), (10, 2000, 16, 1), (10, 100000, 1, 1), (10, 5000, 4, 0), (16, 4000, 8, 1), (10, 200, 64, 1)]:
+    rng = np.random.default_rng(0)
+    init, pair = O.rand_lds_natparam(n, rng)
+    node = O.rand_node_potentials(B, T, n, rng)
+    nat = (tuple(g(x) for x in init), tuple(g(x) for x in pair))
+    nd = tuple(g(x) for x in node)
+    eps = torch.randn((B, T, S, n), dtype=torch.float64, device="cuda") if S else None
+    t_seq = timeit(lambda: K.natural_lds_inference_general(nat, nd, S, eps))
+    row = "n=%d T=%d B=%d S=%d  sequential %.2f ms |" % (n, T, B, S, t_seq)
+    for Lc in (None, 32, 64, 128, 256):
+        if Lc and Lc >= T - 1:
+            continue
+        t_par = timeit(lambda: lds_pit.natural_lds_inference_parallel(nat, nd, S, eps, chunk_len=Lc))
+        row += " Lc=%s %.2f ms (x%.1f)" % (Lc or "sqrt", t_par, t_seq / t_par)
+    print(row, flush=True)

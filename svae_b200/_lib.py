@@ -33,7 +33,9 @@ _SIGNATURES = {
     "svae_b200_launch_count": (ctypes.c_uint64, []),
     "svae_lds_estep_workspace_bytes": (_SZ, [_I] * 5),
     "svae_lds_estep_fwd": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 15 + [_P, _P, _SZ, _P]),
-    "svae_lds_estep_fwd_ex": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 20 + [_P, _P, _SZ, _P]),
+    "svae_lds_estep_fwd_ex": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 21 + [_P, _P, _SZ, _P]),
+    "svae_lds_compose_num_chunks": (_I, [_I, _I]),
+    "svae_lds_compose_chunks": (_I, [_I] * 4 + [_P] * 13 + [_P, _P]),
     "svae_lds_estep_bwd_ex": (_I, [_I] * 5 + [_P] * 17 + [_P, _SZ, _P]),
     "svae_lds_estep_bwd": (_I, [_I] * 5 + [_P] * 16 + [_P, _SZ, _P]),
     "svae_lds_reduce_stats_workspace_bytes": (_SZ, [_I]),

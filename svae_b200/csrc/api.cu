@@ -66,7 +66,7 @@ extern "C" int svae_lds_estep_fwd_ex(
     double* samples, double* lognorm,
     double* Exx_t, double* Exxn_t,
     double* msg_J_pred, double* msg_h_pred, const double* in_J_filt, const double* in_h_filt,
-    const double* node_J_dense,
+    const double* node_J_dense, const double* term_J,
     int* status, void* workspace, size_t workspace_bytes, void* stream) {
   if (B <= 0 || T <= 0 || n <= 0 || S < 0) return SVAE_ERR_BAD_ARG;
   if (!init_J || !init_h || !node_J || !node_h || !workspace) return SVAE_ERR_BAD_ARG;
@@ -92,7 +92,7 @@ extern "C" int svae_lds_estep_fwd_ex(
   const bool per_t = (flags & SVAE_LDS_PER_T_PAIR_STATS) != 0;
   p.Exx_t = per_t ? Exx_t : nullptr; p.Exxn_t = per_t ? Exxn_t : nullptr;
   p.msg_J_pred = msg_J_pred; p.msg_h_pred = msg_h_pred; p.in_J_filt = in_J_filt; p.in_h_filt = in_h_filt;
-  p.node_J_dense = node_J_dense;
+  p.node_J_dense = node_J_dense; p.term_J = term_J;
   p.status = status;
   p.stash = static_cast<double*>(workspace);
   const bool inhomog = (pair_stride_t != 0 || pair_stride_b != 0) && T > 1;
@@ -117,7 +117,7 @@ extern "C" int svae_lds_estep_fwd(
   return svae_lds_estep_fwd_ex(B, T, n, S, flags, init_J, init_h, init_logZ, J11, J12, J22, pair_logZ, pair_stride_t,
                                pair_stride_b, node_J, node_h, node_logZ, eps, E_init_xx, E_init_x, E_pair_xx, E_pair_xxn,
                                E_pair_xnxn, E_node_xx, E_node_x, samples, lognorm, Exx_t, Exxn_t, nullptr, nullptr, nullptr,
-                               nullptr, nullptr, status, workspace, workspace_bytes, stream);
+                               nullptr, nullptr, nullptr, status, workspace, workspace_bytes, stream);
 }
 
 extern "C" int svae_lds_estep_bwd_ex(

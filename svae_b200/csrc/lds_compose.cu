@@ -1,0 +1,70 @@
+// lds_compose.cu -- svae_lds_compose_chunks: one warp per (sequence, chunk) integrates a chunk of the LDS chain into a
+// single pair potential (lds_compose_core.h).  Stage 1 of the parallel-in-time E-step for the small-batch / long-T
+// regime; stages 2 and 3 are ordinary launches of the fused E-step kernel.
+#include <atomic>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "svae_b200.h"
+#include "lds_compose_core.h"
+
+extern std::atomic<uint64_t> g_svae_launches;
+
+namespace {
+constexpr int kWarps = 4;
+
+struct ComposeParams {
+  int B, T, n, Lc, C;
+  const double *J11, *J12, *J22, *pair_logZ, *node_J, *node_h, *node_logZ;
+  double *cJ11, *cJ12, *cJ22, *clogZ, *ce1, *ce2;
+  int* status;
+};
+
+__global__ void __launch_bounds__(32 * kWarps) lds_compose_kernel(const ComposeParams p) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5;
+  const long long tile = (long long)blockIdx.x * kWarps + warp;
+  if (tile >= (long long)p.B * p.C) return;           // warp-uniform
+  const int b = (int)(tile / p.C), c = (int)(tile % p.C);
+  const int s = c * p.Lc;
+  const int L = min(p.Lc, p.T - 1 - s);
+  const int n = p.n, nn = n * n;
+  const size_t bt = (size_t)b * p.T;
+  const int bad = svae::compose_chunk(
+      smem + (size_t)warp * svae::compose_tile_doubles(n), n, s, L, p.J11, p.J12, p.J22, p.pair_logZ ? *p.pair_logZ : 0.0,
+      p.node_J + bt * n, p.node_h + bt * n, p.node_logZ ? p.node_logZ + bt : nullptr, p.cJ11 + tile * nn,
+      p.cJ12 + tile * nn, p.cJ22 + tile * nn, p.clogZ + tile, p.ce1 + tile * n, p.ce2 + tile * n);
+  if (bad && p.status && (threadIdx.x & 31) == 0) atomicCAS(p.status, 0, b + 1);
+}
+}  // namespace
+
+extern "C" int svae_lds_compose_num_chunks(int T, int chunk_len) {
+  if (T < 2 || chunk_len < 1) return 0;
+  return (T - 1 + chunk_len - 1) / chunk_len;
+}
+
+extern "C" int svae_lds_compose_chunks(int B, int T, int n, int chunk_len, const double* J11, const double* J12,
+                                       const double* J22, const double* pair_logZ, const double* node_J,
+                                       const double* node_h, const double* node_logZ, double* chunk_J11,
+                                       double* chunk_J12, double* chunk_J22, double* chunk_logZ, double* chunk_e1,
+                                       double* chunk_e2, int* status, void* stream) {
+  if (B <= 0 || T < 2 || n <= 0 || chunk_len < 1) return SVAE_ERR_BAD_ARG;
+  if (!J11 || !J12 || !J22 || !node_J || !node_h || !chunk_J11 || !chunk_J12 || !chunk_J22 || !chunk_logZ || !chunk_e1 ||
+      !chunk_e2)
+    return SVAE_ERR_BAD_ARG;
+  if (n > SVAE_LDS_MAX_N) return SVAE_ERR_UNSUPPORTED;
+  ComposeParams p;
+  p.B = B; p.T = T; p.n = n; p.Lc = chunk_len; p.C = svae_lds_compose_num_chunks(T, chunk_len);
+  p.J11 = J11; p.J12 = J12; p.J22 = J22; p.pair_logZ = pair_logZ;
+  p.node_J = node_J; p.node_h = node_h; p.node_logZ = node_logZ;
+  p.cJ11 = chunk_J11; p.cJ12 = chunk_J12; p.cJ22 = chunk_J22; p.clogZ = chunk_logZ; p.ce1 = chunk_e1; p.ce2 = chunk_e2;
+  p.status = status;
+  const size_t smem = sizeof(double) * (size_t)kWarps * svae::compose_tile_doubles(n);
+  cudaError_t e = cudaSuccess;
+  if (smem > 48 * 1024) e = cudaFuncSetAttribute(lds_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return SVAE_ERR_CUDA;
+  const long long tiles = (long long)B * p.C;
+  const unsigned grid = (unsigned)((tiles + kWarps - 1) / kWarps);
+  lds_compose_kernel<<<grid, 32 * kWarps, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  g_svae_launches.fetch_add(1);
+  return cudaGetLastError() == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
+}

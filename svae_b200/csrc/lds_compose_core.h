@@ -1,0 +1,179 @@
+// lds_compose_core.h -- chunk composition for the parallel-in-time LDS E-step.
+//
+// A chunk of L consecutive steps of the chain   node_t(x_t) . pair(x_t, x_{t+1}),  t = s .. s+L-1
+// (the potentials natural_filter_forward_general eliminates one at a time, svae/lds/lds_inference.py:86-106,
+// svae/lds/gaussian.py:46-66) is integrated over its interior states into ONE pair potential on (x_s, x_{s+L}):
+//
+//   psi(x, y) = exp( -1/2 x'L11 x - x'L12 y - 1/2 y'L22 y + e1'x + e2'y + c ).
+//
+// Appending step t (M = L22 + diag(Jnode_t) + J11,  v = e2 + hnode_t,  M = L D L'):
+//   R = L^-1 J12,  W = L^-1 L12',  u = L^-1 v
+//   L11 -= W' D^-1 W      e1 -= W' D^-1 u      L12' <- -R' D^-1 W
+//   L22 <- J22 - R' D^-1 R        e2 <- -R' D^-1 u
+//   c += logZnode_t + logZpair + 1/2 u' D^-1 u - 1/2 sum log D      (same dropped constants as gaussian.py:52-66)
+// i.e. natural_predict on (L22, e2) plus the carry of the dependence on the chunk's first state.
+//
+// The code is written as PHASES: in each phase lane c touches only column c of the tile matrices and reads what
+// earlier phases wrote, so one warp runs it with __syncwarp() between phases and a plain loop over lanes
+// reproduces it on the host (tests/emul builds exactly this header with g++ to pin the arithmetic on CPU).
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define SVAE_HD __host__ __device__ __forceinline__
+#else
+#define SVAE_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define SVAE_PHASE(c, lanes) { const int c = (int)(threadIdx.x & 31); if (c < (lanes))
+#define SVAE_PHASE_END __syncwarp(); }
+#else
+#define SVAE_PHASE(c, lanes) { for (int c = 0; c < (lanes); ++c)
+#define SVAE_PHASE_END }
+#endif
+
+namespace svae {
+
+SVAE_HD int compose_np(int n) { return n + (n & 1); }
+// doubles of tile memory one chunk needs
+SVAE_HD int compose_tile_doubles(int n) { const int NP = compose_np(n); return 9 * n * NP + 8 * NP; }
+
+struct ComposeTile {
+  // n x NP matrices, element (i, c) at [i * NP + c]: lane c owns column c
+  double *M, *R, *W;          // elimination workspace: M | J12 | L12'
+  double *L11, *L12T, *L22;   // running element (L12T = L12 transposed)
+  double *J11, *J12, *J22;    // pair potential, information form
+  double *e1, *e2, *u, *mult, *dinv, *nJ, *nh, *acc;   // vectors (NP each)
+};
+
+SVAE_HD ComposeTile compose_tile(double* mem, int n) {
+  const int NP = compose_np(n), MM = n * NP;
+  ComposeTile t;
+  t.M = mem; t.R = mem + MM; t.W = mem + 2 * MM; t.L11 = mem + 3 * MM; t.L12T = mem + 4 * MM; t.L22 = mem + 5 * MM;
+  t.J11 = mem + 6 * MM; t.J12 = mem + 7 * MM; t.J22 = mem + 8 * MM;
+  double* v = mem + 9 * MM;
+  t.e1 = v; t.e2 = v + NP; t.u = v + 2 * NP; t.mult = v + 3 * NP; t.dinv = v + 4 * NP; t.nJ = v + 5 * NP; t.nh = v + 6 * NP;
+  t.acc = v + 7 * NP;
+  return t;
+}
+
+// Compose steps [s, s+L) of sequence-local arrays node_J/node_h (T,n) natural form (diag -1/2 precision), node_logZ
+// (T) or null; pair natural form (J11,J12,J22 (n,n) row-major, logZ).  Writes the chunk element in NATURAL form, the
+// layout the fused kernel takes as per-(b,t) pair parameters: out_J11 = -1/2 L11, out_J12 = -L12, out_J22 = -1/2 L22
+// (n,n row-major), out_logZ = c, out_e1, out_e2 (n).  Returns (uniformly) 0, or 1 + the step of a non-positive pivot.
+SVAE_HD int compose_chunk(double* mem, int n, int s, int L, const double* pJ11, const double* pJ12, const double* pJ22,
+                          double pair_logZ, const double* node_J, const double* node_h, const double* node_logZ,
+                          double* out_J11, double* out_J12, double* out_J22, double* out_logZ, double* out_e1,
+                          double* out_e2) {
+  const int NP = compose_np(n);
+  ComposeTile t = compose_tile(mem, n);
+  double cc = 0.0;
+  int bad = 0;
+  SVAE_PHASE(c, n) {
+    for (int i = 0; i < n; ++i) {
+      t.J11[i * NP + c] = -2.0 * pJ11[i * n + c];
+      t.J12[i * NP + c] = -pJ12[i * n + c];
+      t.J22[i * NP + c] = -2.0 * pJ22[i * n + c];
+    }
+  } SVAE_PHASE_END
+  // first step: the element of node_s . pair
+  SVAE_PHASE(c, n) {
+    for (int i = 0; i < n; ++i) {
+      t.L11[i * NP + c] = t.J11[i * NP + c] + (i == c ? -2.0 * node_J[(size_t)s * n + c] : 0.0);
+      t.L12T[i * NP + c] = t.J12[c * NP + i];
+      t.L22[i * NP + c] = t.J22[i * NP + c];
+    }
+    t.e1[c] = node_h[(size_t)s * n + c];
+    t.e2[c] = 0.0;
+  } SVAE_PHASE_END
+  cc = pair_logZ + (node_logZ ? node_logZ[s] : 0.0);
+
+  for (int q = 1; q < L; ++q) {
+    const size_t o = (size_t)(s + q) * n;
+    // augmented matrix [M | J12 | L12' | v]
+    SVAE_PHASE(c, n) {
+      for (int i = 0; i < n; ++i) {
+        t.M[i * NP + c] = t.L22[i * NP + c] + t.J11[i * NP + c] + (i == c ? -2.0 * node_J[o + c] : 0.0);
+        t.R[i * NP + c] = t.J12[i * NP + c];
+        t.W[i * NP + c] = t.L12T[i * NP + c];
+      }
+      t.u[c] = t.e2[c] + node_h[o + c];
+    } SVAE_PHASE_END
+    // elimination without pivoting: afterwards R = L^-1 J12, W = L^-1 L12', u = L^-1 v, pivots D
+    double logdet = 0.0;
+    for (int k = 0; k < n; ++k) {
+      const double piv = t.M[k * NP + k];
+      if (!(piv > 0.0) && !bad) bad = s + q + 1;
+      const double pinv = 1.0 / piv;
+      logdet += log(piv);
+      SVAE_PHASE(c, n) {
+        if (c > k) t.mult[c] = t.M[k * NP + c] * pinv;     // M symmetric: row k of the trailing block = column k
+        if (c == k) t.dinv[k] = pinv;
+      } SVAE_PHASE_END
+      SVAE_PHASE(c, n + 1) {
+        if (c < n) {
+          const double mk = t.M[k * NP + c], rk = t.R[k * NP + c], wk = t.W[k * NP + c];
+          for (int i = k + 1; i < n; ++i) {
+            const double m = t.mult[i];
+            if (c > k) t.M[i * NP + c] -= m * mk;
+            t.R[i * NP + c] -= m * rk;
+            t.W[i * NP + c] -= m * wk;
+          }
+        } else {
+          const double uk = t.u[k];
+          for (int i = k + 1; i < n; ++i) t.u[i] -= t.mult[i] * uk;
+        }
+      } SVAE_PHASE_END
+    }
+    double quad = 0.0;
+    for (int k = 0; k < n; ++k) quad += t.u[k] * t.u[k] * t.dinv[k];
+    cc += pair_logZ + (node_logZ ? node_logZ[s + q] : 0.0) + 0.5 * quad - 0.5 * logdet;
+    // products; the new L12' is staged in M (free now) because every lane still reads the old W
+    SVAE_PHASE(c, n + 1) {
+      if (c < n) {
+        for (int i = 0; i < n; ++i) {
+          double a11 = 0.0, a12 = 0.0, a22 = 0.0;
+          for (int k = 0; k < n; ++k) {
+            const double wd = t.W[k * NP + c] * t.dinv[k], rd = t.R[k * NP + c] * t.dinv[k];
+            a11 += t.W[k * NP + i] * wd;
+            a12 += t.R[k * NP + i] * wd;
+            a22 += t.R[k * NP + i] * rd;
+          }
+          t.L11[i * NP + c] -= a11;
+          t.M[i * NP + c] = -a12;
+          t.L22[i * NP + c] = t.J22[i * NP + c] - a22;
+        }
+      } else {
+        for (int i = 0; i < n; ++i) {
+          double a1 = 0.0, a2 = 0.0;
+          for (int k = 0; k < n; ++k) {
+            const double ud = t.u[k] * t.dinv[k];
+            a1 += t.W[k * NP + i] * ud;
+            a2 += t.R[k * NP + i] * ud;
+          }
+          t.e1[i] -= a1;
+          t.e2[i] = -a2;
+        }
+      }
+    } SVAE_PHASE_END
+    SVAE_PHASE(c, n) {
+      for (int i = 0; i < n; ++i) t.L12T[i * NP + c] = t.M[i * NP + c];
+    } SVAE_PHASE_END
+  }
+
+  SVAE_PHASE(c, n) {
+    for (int i = 0; i < n; ++i) {
+      // symmetrise the diagonal blocks against rounding drift; natural-form output
+      out_J11[i * n + c] = -0.25 * (t.L11[i * NP + c] + t.L11[c * NP + i]);
+      out_J22[i * n + c] = -0.25 * (t.L22[i * NP + c] + t.L22[c * NP + i]);
+      out_J12[i * n + c] = -t.L12T[c * NP + i];
+    }
+    out_e1[c] = t.e1[c];
+    out_e2[c] = t.e2[c];
+    if (c == 0) *out_logZ = cc;
+  } SVAE_PHASE_END
+  return bad;
+}
+
+}  // namespace svae

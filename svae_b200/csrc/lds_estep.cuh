@@ -56,6 +56,7 @@ struct LdsFwdParams {
   double *msg_J_pred, *msg_h_pred;          // optional outputs: prediction messages, natural form (B,T,n,n), (B,T,n)
   const double *in_J_filt, *in_h_filt;      // optional inputs: run the backward sweeps from GIVEN filtered messages
   const double *node_J_dense;               // optional input: dense node precisions (B,T,n,n), natural form (added to node_J)
+  const double *term_J;                     // optional input: dense precision (B,n,n) added at the LAST step only
   int* status;
   double* stash;
 };
@@ -247,7 +248,7 @@ __global__ void SVAE_LDS_BOUNDS(N, CPL) lds_estep_fwd_kernel(const LdsFwdParams 
     }
     const double* nd = nring + (t & 1) * NODE;
 
-    if (p.msg_J_pred || p.in_J_filt || p.node_J_dense) {
+    if (p.msg_J_pred || p.in_J_filt || p.node_J_dense || (p.term_J && last)) {
       // cold path: the three-primitive interface of the reference (messages out / messages in)
       const size_t off = (size_t)t * p.pair_stride_t + (size_t)b * p.pair_stride_b;
       const size_t bt = (size_t)b * T + t;
@@ -261,6 +262,7 @@ __global__ void SVAE_LDS_BOUNDS(N, CPL) lds_estep_fwd_kernel(const LdsFwdParams 
             if (p.msg_J_pred && valid) p.msg_J_pred[bt * NN + i * N + c[cl]] = -0.5 * (a[cl][i] - j11);
             if (p.in_J_filt) a[cl][i] = -2.0 * p.in_J_filt[bt * NN + i * N + c[cl]] + j11;
             if (p.node_J_dense) a[cl][i] -= 2.0 * p.node_J_dense[bt * NN + i * N + c[cl]];
+            if (p.term_J && last) a[cl][i] -= 2.0 * p.term_J[(size_t)b * NN + i * N + c[cl]];
           } else if (vec[cl]) {
             if (p.msg_h_pred && valid) p.msg_h_pred[bt * N + i] = a[cl][i] - nd[NP + i];
             if (p.in_h_filt) a[cl][i] = p.in_h_filt[bt * N + i];

@@ -88,12 +88,13 @@ def _canonical_pair_params(pair_params, B, T, n, device):
 
 def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=None,
                       per_t_pair_stats=False, want_stats=True, generator=None, check_status=False,
-                      save_for_bwd=False, buffers=None, messages_out=False, from_messages=None):
+                      save_for_bwd=False, buffers=None, messages_out=False, from_messages=None, term_J=None):
     """One launch of the fused filter + smoother + sampler kernel.  Returns a dict of raw tensors.
     With save_for_bwd the workspace keeps what lds_estep_backward needs (returned as out["workspace"]).
     messages_out: also return the prediction messages (out["J_pred"], out["h_pred"]).
     from_messages = (J_filt (B,T,n,n), h_filt (B,T,n)): run the backward sweeps from these filtered messages
-    instead of the kernel's own (node_params must then be zero)."""
+    instead of the kernel's own (node_params must then be zero).
+    term_J (B,n,n): dense natural-form precision added to the last step's node potential (lds_pit.py)."""
     h_any = node_params[1]
     device = h_any.device if torch.is_tensor(h_any) and h_any.is_cuda else torch.device("cuda", torch.cuda.current_device())
     nJ, nh, nlogZ, batched = _canonical_node_params(node_params, device)
@@ -151,6 +152,10 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
         inJ, inh = (_lib.f64(x, device).contiguous() for x in from_messages)
         if inJ.shape != (B, T, n, n) or inh.shape != (B, T, n):
             raise ValueError("from_messages must be ((B,T,n,n), (B,T,n))")
+    if term_J is not None:
+        term_J = _lib.f64(term_J, device).contiguous()
+        if term_J.shape != (B, n, n):
+            raise ValueError("term_J must be (B,n,n)")
     status = _pool.get("status")
     if status is None:
         status = torch.zeros(1, dtype=torch.int32, device=device)
@@ -170,7 +175,7 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
         P(out["E_node_xx"]), P(out["E_node_x"]),
         P(out["samples"]), P(out["lognorm"]),
         P(g("Exx_t")), P(g("Exxn_t")),
-        P(g("J_pred")), P(g("h_pred")), P(inJ), P(inh), P(nJd),
+        P(g("J_pred")), P(g("h_pred")), P(inJ), P(inh), P(nJd), P(term_J),
         ctypes.c_void_p(status.data_ptr()), ctypes.c_void_p(work.data_ptr()), wbytes,
         _lib.stream_ptr(device))
     _lib.check(code, "svae_lds_estep_fwd_ex")

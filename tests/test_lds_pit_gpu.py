@@ -1,0 +1,95 @@
+"""GPU: parallel-in-time LDS E-step (svae_lds_compose_chunks + boundary chain + chunk launches) against the
+sequential oracle -- pointwise, samples included (same noise => same paths)."""
+import numpy as np
+import pytest
+import torch
+from oracle import lds_numpy as O
+from util import rel_err
+import pit_numpy as P
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def _gpu(x):
+    return torch.as_tensor(np.asarray(x), dtype=torch.float64, device="cuda")
+
+
+def _g(tree):
+    return tuple(_gpu(x) for x in tree)
+
+
+def _problem(n, T, B, S, seed):
+    rng = np.random.default_rng(seed)
+    init, pair = O.rand_lds_natparam(n, rng)
+    node = O.rand_node_potentials(B, T, n, rng)
+    node = (node[0], node[1], 0.3 * rng.standard_normal((B, T)))
+    return init, pair, node, rng.standard_normal((B, T, S, n))
+
+
+@pytest.mark.parametrize("n,T,B,Lc", [(1, 9, 2, 3), (3, 14, 3, 4), (10, 41, 5, 8), (16, 20, 2, 7), (5, 12, 2, 1), (10, 203, 9, 16)])
+def test_compose_kernel_matches_dense_algebra(n, T, B, Lc):
+    from svae_b200.lds import lds_pit
+    init, pair, node, _ = _problem(n, T, B, 1, 10 + n)
+    want, w1, w2 = P.compose_numpy(pair, node, Lc)
+    got, g1, g2 = lds_pit.compose_chunks(_g(pair), _g(node), Lc)
+    for x, y in zip(want + (w1, w2), got + (g1, g2)):
+        assert rel_err(y.cpu().numpy(), x) < 1e-10
+
+
+@pytest.mark.parametrize("n,T,B,S,Lc", [
+    (4, 25, 2, 2, 6),          # T-1 divisible by Lc
+    (3, 14, 3, 1, 5),          # ragged tail chunk
+    (10, 200, 4, 1, None),     # metric shape, default chunk length, probes ride in the statistics launch
+    (16, 60, 2, 1, 9),         # n = 16: the unit probes need their own launches
+    (8, 50, 3, 0, 7),          # statistics only
+    (2, 400, 1, 3, 20),        # one long sequence
+])
+def test_parallel_equals_sequential(n, T, B, S, Lc):
+    from svae_b200.lds import lds_pit
+    init, pair, node, eps = _problem(n, T, B, S, 50 + n)
+    w_samples, (wE_init, wE_pair, wE_node), w_lognorm = O.natural_lds_inference_general((init, pair), node, eps)
+    samples, (E_init, E_pair, E_node), lognorm = lds_pit.natural_lds_inference_parallel(
+        (_g(init), _g(pair)), _g(node), num_samples=S, eps=_gpu(eps) if S else None, chunk_len=Lc)
+    c = lambda x: x.cpu().numpy()
+    assert rel_err(c(lognorm), w_lognorm) < RTOL
+    assert rel_err(c(E_init[0]), wE_init[0]) < RTOL and rel_err(c(E_init[1]), wE_init[1]) < RTOL
+    for k in range(3):
+        assert rel_err(c(E_pair[k]), wE_pair[k]) < RTOL, k
+    assert np.allclose(c(E_pair[3]), T - 1.0)
+    assert rel_err(c(E_node[0]), wE_node[0]) < RTOL and rel_err(c(E_node[1]), wE_node[1]) < RTOL
+    if S:
+        assert samples.shape == (B, T, S, n)
+        assert rel_err(c(samples), w_samples) < 1e-8
+    else:
+        assert samples is None
+
+
+def test_parallel_matches_the_fused_kernel_on_a_long_sequence():
+    """T = 20000, B = 1: against this package's own sequential kernel (the oracle would take minutes)."""
+    from svae_b200.lds import lds_pit, lds_inference as K
+    n, T, B, S = 10, 20000, 1, 1
+    init, pair, node, eps = _problem(n, T, B, S, 77)
+    nat, nd, e = (_g(init), _g(pair)), _g(node), _gpu(eps)
+    a = K.natural_lds_inference_general(nat, nd, S, e)
+    b = lds_pit.natural_lds_inference_parallel(nat, nd, S, e)
+    c = lambda x: x.cpu().numpy()
+    assert rel_err(c(b[2]), c(a[2])) < RTOL and rel_err(c(b[0]), c(a[0])) < 1e-7
+    for x, y in zip(a[1][1][:3] + a[1][2][:2], b[1][1][:3] + b[1][2][:2]):
+        assert rel_err(c(y), c(x)) < RTOL
+
+
+def test_unbatched_and_errors():
+    from svae_b200.lds import lds_pit
+    n, T = 3, 30
+    init, pair, node, eps = _problem(n, T, 1, 1, 5)
+    node1 = tuple(x[0] for x in node)
+    w = O.natural_lds_inference_general((init, pair), node, eps)
+    samples, stats, lognorm = lds_pit.natural_lds_inference_parallel((_g(init), _g(pair)), _g(node1), 1, _gpu(eps[0]), chunk_len=4)
+    assert samples.shape == (T, 1, n) and lognorm.dim() == 0
+    assert rel_err(samples.cpu().numpy(), w[0][0]) < 1e-8 and rel_err(lognorm.cpu().numpy(), w[2][0]) < RTOL
+    with pytest.raises(ValueError):       # dense node potentials are not chunked
+        lds_pit.natural_lds_inference_parallel((_g(init), _g(pair)), (_gpu(np.zeros((1, T, n, n))), _gpu(node[1])), 0)
+    hn = _gpu(node[1]).requires_grad_(True)
+    with pytest.raises(RuntimeError):     # forward-only
+        lds_pit.natural_lds_inference_parallel((_g(init), _g(pair)), (_gpu(node[0]), hn), 0)

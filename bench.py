@@ -338,6 +338,23 @@ def run_ours(args):
                     K.lds_estep_forward(gi2, gp2, (J2, h2), 1, e2)
                 b_.record(); torch.cuda.synchronize()
                 extra["lds_estep_d%d_T%d_B%d_seq_per_s" % (n2, T2, B2)] = B2 / (a.elapsed_time(b_) / 5 * 1e-3)
+            # small-batch / long-T regime: one sequence of 20000 steps, sequential vs
+            # parallel-in-time driver (same outputs, tests/test_lds_pit_gpu.py)
+            from svae_b200.lds import lds_pit
+            T3 = 20000
+            J3 = -0.5 * torch.nn.functional.softplus(torch.randn(1, T3, n, dtype=torch.float64, device=dev, generator=gen))
+            h3 = torch.randn(1, T3, n, dtype=torch.float64, device=dev, generator=gen)
+            e3 = torch.randn(1, T3, 1, n, dtype=torch.float64, device=dev, generator=gen)
+            for name, fn in (("sequential", lambda: K.natural_lds_inference_general((gi, gp), (J3, h3), 1, e3)),
+                             ("parallel_in_time", lambda: lds_pit.natural_lds_inference_parallel((gi, gp), (J3, h3), 1, e3))):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(5):
+                    fn()
+                b_.record(); torch.cuda.synchronize()
+                extra["lds_estep_d%d_T%d_B1_%s_ms" % (n, T3, name)] = a.elapsed_time(b_) / 5
         except Exception as e:  # pragma: no cover
             extra["error"] = repr(e)
 

@@ -217,6 +217,21 @@ int svae_hmm_estep(int B, int T, int K, int flags, const double* log_pi, const d
                    const double* node, double* logZ, double* Ez0, double* Etrans, double* Ez,
                    void* stream);
 
+/* Parallel-in-time HMM E-step, stages 1 and 2 (the sequential recursion is
+ * svae/hmm/hmm_inference.py:44-51, its reverse sweep svae/hmm/cython_hmm_inference.pyx:126-166).
+ *   svae_hmm_compose_chunks: C = svae_lds_compose_num_chunks(T, chunk_len) chunks per sequence; chunk_P (B,C,K,K) =
+ *       prod_t diag(exp(node_t)) A over the chunk's steps, scaled to max 1, chunk_logscale (B,C) the log of the scale.
+ *   svae_hmm_chain_messages: forward / backward messages at the C+1 chunk boundaries, log_alpha, log_beta (B,C+1,K)
+ *       (log_alpha excludes, log_beta includes the node potential at the boundary; node_last (B,K) is the node
+ *       potential of the last time step), and the total log-normaliser logZ (B).
+ * Stage 3 is svae_hmm_estep on the B*C chunks with log_alpha added to each chunk's first node potential, log_beta
+ * replacing its last one and log_pi = 0 (svae_b200/hmm/hmm_pit.py). */
+int svae_hmm_compose_chunks(int B, int T, int K, int chunk_len, const double* log_A, const double* node,
+                            double* chunk_P, double* chunk_logscale, void* stream);
+int svae_hmm_chain_messages(int B, int C, int K, const double* log_pi, const double* chunk_P,
+                            const double* chunk_logscale, const double* node_last, double* log_alpha,
+                            double* log_beta, double* logZ, void* stream);
+
 /* Viterbi path (svae/hmm/hmm_inference.py:54-63, pyhsmm `viterbi`): path (B,T) int32, first maximal
  * index on ties.  workspace: svae_hmm_viterbi_workspace_bytes() bytes of device scratch (back-pointers). */
 size_t svae_hmm_viterbi_workspace_bytes(int B, int T, int K);

@@ -32,3 +32,18 @@ for n, T, B, S in [(10, 20000, 1, 1), (10, 2000, 16, 1), (10, 100000, 1, 1), (10
         t_par = timeit(lambda: lds_pit.natural_lds_inference_parallel(nat, nd, S, eps, chunk_len=Lc))
         row += " Lc=%s %.2f ms (x%.1f)" % (Lc or "sqrt", t_par, t_seq / t_par)
     print(row, flush=True)
+
+from oracle import hmm_numpy as HO
+from svae_b200.hmm import hmm_inference as H, hmm_pit
+for K, T, B in [(32, 100000, 1), (32, 20000, 4), (8, 100000, 1), (32, 2000, 16), (32, 500, 64)]:
+    rng = np.random.default_rng(0)
+    lp, lA = HO.rand_hmm_natparam(K, rng)
+    nat = (g(lp), g(lA), torch.randn((B, T, K), dtype=torch.float64, device="cuda"))
+    t_seq = timeit(lambda: H.hmm_estep(nat))
+    row = "HMM K=%d T=%d B=%d  sequential %.2f ms |" % (K, T, B, t_seq)
+    for Lc in (None, 64, 256, 1024):
+        if Lc and Lc >= T - 1:
+            continue
+        t_par = timeit(lambda: hmm_pit.hmm_estep_parallel(nat, chunk_len=Lc))
+        row += " Lc=%s %.2f ms (x%.1f)" % (Lc or "sqrt", t_par, t_seq / t_par)
+    print(row, flush=True)

@@ -1,0 +1,164 @@
+// hmm_compose_core.h -- chunk composition and boundary messages for the parallel-in-time HMM E-step
+// (the sequential recursion is svae/hmm/hmm_inference.py:44-51 and its reverse sweep
+// svae/hmm/cython_hmm_inference.pyx:126-166).
+//
+// A chunk of L steps [s, s+L) of the chain  exp(node_t(z_t)) A(z_t, z_{t+1})  summed over its interior states is the
+// K x K matrix  Psi = prod_t (D_t A),  D_t = diag(exp(node_t)):  Psi(i, j) = weight of all paths from z_s = i to
+// z_{s+L} = j (node potentials s .. s+L-1 included, the one at s+L not).  It is kept as P = Psi / scale with
+// max(P) = 1 and log(scale) separately.  The boundary chain then needs one vector-matrix product per chunk in each
+// direction.
+//
+// Same phase discipline as lds_compose_core.h: in a phase lane j touches only column j (or entry j) of the tile
+// arrays and reads what earlier phases wrote, so a warp runs it with __syncwarp() between phases and a loop over the
+// lanes reproduces it on the host (tests/emul).
+#pragma once
+#include <math.h>
+#include "lds_compose_core.h"   // SVAE_HD, SVAE_PHASE, SVAE_PHASE_END
+
+#if defined(__CUDACC__)
+#define SVAE_UNROLL _Pragma("unroll")
+#else
+#define SVAE_UNROLL
+#endif
+
+namespace svae {
+
+SVAE_HD int hmm_compose_tile_doubles(int K) { return 3 * K * K + 3 * K; }
+
+// log_A (K,K) row = from-state; node (T,K) of this sequence.  Writes P (K,K) row-major with max entry 1 and
+// *logscale such that Psi = P * exp(*logscale).
+SVAE_HD void hmm_compose_chunk(double* mem, int K, int s, int L, const double* log_A, const double* node, double* out_P,
+                               double* out_logscale) {
+  double* A = mem;               // exp(log_A - amax), element (k, j) at [k*K + j]
+  double* P = mem + K * K;       // running product
+  double* PD = mem + 2 * K * K;  // P * D_t
+  double* colmax = mem + 3 * K * K;
+  double* d = colmax + K;
+  double* nd = d + K;
+  // global max of log_A (uniform)
+  SVAE_PHASE(j, K) {
+    double m = log_A[j];
+    for (int k = 1; k < K; ++k) m = fmax(m, log_A[k * K + j]);
+    colmax[j] = m;
+  } SVAE_PHASE_END
+  double amax = colmax[0];
+  for (int j = 1; j < K; ++j) amax = fmax(amax, colmax[j]);
+  SVAE_PHASE(j, K) {
+    for (int k = 0; k < K; ++k) {
+      A[k * K + j] = exp(log_A[k * K + j] - amax);
+      P[k * K + j] = (k == j) ? 1.0 : 0.0;
+    }
+  } SVAE_PHASE_END
+  double logscale = (double)L * amax;
+  for (int q = 0; q < L; ++q) {
+    const double* nt = node + (size_t)(s + q) * K;
+    SVAE_PHASE(j, K) { nd[j] = nt[j]; } SVAE_PHASE_END
+    double nmax = nd[0];
+    for (int j = 1; j < K; ++j) nmax = fmax(nmax, nd[j]);
+    SVAE_PHASE(j, K) { d[j] = exp(nd[j] - nmax); } SVAE_PHASE_END
+    SVAE_PHASE(j, K) {
+      for (int i = 0; i < K; ++i) PD[i * K + j] = P[i * K + j] * d[j];
+    } SVAE_PHASE_END
+    SVAE_PHASE(j, K) {
+      double acc[32];                      // fixed trip counts + predicates keep it in registers on the device
+      SVAE_UNROLL
+      for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const double a = A[k * K + j];
+        SVAE_UNROLL
+        for (int i = 0; i < 32; ++i)
+          if (i < K) acc[i] = fma(PD[i * K + k], a, acc[i]);
+      }
+      double m = 0.0;
+      SVAE_UNROLL
+      for (int i = 0; i < 32; ++i)
+        if (i < K) {
+          P[i * K + j] = acc[i];
+          m = fmax(m, acc[i]);
+        }
+      colmax[j] = m;
+    } SVAE_PHASE_END
+    double pmax = colmax[0];
+    for (int j = 1; j < K; ++j) pmax = fmax(pmax, colmax[j]);
+    const double inv = 1.0 / pmax;
+    SVAE_PHASE(j, K) {
+      for (int i = 0; i < K; ++i) P[i * K + j] *= inv;
+    } SVAE_PHASE_END
+    logscale += nmax + log(pmax);
+  }
+  SVAE_PHASE(j, K) {
+    for (int i = 0; i < K; ++i) out_P[i * K + j] = P[i * K + j];
+    if (j == 0) *out_logscale = logscale;
+  } SVAE_PHASE_END
+}
+
+SVAE_HD int hmm_chain_tile_doubles(int K) { return 4 * K; }
+
+// Boundary chain of one sequence: C chunk matrices P_c (K,K) with log scales, initial log pi, and the node potential
+// of the LAST time step.  Writes, for every boundary c = 0..C:
+//   log_alpha[c][j] = log p(z_{s_c} = j, node potentials before s_c) + const  (normalised: logsumexp = 0)
+//   log_beta[c][j]  = log p(node potentials from s_c on | z_{s_c} = j) + const (max = 0)
+// (both clamped below at kLogFloor so they can be added to node potentials), and the total log-normaliser.
+SVAE_HD void hmm_chain_messages(double* mem, int K, int C, const double* log_pi, const double* P, const double* logscale,
+                                const double* node_last, double* log_alpha, double* log_beta, double* out_logZ) {
+  const double kLogFloor = -700.0;
+  double* a = mem;        // current forward vector (normalised)
+  double* b = mem + K;    // current backward vector
+  double* tmp = mem + 2 * K;
+  double* red = mem + 3 * K;
+  SVAE_PHASE(j, K) { tmp[j] = log_pi[j]; } SVAE_PHASE_END
+  double m = tmp[0];
+  for (int j = 1; j < K; ++j) m = fmax(m, tmp[j]);
+  SVAE_PHASE(j, K) { a[j] = exp(tmp[j] - m); } SVAE_PHASE_END
+  double sum = 0.0;
+  for (int j = 0; j < K; ++j) sum += a[j];
+  double logZ = m + log(sum);
+  SVAE_PHASE(j, K) {
+    a[j] /= sum;
+    log_alpha[j] = fmax(log(a[j]), kLogFloor);
+  } SVAE_PHASE_END
+  for (int c = 0; c < C; ++c) {
+    const double* Pc = P + (size_t)c * K * K;
+    SVAE_PHASE(j, K) {
+      double acc = 0.0;
+      for (int i = 0; i < K; ++i) acc = fma(a[i], Pc[i * K + j], acc);
+      tmp[j] = acc;
+    } SVAE_PHASE_END
+    sum = 0.0;
+    for (int j = 0; j < K; ++j) sum += tmp[j];
+    logZ += logscale[c] + log(sum);
+    SVAE_PHASE(j, K) {
+      a[j] = tmp[j] / sum;
+      log_alpha[(size_t)(c + 1) * K + j] = fmax(log(a[j]), kLogFloor);
+    } SVAE_PHASE_END
+  }
+  // last node potential closes the normaliser and starts the backward vector
+  SVAE_PHASE(j, K) { tmp[j] = node_last[j]; } SVAE_PHASE_END
+  m = tmp[0];
+  for (int j = 1; j < K; ++j) m = fmax(m, tmp[j]);
+  SVAE_PHASE(j, K) {
+    b[j] = exp(tmp[j] - m);
+    red[j] = a[j] * b[j];
+    log_beta[(size_t)C * K + j] = fmax(tmp[j] - m, kLogFloor);
+  } SVAE_PHASE_END
+  sum = 0.0;
+  for (int j = 0; j < K; ++j) sum += red[j];
+  logZ += m + log(sum);
+  for (int c = C - 1; c >= 0; --c) {
+    const double* Pc = P + (size_t)c * K * K;
+    SVAE_PHASE(i, K) {
+      double acc = 0.0;
+      for (int j = 0; j < K; ++j) acc = fma(Pc[i * K + j], b[j], acc);
+      tmp[i] = acc;
+    } SVAE_PHASE_END
+    m = tmp[0];
+    for (int j = 1; j < K; ++j) m = fmax(m, tmp[j]);
+    SVAE_PHASE(j, K) {
+      b[j] = tmp[j] / m;
+      log_beta[(size_t)c * K + j] = fmax(log(b[j]), kLogFloor);
+    } SVAE_PHASE_END
+  }
+  SVAE_PHASE(j, 1) { *out_logZ = logZ; } SVAE_PHASE_END
+}
+
+}  // namespace svae

@@ -1,0 +1,58 @@
+"""Parallel-in-time HMM E-step for the small-batch / long-T regime.
+
+Same contract and numbers as hmm_estep (svae/hmm/hmm_inference.py:21-41), from three wide launches:
+  1. svae_hmm_compose_chunks -- each chunk's  prod_t diag(exp(node_t)) A  as one scaled K x K matrix (B x C warps);
+  2. svae_hmm_chain_messages -- forward / backward messages at the chunk boundaries and the total logZ (B warps,
+     one vector-matrix product per chunk and direction);
+  3. svae_hmm_estep on all B x C chunks as independent sequences: forward message added to the chunk's first node
+     potential, backward message in place of its last one, log pi = 0 -- so every chunk's forward-backward returns
+     the exact posterior marginals and expected transition counts of its steps.
+Forward values only.
+"""
+from __future__ import annotations
+import math
+import torch
+from .. import _lib
+from . import hmm_inference as H
+
+
+def hmm_estep_parallel(natparam, chunk_len=None):
+    """(logZ, (E[z_0], E[transition counts], E[z_t]))."""
+    lp, lA, node, batched, dev = H._canon(natparam)
+    B, T, K = node.shape
+    Lc = int(chunk_len) if chunk_len else max(2, int(round(math.sqrt(max(T - 1, 1)))))
+    if T < 4 or Lc >= T - 1:
+        return H.hmm_estep(natparam)
+    L = _lib.lib()
+    C = L.svae_lds_compose_num_chunks(T, Lc)
+    new = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)
+    P_, ls = new(B, C, K, K), new(B, C)
+    ptr, st = _lib.ptr, _lib.stream_ptr(dev)
+    _lib.check(L.svae_hmm_compose_chunks(B, T, K, Lc, ptr(lA), ptr(node), ptr(P_), ptr(ls), st), "svae_hmm_compose_chunks")
+    la, lb, logZ = new(B, C + 1, K), new(B, C + 1, K), new(B)
+    last = node[:, -1].contiguous()
+    _lib.check(L.svae_hmm_chain_messages(B, C, K, ptr(lp), ptr(P_), ptr(ls), ptr(last), ptr(la), ptr(lb), ptr(logZ), st),
+               "svae_hmm_chain_messages")
+    nfull = (T - 1) // Lc
+    tail = (T - 1) - nfull * Lc
+    Ez = new(B, T, K)
+    Etrans = torch.zeros((B, K, K), dtype=torch.float64, device=dev)
+    zero_pi = torch.zeros(K, dtype=torch.float64, device=dev)
+    Ez0 = None
+    for c0, cnt, Ls in [(0, nfull, Lc)] + ([(nfull, 1, tail)] if tail else []):
+        t0, t1 = c0 * Lc, c0 * Lc + cnt * Ls
+        sub = new(B, cnt, Ls + 1, K)
+        sub[:, :, :Ls] = node[:, t0:t1].reshape(B, cnt, Ls, K)
+        sub[:, :, 0] += la[:, c0:c0 + cnt]
+        sub[:, :, Ls] = lb[:, c0 + 1:c0 + cnt + 1]
+        _, e0, et, ez = H.hmm_estep_forward(zero_pi, lA, sub.reshape(B * cnt, Ls + 1, K))
+        Etrans += et.reshape(B, cnt, K, K).sum(1)
+        ez = ez.reshape(B, cnt, Ls + 1, K)
+        Ez[:, t0:t1] = ez[:, :, :Ls].reshape(B, cnt * Ls, K)
+        if t1 == T - 1:
+            Ez[:, -1] = ez[:, -1, Ls]
+        if c0 == 0:
+            Ez0 = e0.reshape(B, cnt, K)[:, 0].contiguous()
+    if not batched:
+        return logZ[0], (Ez0[0], Etrans[0], Ez[0])
+    return logZ, (Ez0, Etrans, Ez)

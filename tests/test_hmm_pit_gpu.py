@@ -1,0 +1,42 @@
+"""GPU: parallel-in-time HMM E-step against the sequential oracle and this package's sequential kernel."""
+import numpy as np
+import pytest
+import torch
+from oracle import hmm_numpy as HO
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(x):
+    return torch.as_tensor(np.asarray(x), dtype=torch.float64, device="cuda")
+
+
+@pytest.mark.parametrize("K,T,B,Lc", [(3, 10, 2, 3), (8, 41, 3, 7), (32, 50, 2, 10), (5, 9, 2, 1), (4, 30, 1, 12), (32, 400, 3, None),
+                                      (17, 203, 2, 16)])
+def test_parallel_equals_sequential_oracle(K, T, B, Lc):
+    from svae_b200.hmm import hmm_pit
+    rng = np.random.default_rng(K + T)
+    lp, lA = HO.rand_hmm_natparam(K, rng)
+    lA = lA + rng.standard_normal((K, 1))
+    node = 2.0 * rng.standard_normal((B, T, K))
+    w_logZ, (w0, wt, wz) = HO.hmm_estep((lp, lA, node))
+    logZ, (E0, Et, Ez) = hmm_pit.hmm_estep_parallel((_gpu(lp), _gpu(lA), _gpu(node)), chunk_len=Lc)
+    c = lambda x: x.cpu().numpy()
+    assert rel_err(c(logZ), w_logZ) < 1e-11
+    assert rel_err(c(E0), w0) < 1e-9 and rel_err(c(Et), wt) < 1e-9 and rel_err(c(Ez), wz) < 1e-9
+
+
+def test_long_sequence_against_the_sequential_kernel_and_unbatched():
+    from svae_b200.hmm import hmm_pit, hmm_inference as H
+    rng = np.random.default_rng(1)
+    K, T = 32, 50000
+    lp, lA = HO.rand_hmm_natparam(K, rng)
+    node = _gpu(rng.standard_normal((T, K)))
+    nat = (_gpu(lp), _gpu(lA), node)
+    a_logZ, (a0, at, az) = H.hmm_estep(nat)
+    b_logZ, (b0, bt, bz) = hmm_pit.hmm_estep_parallel(nat)
+    assert b_logZ.dim() == 0 and bz.shape == (T, K) and bt.shape == (K, K)
+    c = lambda x: x.cpu().numpy()
+    assert rel_err(c(b_logZ), c(a_logZ)) < 1e-11
+    assert rel_err(c(bz), c(az)) < 1e-8 and rel_err(c(bt), c(at)) < 1e-8 and rel_err(c(b0), c(a0)) < 1e-8

@@ -355,6 +355,18 @@ def run_ours(args):
                     fn()
                 b_.record(); torch.cuda.synchronize()
                 extra["lds_estep_d%d_T%d_B1_%s_ms" % (n, T3, name)] = a.elapsed_time(b_) / 5
+            from svae_b200.hmm import hmm_pit
+            hnode1 = torch.randn(1, 100000, 32, dtype=torch.float64, device=dev, generator=gen)
+            nat1 = (g(lp), g(lA), hnode1)
+            for name, fn in (("sequential", lambda: HK.hmm_estep(nat1)), ("parallel_in_time", lambda: hmm_pit.hmm_estep_parallel(nat1))):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(5):
+                    fn()
+                b_.record(); torch.cuda.synchronize()
+                extra["hmm_estep_K32_T100000_B1_%s_ms" % name] = a.elapsed_time(b_) / 5
         except Exception as e:  # pragma: no cover
             extra["error"] = repr(e)
 

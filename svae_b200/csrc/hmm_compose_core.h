@@ -23,71 +23,85 @@
 
 namespace svae {
 
-SVAE_HD int hmm_compose_tile_doubles(int K) { return 3 * K * K + 3 * K; }
+// Tile layout (compile-time strides so every shared-memory address in the hot loop is an immediate):
+//   A   [k*32 + j]            exp(log_A - amax)
+//   PDt [k*kHmmRow + i]       (P D)^T, double-buffered: row k = column k of P times d_k, contiguous in i so the product
+//                             loop reads it with 128-bit broadcasts; row stride 34 keeps rows 16-byte aligned and the
+//                             per-lane row stores at a 4-way bank conflict instead of 32-way.
+constexpr int kHmmRow = 34;
+SVAE_HD int hmm_compose_tile_doubles(int /*K*/) { return 32 * 32 + 2 * 32 * kHmmRow + 3 * 32; }
 
 // log_A (K,K) row = from-state; node (T,K) of this sequence.  Writes P (K,K) row-major with max entry 1 and
 // *logscale such that Psi = P * exp(*logscale).
 SVAE_HD void hmm_compose_chunk(double* mem, int K, int s, int L, const double* log_A, const double* node, double* out_P,
                                double* out_logscale) {
-  double* A = mem;               // exp(log_A - amax), element (k, j) at [k*K + j]
-  double* P = mem + K * K;       // running product
-  double* PD = mem + 2 * K * K;  // P * D_t
-  double* colmax = mem + 3 * K * K;
-  double* d = colmax + K;
-  double* nd = d + K;
-  // global max of log_A (uniform)
+  double* A = mem;
+  double* PDt0 = mem + 32 * 32;
+  double* PDt1 = PDt0 + 32 * kHmmRow;
+  double* colmax = PDt1 + 32 * kHmmRow;
+  double* d = colmax + 32;
+  double* nd = d + 32;
   SVAE_PHASE(j, K) {
     double m = log_A[j];
     for (int k = 1; k < K; ++k) m = fmax(m, log_A[k * K + j]);
     colmax[j] = m;
+    nd[j] = node[(size_t)s * K + j];
   } SVAE_PHASE_END
-  double amax = colmax[0];
-  for (int j = 1; j < K; ++j) amax = fmax(amax, colmax[j]);
+  double amax = colmax[0], nmax = nd[0];
+  for (int j = 1; j < K; ++j) {
+    amax = fmax(amax, colmax[j]);
+    nmax = fmax(nmax, nd[j]);
+  }
+  // P = I, so (P D_s)^T row k = d_k e_k
   SVAE_PHASE(j, K) {
-    for (int k = 0; k < K; ++k) {
-      A[k * K + j] = exp(log_A[k * K + j] - amax);
-      P[k * K + j] = (k == j) ? 1.0 : 0.0;
-    }
+    for (int k = 0; k < K; ++k) A[k * 32 + j] = exp(log_A[k * K + j] - amax);
+    const double dj = exp(nd[j] - nmax);
+    for (int i = 0; i < K; ++i) PDt0[j * kHmmRow + i] = (i == j) ? dj : 0.0;
+    if (L > 1) nd[j] = node[(size_t)(s + 1) * K + j];
   } SVAE_PHASE_END
-  double logscale = (double)L * amax;
+  double logscale = (double)L * amax + nmax;
+  double inv = 1.0;                      // 1 / max of the previous (unscaled) product, folded into the A operand
   for (int q = 0; q < L; ++q) {
-    const double* nt = node + (size_t)(s + q) * K;
-    SVAE_PHASE(j, K) { nd[j] = nt[j]; } SVAE_PHASE_END
-    double nmax = nd[0];
-    for (int j = 1; j < K; ++j) nmax = fmax(nmax, nd[j]);
-    SVAE_PHASE(j, K) { d[j] = exp(nd[j] - nmax); } SVAE_PHASE_END
-    SVAE_PHASE(j, K) {
-      for (int i = 0; i < K; ++i) PD[i * K + j] = P[i * K + j] * d[j];
-    } SVAE_PHASE_END
+    const double* cur = (q & 1) ? PDt1 : PDt0;
+    double* nxt = (q & 1) ? PDt0 : PDt1;
+    const bool more = q + 1 < L;
+    double nmax2 = 0.0;
+    if (more) {
+      nmax2 = nd[0];
+      for (int j = 1; j < K; ++j) nmax2 = fmax(nmax2, nd[j]);
+    }
     SVAE_PHASE(j, K) {
       double acc[32];                      // fixed trip counts + predicates keep it in registers on the device
       SVAE_UNROLL
       for (int i = 0; i < 32; ++i) acc[i] = 0.0;
       for (int k = 0; k < K; ++k) {
-        const double a = A[k * K + j];
+        const double a = A[k * 32 + j] * inv;
+        const double* row = cur + k * kHmmRow;
         SVAE_UNROLL
         for (int i = 0; i < 32; ++i)
-          if (i < K) acc[i] = fma(PD[i * K + k], a, acc[i]);
+          if (i < K) acc[i] = fma(row[i], a, acc[i]);
       }
       double m = 0.0;
+      const double dj = more ? exp(nd[j] - nmax2) : 1.0;
       SVAE_UNROLL
       for (int i = 0; i < 32; ++i)
         if (i < K) {
-          P[i * K + j] = acc[i];
           m = fmax(m, acc[i]);
+          nxt[j * kHmmRow + i] = acc[i] * dj;   // row j of the next (P D)^T (or of P^T after the last step)
         }
       colmax[j] = m;
     } SVAE_PHASE_END
     double pmax = colmax[0];
     for (int j = 1; j < K; ++j) pmax = fmax(pmax, colmax[j]);
-    const double inv = 1.0 / pmax;
-    SVAE_PHASE(j, K) {
-      for (int i = 0; i < K; ++i) P[i * K + j] *= inv;
-    } SVAE_PHASE_END
-    logscale += nmax + log(pmax);
+    inv = 1.0 / pmax;
+    logscale += log(pmax) + (more ? nmax2 : 0.0);
+    if (q + 2 < L) {
+      SVAE_PHASE(j, K) { nd[j] = node[(size_t)(s + q + 2) * K + j]; } SVAE_PHASE_END
+    }
   }
+  const double* fin = (L & 1) ? PDt1 : PDt0;
   SVAE_PHASE(j, K) {
-    for (int i = 0; i < K; ++i) out_P[i * K + j] = P[i * K + j];
+    for (int i = 0; i < K; ++i) out_P[i * K + j] = fin[j * kHmmRow + i] * inv;
     if (j == 0) *out_logscale = logscale;
   } SVAE_PHASE_END
 }

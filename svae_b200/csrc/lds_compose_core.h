@@ -14,8 +14,9 @@
 // i.e. natural_predict on (L22, e2) plus the carry of the dependence on the chunk's first state.
 //
 // The code is written as PHASES: in each phase lane c touches only column c of the tile matrices and reads what
-// earlier phases wrote, so one warp runs it with __syncwarp() between phases and a plain loop over lanes
-// reproduces it on the host (tests/emul builds exactly this header with g++ to pin the arithmetic on CPU).
+// earlier phases wrote, so one warp runs it with __syncwarp() around every phase (also BEFORE it: the lane-uniform
+// code between phases reads tile memory the next phase may overwrite) and a plain loop over lanes reproduces it on
+// the host (tests/emul builds exactly this header with g++ to pin the arithmetic on CPU).
 #pragma once
 #include <math.h>
 
@@ -26,7 +27,7 @@
 #endif
 
 #if defined(__CUDA_ARCH__)
-#define SVAE_PHASE(c, lanes) { const int c = (int)(threadIdx.x & 31); if (c < (lanes))
+#define SVAE_PHASE(c, lanes) { __syncwarp(); const int c = (int)(threadIdx.x & 31); if (c < (lanes))
 #define SVAE_PHASE_END __syncwarp(); }
 #else
 #define SVAE_PHASE(c, lanes) { for (int c = 0; c < (lanes); ++c)

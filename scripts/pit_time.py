@@ -47,3 +47,21 @@ for K, T, B in [(32, 100000, 1), (32, 20000, 4), (8, 100000, 1), (32, 2000, 16),
         t_par = timeit(lambda: hmm_pit.hmm_estep_parallel(nat, chunk_len=Lc))
         row += " Lc=%s %.2f ms (x%.1f)" % (Lc or "sqrt", t_par, t_seq / t_par)
     print(row, flush=True)
+
+# stage breakdown
+n, T, B = 10, 100000, 1
+rng = np.random.default_rng(0)
+init, pair = O.rand_lds_natparam(n, rng)
+node = O.rand_node_potentials(B, T, n, rng)
+gp, nd = tuple(g(x) for x in pair), tuple(g(x) for x in node)
+for Lc in (128, 316):
+    print("LDS compose alone T=%d Lc=%d: %.2f ms" % (T, Lc, timeit(lambda: lds_pit.compose_chunks(gp, nd, Lc))))
+K = 32
+lp, lA = HO.rand_hmm_natparam(K, rng)
+hn = torch.randn((1, T, K), dtype=torch.float64, device="cuda")
+L_ = H._lib.lib()
+for Lc in (316, 1024):
+    C = L_.svae_lds_compose_num_chunks(T, Lc)
+    P_, ls = torch.empty((1, C, K, K), dtype=torch.float64, device="cuda"), torch.empty((1, C), dtype=torch.float64, device="cuda")
+    f = lambda: L_.svae_hmm_compose_chunks(1, T, K, Lc, H._lib.ptr(g(lA)), H._lib.ptr(hn), H._lib.ptr(P_), H._lib.ptr(ls), H._lib.stream_ptr(hn.device))
+    print("HMM compose alone T=%d Lc=%d: %.2f ms" % (T, Lc, timeit(f)))

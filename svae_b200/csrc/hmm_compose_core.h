@@ -56,7 +56,7 @@ SVAE_HD void hmm_compose_chunk(double* mem, int K, int s, int L, const double* l
   SVAE_PHASE(j, K) {
     for (int k = 0; k < K; ++k) A[k * 32 + j] = exp(log_A[k * K + j] - amax);
     const double dj = exp(nd[j] - nmax);
-    for (int i = 0; i < K; ++i) PDt0[j * kHmmRow + i] = (i == j) ? dj : 0.0;
+    for (int i = 0; i < 32; ++i) PDt0[j * kHmmRow + i] = (i == j) ? dj : 0.0;   // entries i >= K stay exactly zero
     if (L > 1) nd[j] = node[(size_t)(s + 1) * K + j];
   } SVAE_PHASE_END
   double logscale = (double)L * amax + nmax;
@@ -71,24 +71,22 @@ SVAE_HD void hmm_compose_chunk(double* mem, int K, int s, int L, const double* l
       for (int j = 1; j < K; ++j) nmax2 = fmax(nmax2, nd[j]);
     }
     SVAE_PHASE(j, K) {
-      double acc[32];                      // fixed trip counts + predicates keep it in registers on the device
+      double acc[32];                      // fixed trip counts keep it in registers on the device
       SVAE_UNROLL
       for (int i = 0; i < 32; ++i) acc[i] = 0.0;
       for (int k = 0; k < K; ++k) {
         const double a = A[k * 32 + j] * inv;
         const double* row = cur + k * kHmmRow;
         SVAE_UNROLL
-        for (int i = 0; i < 32; ++i)
-          if (i < K) acc[i] = fma(row[i], a, acc[i]);
+        for (int i = 0; i < 32; ++i) acc[i] = fma(row[i], a, acc[i]);   // straight-line: the padding rows are zeros
       }
       double m = 0.0;
       const double dj = more ? exp(nd[j] - nmax2) : 1.0;
       SVAE_UNROLL
-      for (int i = 0; i < 32; ++i)
-        if (i < K) {
-          m = fmax(m, acc[i]);
-          nxt[j * kHmmRow + i] = acc[i] * dj;   // row j of the next (P D)^T (or of P^T after the last step)
-        }
+      for (int i = 0; i < 32; ++i) {
+        m = fmax(m, acc[i]);
+        nxt[j * kHmmRow + i] = acc[i] * dj;   // row j of the next (P D)^T (or of P^T after the last step)
+      }
       colmax[j] = m;
     } SVAE_PHASE_END
     double pmax = colmax[0];

@@ -137,12 +137,15 @@ int svae_lds_estep_fwd_ex(
  *   chunk_J11, chunk_J12, chunk_J22 (B,C,n,n), chunk_logZ (B,C): natural form, the layout svae_lds_estep_fwd takes as
  *       per-sequence time-inhomogeneous pair parameters (pair_stride_t = n*n, pair_stride_b = C*n*n);
  *   chunk_e1, chunk_e2 (B,C,n): linear terms on the chunk's first / last state (node_h of the boundary chain).
- * Homogeneous pair parameters (n,n), diagonal node potentials (B,T,n); node_logZ (B,T) / pair_logZ (1) may be NULL.
+ * Pair parameters addressed like svae_lds_estep_fwd (pair_stride_t = pair_stride_b = 0: homogeneous (n,n) blocks and
+ * one pair_logZ; else per-time / per-sequence blocks with pair_logZ indexed by stride / n^2); diagonal node potentials
+ * (B,T,n); node_logZ (B,T) / pair_logZ may be NULL.
  * *status (may be NULL): 1 + index of the first sequence with a non-positive pivot.
  */
 int svae_lds_compose_num_chunks(int T, int chunk_len);
 int svae_lds_compose_chunks(int B, int T, int n, int chunk_len, const double* J11, const double* J12,
-                            const double* J22, const double* pair_logZ, const double* node_J,
+                            const double* J22, const double* pair_logZ, long long pair_stride_t,
+                            long long pair_stride_b, const double* node_J,
                             const double* node_h, const double* node_logZ, double* chunk_J11,
                             double* chunk_J12, double* chunk_J22, double* chunk_logZ, double* chunk_e1,
                             double* chunk_e2, int* status, void* stream);

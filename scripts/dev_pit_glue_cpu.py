@@ -14,7 +14,7 @@ lds_pit._dev = lambda h: torch.device("cpu")
 
 
 def fake_compose(pair_params, node_params, chunk_len):
-    pair = tuple(N(T64(x)) for x in pair_params[:3]) + (float(pair_params[3]),)
+    pair = tuple(N(T64(x)) for x in pair_params[:3]) + (N(T64(pair_params[3])),)
     node = tuple(N(T64(x)) for x in node_params)
     if len(node) == 2:
         node = node + (np.zeros(node[1].shape[:2]),)
@@ -33,7 +33,7 @@ def fake_forward(init_params, pair_params, node_params, num_samples=1, eps=None,
     pair = tuple(N(T64(x)) for x in pair_params)
     out = dict(B=B, T=T, n=n, S=S, batched=True)
     keys = ["lognorm", "E_node_xx", "E_node_x", "samples", "E_init_xx", "E_init_x", "E_pair_xx", "E_pair_xxn", "E_pair_xnxn",
-            "Exx_t", "J_pred", "h_pred"]
+            "Exx_t", "Exxn_t", "J_pred", "h_pred"]
     acc = {k: [] for k in keys}
     for b in range(B):
         init_b = (iJ[b] if iJ.ndim == 3 else iJ, ih[b] if ih.ndim == 2 else ih, ilZ)
@@ -53,6 +53,8 @@ def fake_forward(init_params, pair_params, node_params, num_samples=1, eps=None,
         if homog:
             for k, key in enumerate(("E_pair_xx", "E_pair_xxn", "E_pair_xnxn")):
                 acc[key].append(Ep[k][0])
+        else:
+            acc["Exxn_t"].append(Ep[1][0])
         if S:
             acc["samples"].append(x[0])
     for k in keys:
@@ -80,3 +82,22 @@ for (n, T, B, S, Lc) in [(4, 25, 2, 2, 6), (3, 14, 3, 1, 5), (10, 60, 2, 1, None
           "Epair %.1e %.1e %.1e" % tuple(err(E_pair[k], wE_pair[k]) for k in range(3)),
           "Enode %.1e %.1e" % (err(E_node[0], wE_node[0]), err(E_node[1], wE_node[1])),
           "samples %.1e" % (err(samples, w_samples) if S else 0.))
+
+
+# time-inhomogeneous pair parameters
+for per_seq in (False, True):
+    n, T, B, S, Lc = 5, 23, 2, 1, 4
+    rng = np.random.default_rng(7)
+    init, _ = O.rand_lds_natparam(n, rng)
+    shape = (B, T - 1) if per_seq else (T - 1,)
+    prs = [O.rand_lds_natparam(n, rng)[1] for _ in range(int(np.prod(shape)))]
+    pair = tuple(np.stack([p[k] for p in prs]).reshape(shape + np.shape(prs[0][k])) for k in range(4))
+    node = O.rand_node_potentials(B, T, n, rng)
+    eps = rng.standard_normal((B, T, S, n))
+    want = [O.natural_lds_inference_general((init, tuple(x[q] for x in pair) if per_seq else pair), tuple(x[q:q + 1] for x in node), eps[q:q + 1]) for q in range(B)]
+    samples, (E_init, E_pair, E_node), lognorm = lds_pit.natural_lds_inference_parallel(
+        (g(init), g(pair)), g(node), num_samples=S, eps=T64(eps), chunk_len=Lc)
+    cat = lambda f: np.concatenate([f(w) for w in want])
+    print("inhomog per_seq=%s" % per_seq, "lognorm %.1e" % err(lognorm, cat(lambda w: w[2])), "samples %.1e" % err(samples, cat(lambda w: w[0])),
+          "Epair %.1e %.1e %.1e" % tuple(err(E_pair[k], cat(lambda w: w[1][1][k])) for k in range(3)),
+          "Enode %.1e %.1e" % tuple(err(E_node[k], cat(lambda w: w[1][2][k])) for k in range(2)))

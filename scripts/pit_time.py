@@ -65,3 +65,20 @@ for Lc in (316, 1024):
     P_, ls = torch.empty((1, C, K, K), dtype=torch.float64, device="cuda"), torch.empty((1, C), dtype=torch.float64, device="cuda")
     f = lambda: L_.svae_hmm_compose_chunks(1, T, K, Lc, H._lib.ptr(g(lA)), H._lib.ptr(hn), H._lib.ptr(P_), H._lib.ptr(ls), H._lib.stream_ptr(hn.device))
     print("HMM compose alone T=%d Lc=%d: %.2f ms" % (T, Lc, timeit(f)))
+
+# SLDS local mean field on one long sequence
+import time
+from svae_b200.models import slds_svae as M
+Ks, ns, Ts, Bs = 8, 10, 20000, 1
+gg = torch.Generator().manual_seed(0)
+glob = M.make_slds_global_natparam(Ks, ns, alpha=2., sticky_bias=1., random=True, generator=gg, device="cuda")
+nJ = -0.5 * torch.nn.functional.softplus(torch.randn(Bs, Ts, ns, dtype=torch.float64, device="cuda"))
+nh = torch.randn(Bs, Ts, ns, dtype=torch.float64, device="cuda")
+ie = torch.randn(Bs, Ts, 1, ns, dtype=torch.float64, device="cuda")
+for flag in (False, True, False, True):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    with torch.no_grad():
+        out = M.optimize_local_meanfield(glob, (nJ, nh), init_eps=ie, parallel_in_time=flag)
+    torch.cuda.synchronize()
+    print("SLDS K=%d d=%d T=%d B=%d optimize_local_meanfield parallel_in_time=%s: %.1f ms (vlb %.6f)" %
+          (Ks, ns, Ts, Bs, flag, (time.perf_counter() - t0) * 1e3, float((out[2][0] + out[2][1]).sum())), flush=True)

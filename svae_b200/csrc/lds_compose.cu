@@ -14,6 +14,7 @@ constexpr int kWarps = 4;
 
 struct ComposeParams {
   int B, T, n, Lc, C;
+  long long stride_t, stride_b;
   const double *J11, *J12, *J22, *pair_logZ, *node_J, *node_h, *node_logZ;
   double *cJ11, *cJ12, *cJ22, *clogZ, *ce1, *ce2;
   int* status;
@@ -29,9 +30,10 @@ __global__ void __launch_bounds__(32 * kWarps) lds_compose_kernel(const ComposeP
   const int L = min(p.Lc, p.T - 1 - s);
   const int n = p.n, nn = n * n;
   const size_t bt = (size_t)b * p.T;
+  const size_t pb = (size_t)b * p.stride_b;
   const int bad = svae::compose_chunk(
-      smem + (size_t)warp * svae::compose_tile_doubles(n), n, s, L, p.J11, p.J12, p.J22, p.pair_logZ ? *p.pair_logZ : 0.0,
-      p.node_J + bt * n, p.node_h + bt * n, p.node_logZ ? p.node_logZ + bt : nullptr, p.cJ11 + tile * nn,
+      smem + (size_t)warp * svae::compose_tile_doubles(n), n, s, L, p.J11 + pb, p.J12 + pb, p.J22 + pb,
+      p.pair_logZ ? p.pair_logZ + pb / nn : nullptr, p.stride_t, p.node_J + bt * n, p.node_h + bt * n, p.node_logZ ? p.node_logZ + bt : nullptr, p.cJ11 + tile * nn,
       p.cJ12 + tile * nn, p.cJ22 + tile * nn, p.clogZ + tile, p.ce1 + tile * n, p.ce2 + tile * n);
   if (bad && p.status && (threadIdx.x & 31) == 0) atomicCAS(p.status, 0, b + 1);
 }
@@ -43,11 +45,13 @@ extern "C" int svae_lds_compose_num_chunks(int T, int chunk_len) {
 }
 
 extern "C" int svae_lds_compose_chunks(int B, int T, int n, int chunk_len, const double* J11, const double* J12,
-                                       const double* J22, const double* pair_logZ, const double* node_J,
+                                       const double* J22, const double* pair_logZ, long long pair_stride_t,
+                                       long long pair_stride_b, const double* node_J,
                                        const double* node_h, const double* node_logZ, double* chunk_J11,
                                        double* chunk_J12, double* chunk_J22, double* chunk_logZ, double* chunk_e1,
                                        double* chunk_e2, int* status, void* stream) {
-  if (B <= 0 || T < 2 || n <= 0 || chunk_len < 1) return SVAE_ERR_BAD_ARG;
+  if (B <= 0 || T < 2 || n <= 0 || chunk_len < 1 || pair_stride_t < 0 || pair_stride_b < 0) return SVAE_ERR_BAD_ARG;
+  if (pair_stride_t % ((long long)n * n) != 0 || pair_stride_b % ((long long)n * n) != 0) return SVAE_ERR_BAD_ARG;
   if (!J11 || !J12 || !J22 || !node_J || !node_h || !chunk_J11 || !chunk_J12 || !chunk_J22 || !chunk_logZ || !chunk_e1 ||
       !chunk_e2)
     return SVAE_ERR_BAD_ARG;
@@ -55,6 +59,7 @@ extern "C" int svae_lds_compose_chunks(int B, int T, int n, int chunk_len, const
   ComposeParams p;
   p.B = B; p.T = T; p.n = n; p.Lc = chunk_len; p.C = svae_lds_compose_num_chunks(T, chunk_len);
   p.J11 = J11; p.J12 = J12; p.J22 = J22; p.pair_logZ = pair_logZ;
+  p.stride_t = pair_stride_t; p.stride_b = pair_stride_b;
   p.node_J = node_J; p.node_h = node_h; p.node_logZ = node_logZ;
   p.cJ11 = chunk_J11; p.cJ12 = chunk_J12; p.cJ22 = chunk_J22; p.clogZ = chunk_logZ; p.ce1 = chunk_e1; p.ce2 = chunk_e2;
   p.status = status;

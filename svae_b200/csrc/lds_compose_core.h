@@ -63,19 +63,24 @@ SVAE_HD ComposeTile compose_tile(double* mem, int n) {
 // (T) or null; pair natural form (J11,J12,J22 (n,n) row-major, logZ).  Writes the chunk element in NATURAL form, the
 // layout the fused kernel takes as per-(b,t) pair parameters: out_J11 = -1/2 L11, out_J12 = -L12, out_J22 = -1/2 L22
 // (n,n row-major), out_logZ = c, out_e1, out_e2 (n).  Returns (uniformly) 0, or 1 + the step of a non-positive pivot.
+// Time-inhomogeneous pair parameters: pair_stride_t doubles between consecutive steps' (n,n) blocks (0 = homogeneous);
+// pJ11/pJ12/pJ22 point at this sequence's step 0 and pair_logZ (or null) at its step-0 entry with stride
+// pair_stride_t / (n*n), exactly the addressing of the fused kernel (lds_estep.cuh).
 SVAE_HD int compose_chunk(double* mem, int n, int s, int L, const double* pJ11, const double* pJ12, const double* pJ22,
-                          double pair_logZ, const double* node_J, const double* node_h, const double* node_logZ,
-                          double* out_J11, double* out_J12, double* out_J22, double* out_logZ, double* out_e1,
-                          double* out_e2) {
+                          const double* pair_logZ, long long pair_stride_t, const double* node_J, const double* node_h,
+                          const double* node_logZ, double* out_J11, double* out_J12, double* out_J22, double* out_logZ,
+                          double* out_e1, double* out_e2) {
   const int NP = compose_np(n);
   ComposeTile t = compose_tile(mem, n);
   double cc = 0.0;
   int bad = 0;
+  const long long lz_stride = pair_stride_t / ((long long)n * n);
   SVAE_PHASE(c, n) {
+    const size_t po = (size_t)s * pair_stride_t;
     for (int i = 0; i < n; ++i) {
-      t.J11[i * NP + c] = -2.0 * pJ11[i * n + c];
-      t.J12[i * NP + c] = -pJ12[i * n + c];
-      t.J22[i * NP + c] = -2.0 * pJ22[i * n + c];
+      t.J11[i * NP + c] = -2.0 * pJ11[po + i * n + c];
+      t.J12[i * NP + c] = -pJ12[po + i * n + c];
+      t.J22[i * NP + c] = -2.0 * pJ22[po + i * n + c];
     }
   } SVAE_PHASE_END
   // first step: the element of node_s . pair
@@ -88,10 +93,20 @@ SVAE_HD int compose_chunk(double* mem, int n, int s, int L, const double* pJ11, 
     t.e1[c] = node_h[(size_t)s * n + c];
     t.e2[c] = 0.0;
   } SVAE_PHASE_END
-  cc = pair_logZ + (node_logZ ? node_logZ[s] : 0.0);
+  cc = (pair_logZ ? pair_logZ[(size_t)s * lz_stride] : 0.0) + (node_logZ ? node_logZ[s] : 0.0);
 
   for (int q = 1; q < L; ++q) {
     const size_t o = (size_t)(s + q) * n;
+    if (pair_stride_t != 0) {   // this step's pair potential
+      SVAE_PHASE(c, n) {
+        const size_t po = (size_t)(s + q) * pair_stride_t;
+        for (int i = 0; i < n; ++i) {
+          t.J11[i * NP + c] = -2.0 * pJ11[po + i * n + c];
+          t.J12[i * NP + c] = -pJ12[po + i * n + c];
+          t.J22[i * NP + c] = -2.0 * pJ22[po + i * n + c];
+        }
+      } SVAE_PHASE_END
+    }
     // augmented matrix [M | J12 | L12' | v]
     SVAE_PHASE(c, n) {
       for (int i = 0; i < n; ++i) {
@@ -129,7 +144,7 @@ SVAE_HD int compose_chunk(double* mem, int n, int s, int L, const double* pJ11, 
     }
     double quad = 0.0;
     for (int k = 0; k < n; ++k) quad += t.u[k] * t.u[k] * t.dinv[k];
-    cc += pair_logZ + (node_logZ ? node_logZ[s + q] : 0.0) + 0.5 * quad - 0.5 * logdet;
+    cc += (pair_logZ ? pair_logZ[(size_t)(s + q) * lz_stride] : 0.0) + (node_logZ ? node_logZ[s + q] : 0.0) + 0.5 * quad - 0.5 * logdet;
     // products; the new L12' is staged in M (free now) because every lane still reads the old W
     SVAE_PHASE(c, n + 1) {
       if (c < n) {

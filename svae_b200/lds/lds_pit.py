@@ -17,7 +17,8 @@ statistics, log-normaliser and, for the same noise, the same samples as natural_
      over the chunks replaces every terminal draw by the next chunk's first state -- which reproduces the sequential
      recursion x_t = b_t + G_t x_{t+1} (cython_lds_inference.pyx:335-352) exactly.
 
-Forward values only (no VJP); homogeneous pair parameters and diagonal node potentials.  The torch calls below are
+Forward values only (no VJP); diagonal node potentials; pair parameters homogeneous, per-time or per-sequence (the
+SLDS case, svae/models/slds_svae.py:92-103).  The torch calls below are
 reshapes, two batched n x n inverses at the C boundaries and the O(log C) stitch -- the arithmetic is in the kernels.
 """
 from __future__ import annotations
@@ -40,15 +41,13 @@ def compose_chunks(pair_params, node_params, chunk_len):
         raise ValueError("parallel-in-time driver: diagonal node potentials only")
     B, T, n = nh.shape
     J11, J12, J22, plogZ, st, sb = K._canonical_pair_params(pair_params, B, T, n, device)
-    if st != 0 or sb != 0:
-        raise ValueError("parallel-in-time driver: homogeneous pair parameters only")
     L = _lib.lib()
     C = L.svae_lds_compose_num_chunks(T, int(chunk_len))
     new = lambda *s: torch.empty(s, dtype=torch.float64, device=device)
     cJ11, cJ12, cJ22, clogZ, e1, e2 = new(B, C, n, n), new(B, C, n, n), new(B, C, n, n), new(B, C), new(B, C, n), new(B, C, n)
     status = torch.zeros(1, dtype=torch.int32, device=device)
     P = _lib.ptr
-    code = L.svae_lds_compose_chunks(B, T, n, int(chunk_len), P(J11), P(J12), P(J22), P(plogZ), P(nJ), P(nh), P(nlogZ),
+    code = L.svae_lds_compose_chunks(B, T, n, int(chunk_len), P(J11), P(J12), P(J22), P(plogZ), st, sb, P(nJ), P(nh), P(nlogZ),
                                      P(cJ11), P(cJ12), P(cJ22), P(clogZ), P(e1), P(e2),
                                      ctypes.c_void_p(status.data_ptr()), _lib.stream_ptr(device))
     _lib.check(code, "svae_lds_compose_chunks")
@@ -93,6 +92,11 @@ def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=Non
             eps = eps[None] if (not batched and eps.dim() == 3) else eps
             if eps.shape != (B, T, S, n):
                 raise ValueError("eps must be (B,T,S,n)")
+    homog = K._is_homog(pair_params)
+    if not homog:                            # per-time / per-sequence pair parameters (the SLDS case), as (B,T-1,...)
+        pJ11, pJ12, pJ22, plogZ, _, _ = K._canonical_pair_params(pair_params, B, T, n, device)
+        pfull = tuple(x.expand(B, T - 1, n, n) for x in (pJ11, pJ12, pJ22))
+        plz = None if plogZ is None else plogZ.reshape((-1, T - 1)).expand(B, T - 1)
     lanes = 32 - (n + 1)                     # sample lanes one tile can carry next to the n+1 filter lanes
     if S > lanes:
         raise ValueError("num_samples %d > %d" % (S, lanes))
@@ -132,6 +136,8 @@ def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=Non
     E_node_xx, E_node_x = torch.empty((B, T, n), **f64), torch.empty((B, T, n), **f64)
     samples = torch.empty((B, T, S, n), **f64) if S else None
     E_pair = [torch.zeros((B, n, n), **f64) for _ in range(3)]
+    Exx_t = None if homog else torch.empty((B, T, n, n), **f64)
+    Exxn_t = None if homog else torch.empty((B, T - 1, n, n), **f64)
     E_init = None
     x_start = torch.empty((B, C, S, n), **f64) if S else None       # kernel paths at the chunk ends, and G_{s->e}
     x_end = torch.empty((B, C, S, n), **f64) if S else None
@@ -148,6 +154,11 @@ def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=Non
         sub_init = (Jp[:, c0:c0 + cnt].reshape(Q, n, n), hp[:, c0:c0 + cnt].reshape(Q, n))
         sub_node = (sJ.reshape(Q, L + 1, n), sh.reshape(Q, L + 1, n))
         sub_term = tJ[:, c0:c0 + cnt].reshape(Q, n, n)
+        if homog:
+            sub_pair = pair_params
+        else:
+            sub_pair = tuple(x[:, t0:t1].reshape(Q, L, n, n) for x in pfull)
+            sub_pair += (torch.zeros((), **f64) if plz is None else plz[:, t0:t1].reshape(Q, L),)
 
         def window(x):                       # (B,T,...) -> (B,cnt,L+1,...): steps t0 + c L .. t0 + (c+1) L inclusive
             body = x[:, t0:t1].reshape((B, cnt, L) + x.shape[2:])
@@ -164,7 +175,8 @@ def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=Non
             seps[:, :, :, :S] = window(eps)
             if probes:
                 seps[:, :, L, S + 1:] = torch.eye(n, **f64)[:probes - 1]
-            o = K.lds_estep_forward(sub_init, pair_params, sub_node, SP, seps.reshape(Q, L + 1, SP, n), term_J=sub_term)
+            o = K.lds_estep_forward(sub_init, sub_pair, sub_node, SP, seps.reshape(Q, L + 1, SP, n), term_J=sub_term,
+                                    per_t_pair_stats=not homog)
             xs = o["samples"].reshape(B, cnt, L + 1, SP, n)
             xk = xs[..., :S, :]
             cols = [xs[..., S + 1:, :] - xs[..., S:S + 1, :]] if probes else []
@@ -173,7 +185,7 @@ def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=Non
                 k = min(n - done, lanes - 1)
                 peps = torch.zeros((Q, L + 1, k + 1, n), **f64)
                 peps[:, L, 1:] = torch.eye(n, **f64)[done:done + k]
-                po = K.lds_estep_forward(sub_init, pair_params, sub_node, k + 1, peps, want_stats=False, term_J=sub_term)
+                po = K.lds_estep_forward(sub_init, sub_pair, sub_node, k + 1, peps, want_stats=False, term_J=sub_term)
                 ps = po["samples"].reshape(B, cnt, L + 1, k + 1, n)
                 cols.append(ps[..., 1:, :] - ps[..., :1, :])
                 done += k
@@ -182,10 +194,17 @@ def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=Non
             x_start[:, c0:c0 + cnt], x_end[:, c0:c0 + cnt] = xk[:, :, 0], xk[:, :, L]
             R_start[:, c0:c0 + cnt] = Rt[:, :, 0]
         else:
-            o = K.lds_estep_forward(sub_init, pair_params, sub_node, 0, None, term_J=sub_term)
+            o = K.lds_estep_forward(sub_init, sub_pair, sub_node, 0, None, term_J=sub_term, per_t_pair_stats=not homog)
             xk = Rt = None
-        for k, key in enumerate(("E_pair_xx", "E_pair_xxn", "E_pair_xnxn")):
-            E_pair[k] += o[key].reshape(B, cnt, n, n).sum(1)
+        if homog:
+            for k, key in enumerate(("E_pair_xx", "E_pair_xxn", "E_pair_xnxn")):
+                E_pair[k] += o[key].reshape(B, cnt, n, n).sum(1)
+        else:
+            xx = o["Exx_t"].reshape(B, cnt, L + 1, n, n)
+            Exx_t[:, t0:t1] = xx[:, :, :L].reshape(B, cnt * L, n, n)
+            if t1 == T - 1:
+                Exx_t[:, -1] = xx[:, -1, L]
+            Exxn_t[:, t0:t1] = o["Exxn_t"].reshape(B, cnt * L, n, n)
         if c0 == 0:
             E_init = (o["E_init_xx"].reshape(B, cnt, n, n)[:, 0].contiguous(), o["E_init_x"].reshape(B, cnt, n)[:, 0].contiguous())
         exx, ex = o["E_node_xx"].reshape(B, cnt, L + 1, n), o["E_node_x"].reshape(B, cnt, L + 1, n)
@@ -208,5 +227,6 @@ def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=Non
                 samples[:, -1] = fixed[:, -1, L]
 
     o = dict(B=B, T=T, n=n, S=S, batched=batched, lognorm=lognorm, samples=samples, E_node_xx=E_node_xx, E_node_x=E_node_x,
-             E_init_xx=E_init[0], E_init_x=E_init[1], E_pair_xx=E_pair[0], E_pair_xxn=E_pair[1], E_pair_xnxn=E_pair[2])
-    return K._pack_stats(o, True)
+             E_init_xx=E_init[0], E_init_x=E_init[1], E_pair_xx=E_pair[0], E_pair_xxn=E_pair[1], E_pair_xnxn=E_pair[2],
+             Exx_t=Exx_t, Exxn_t=Exxn_t)
+    return K._pack_stats(o, homog)

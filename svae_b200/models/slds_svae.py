@@ -80,10 +80,22 @@ def get_var_lds_local_natparam(lds_global_natparams, hmm_expected_stats, dense=N
     return init_param, pair_params
 
 
-def lds_meanfield(lds_global_natparams, node_potentials, hmm_expected_stats, dense=None):
+def use_parallel_in_time(B, T, flag="auto"):
+    """Few long sequences leave the sequential kernels on B tiles of the GPU: chunk-parallel drivers then
+    (lds/lds_pit.py, hmm/hmm_pit.py; same numbers).  Measured crossover on a B200: B <= 16 and T >= 2000."""
+    if flag is None or flag == "auto":
+        return B <= 16 and T >= 2000
+    return bool(flag)
+
+
+def lds_meanfield(lds_global_natparams, node_potentials, hmm_expected_stats, dense=None, pit=False):
     """slds_svae.py:80-83."""
     local_natparam = get_var_lds_local_natparam(lds_global_natparams, hmm_expected_stats, dense)
-    vlb, expected_stats = natural_lds_estep_general(local_natparam, node_potentials)
+    if pit:
+        from ..lds.lds_pit import natural_lds_inference_parallel
+        _, expected_stats, vlb = natural_lds_inference_parallel(local_natparam, node_potentials, 0)
+    else:
+        vlb, expected_stats = natural_lds_estep_general(local_natparam, node_potentials)
     return local_natparam, expected_stats, vlb
 
 
@@ -112,12 +124,16 @@ def get_arhmm_local_nodeparams(lds_global_natparam, lds_expected_stats, dense=No
     return torch.cat((init_node[:, None], rest), 1)                   # (B,T,K)
 
 
-def hmm_meanfield(hmm_global_natparam, lds_global_natparam, lds_expected_stats, dense=None, hmm_local=None):
+def hmm_meanfield(hmm_global_natparam, lds_global_natparam, lds_expected_stats, dense=None, hmm_local=None, pit=False):
     """slds_svae.py:108-115."""
     init_params, pair_params = hmm_local if hmm_local is not None else get_hmm_local_natparam(hmm_global_natparam)
     node_params = get_arhmm_local_nodeparams(lds_global_natparam, lds_expected_stats, dense)
     local_natparam = (init_params, pair_params, node_params)
-    vlb, stats = hmm_estep(local_natparam)
+    if pit:
+        from ..hmm.hmm_pit import hmm_estep_parallel
+        vlb, stats = hmm_estep_parallel(local_natparam)
+    else:
+        vlb, stats = hmm_estep(local_natparam)
     return local_natparam, stats, vlb
 
 
@@ -128,7 +144,7 @@ def get_hmm_vlb(lds_global_natparam, hmm_local_natparam, lds_expected_stats, den
     return hmm_logZ((init_params, pair_params, node_params))
 
 
-def initialize_local_meanfield(node_potentials, eps=None, generator=None):
+def initialize_local_meanfield(node_potentials, eps=None, generator=None, pit=False):
     """slds_svae.py:203-226: statistics of ONE sample path of a 0.9-random-walk LDS given the node potentials."""
     h = node_potentials[1]
     N, dev = h.shape[-1], h.device
@@ -136,7 +152,11 @@ def initialize_local_meanfield(node_potentials, eps=None, generator=None):
     A = 0.9 * eye
     init_params = (-0.5 * eye, torch.zeros(N, dtype=torch.float64, device=dev), 0.)
     pair_params = (-0.5 * A.T @ A, A.T, -0.5 * eye, 0.)
-    x = natural_lds_sample((init_params, pair_params), node_potentials, num_samples=1, eps=eps, generator=generator)[:, :, 0]
+    if pit:
+        from ..lds.lds_pit import natural_lds_inference_parallel
+        x = natural_lds_inference_parallel((init_params, pair_params), node_potentials, 1, eps=eps, generator=generator)[0][:, :, 0]
+    else:
+        x = natural_lds_sample((init_params, pair_params), node_potentials, num_samples=1, eps=eps, generator=generator)[:, :, 0]
     out = lambda u, v: u[..., :, None] * v[..., None, :]
     ones = torch.ones(x.shape[0], dtype=torch.float64, device=dev)
     init_stats = (out(x[:, 0], x[:, 0]), x[:, 0], ones, ones)
@@ -146,17 +166,19 @@ def initialize_local_meanfield(node_potentials, eps=None, generator=None):
 
 
 def optimize_local_meanfield(global_natparam, node_potentials, tol=1e-2, max_iter=100, init_eps=None, generator=None,
-                             dense=None):
+                             dense=None, parallel_in_time="auto"):
     """slds_svae.py:159-175.  The per-mode expected parameters (K small NIW/MNIW maps, loop-invariant) are
-    evaluated once per call instead of once per sweep."""
+    evaluated once per call instead of once per sweep.  parallel_in_time: "auto" | True | False (use_parallel_in_time)."""
     hmm_global, lds_global = global_natparam
     dense = dense if dense is not None else get_all_lds_local_natparams(lds_global)
     hmm_local = get_hmm_local_natparam(hmm_global)
-    lds_stats = initialize_local_meanfield(node_potentials, init_eps, generator)
+    pit = use_parallel_in_time(node_potentials[1].shape[0], node_potentials[1].shape[1], parallel_in_time) \
+        and not (torch.is_grad_enabled() and any(p.requires_grad for p in node_potentials[:2]))
+    lds_stats = initialize_local_meanfield(node_potentials, init_eps, generator, pit)
     local_vlb = None
     for _ in range(max_iter):
-        hmm_natparam, hmm_stats, hmm_vlb = hmm_meanfield(hmm_global, lds_global, lds_stats, dense, hmm_local)
-        lds_natparam, lds_stats, lds_vlb = lds_meanfield(lds_global, node_potentials, hmm_stats, dense)
+        hmm_natparam, hmm_stats, hmm_vlb = hmm_meanfield(hmm_global, lds_global, lds_stats, dense, hmm_local, pit)
+        lds_natparam, lds_stats, lds_vlb = lds_meanfield(lds_global, node_potentials, hmm_stats, dense, pit)
         local_vlb, prev = hmm_vlb + lds_vlb, local_vlb
         if prev is not None and float((local_vlb - prev).abs().max()) < tol:   # the one host sync per sweep
             break

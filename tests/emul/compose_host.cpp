@@ -5,7 +5,8 @@
 #include "lds_compose_core.h"
 
 extern "C" int compose_chunks_host(int B, int T, int n, int chunk_len, const double* J11, const double* J12,
-                                   const double* J22, const double* pair_logZ, const double* node_J,
+                                   const double* J22, const double* pair_logZ, long long stride_t, long long stride_b,
+                                   const double* node_J,
                                    const double* node_h, const double* node_logZ, double* cJ11, double* cJ12,
                                    double* cJ22, double* clogZ, double* ce1, double* ce2) {
   const int C = (T - 1 + chunk_len - 1) / chunk_len;
@@ -15,7 +16,9 @@ extern "C" int compose_chunks_host(int B, int T, int n, int chunk_len, const dou
     for (int c = 0; c < C; ++c) {
       const long long tile = (long long)b * C + c;
       const int s = c * chunk_len, L = std::min(chunk_len, T - 1 - s);
-      const int bad = svae::compose_chunk(mem.data(), n, s, L, J11, J12, J22, pair_logZ ? *pair_logZ : 0.0,
+      const size_t pb = (size_t)b * stride_b;
+      const int bad = svae::compose_chunk(mem.data(), n, s, L, J11 + pb, J12 + pb, J22 + pb,
+                                          pair_logZ ? pair_logZ + pb / (n * n) : nullptr, stride_t,
                                           node_J + (size_t)b * T * n, node_h + (size_t)b * T * n,
                                           node_logZ ? node_logZ + (size_t)b * T : nullptr, cJ11 + tile * n * n,
                                           cJ12 + tile * n * n, cJ22 + tile * n * n, clogZ + tile, ce1 + tile * n,

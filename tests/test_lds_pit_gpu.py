@@ -93,3 +93,33 @@ def test_unbatched_and_errors():
     hn = _gpu(node[1]).requires_grad_(True)
     with pytest.raises(RuntimeError):     # forward-only
         lds_pit.natural_lds_inference_parallel((_g(init), _g(pair)), (_gpu(node[0]), hn), 0)
+
+
+@pytest.mark.parametrize("per_seq", [False, True])
+@pytest.mark.parametrize("n,T,B,S,Lc", [(3, 14, 2, 1, 5), (10, 61, 3, 1, 7), (6, 40, 2, 0, 6)])
+def test_time_inhomogeneous_pair_parameters(per_seq, n, T, B, S, Lc):
+    """Per-time and per-sequence pair parameters (what the SLDS feeds the LDS E-step, slds_svae.py:92-103)."""
+    from svae_b200.lds import lds_pit
+    rng = np.random.default_rng(30 + n)
+    init, _ = O.rand_lds_natparam(n, rng)
+    shape = (B, T - 1) if per_seq else (T - 1,)
+    prs = [O.rand_lds_natparam(n, rng)[1] for _ in range(int(np.prod(shape)))]
+    pair = tuple(np.stack([p[k] for p in prs]).reshape(shape + np.shape(prs[0][k])) for k in range(4))
+    node = O.rand_node_potentials(B, T, n, rng)
+    node = (node[0], node[1], 0.3 * rng.standard_normal((B, T)))
+    eps = rng.standard_normal((B, T, S, n))
+    want = [O.natural_lds_inference_general((init, tuple(x[q] for x in pair) if per_seq else pair),
+                                            tuple(x[q:q + 1] for x in node), eps[q:q + 1]) for q in range(B)]
+    cat = lambda f: np.concatenate([f(w) for w in want])
+    samples, (E_init, E_pair, E_node), lognorm = lds_pit.natural_lds_inference_parallel(
+        (_g(init), _g(pair)), _g(node), num_samples=S, eps=_gpu(eps) if S else None, chunk_len=Lc)
+    c = lambda x: x.cpu().numpy()
+    assert E_pair[1].shape == (B, T - 1, n, n)
+    assert rel_err(c(lognorm), cat(lambda w: w[2])) < RTOL
+    for k in range(3):
+        assert rel_err(c(E_pair[k]), cat(lambda w: w[1][1][k])) < RTOL
+    for k in range(2):
+        assert rel_err(c(E_node[k]), cat(lambda w: w[1][2][k])) < RTOL
+        assert rel_err(c(E_init[k]), cat(lambda w: w[1][0][k])) < RTOL
+    if S:
+        assert rel_err(c(samples), cat(lambda w: w[0])) < 1e-8

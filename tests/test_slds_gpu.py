@@ -51,3 +51,19 @@ def test_run_inference_differentiable_and_structured():
     (samples.sum() + local_vlb).backward()
     assert torch.isfinite(nJ.grad).all() and torch.isfinite(nh.grad).all() and float(nh.grad.abs().max()) > 0
     assert torch.isfinite(global_vlb)
+
+
+def test_parallel_in_time_meanfield_matches_sequential():
+    """Few long sequences: the chunk-parallel LDS / HMM drivers inside the mean-field loop (same fixed point)."""
+    M, prior, glob, node, init_eps = _setup(K=3, n=3, T=300, B=2, seed=5)
+    t = lambda x: torch.as_tensor(x, dtype=torch.float64, device="cuda")
+    args = (glob, (t(node[0]), t(node[1])))
+    a = M.optimize_local_meanfield(*args, init_eps=t(init_eps), parallel_in_time=False)
+    b = M.optimize_local_meanfield(*args, init_eps=t(init_eps), parallel_in_time=True)
+    c = lambda x: x.cpu().numpy()
+    (ah, al), _, (ahv, alv) = a
+    (bh, bl), _, (bhv, blv) = b
+    assert rel_err(c(bh[2]), c(ah[2])) < 1e-7 and rel_err(c(bh[1]), c(ah[1])) < 1e-7
+    assert rel_err(c(bl[1][1]), c(al[1][1])) < 1e-7 and rel_err(c(bl[2][1]), c(al[2][1])) < 1e-7
+    assert rel_err(c(bhv), c(ahv)) < 1e-8 and rel_err(c(blv), c(alv)) < 1e-8
+    assert M.use_parallel_in_time(1, 20000) and not M.use_parallel_in_time(1024, 200)

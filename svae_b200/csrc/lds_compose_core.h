@@ -36,9 +36,16 @@
 
 namespace svae {
 
-SVAE_HD int compose_np(int n) { return n + (n & 1); }
+// tile row stride: a compile-time constant (SVAE_LDS_MAX_N) so that the unrolled loops below address shared memory
+// with immediates instead of an integer multiply per access
+SVAE_HD int compose_np(int /*n*/) { return 16; }
 // doubles of tile memory one chunk needs
 SVAE_HD int compose_tile_doubles(int n) { const int NP = compose_np(n); return 9 * n * NP + 8 * NP; }
+#if defined(__CUDACC__)
+#define SVAE_UNROLL _Pragma("unroll")
+#else
+#define SVAE_UNROLL
+#endif
 
 struct ComposeTile {
   // n x NP matrices, element (i, c) at [i * NP + c]: lane c owns column c
@@ -70,7 +77,7 @@ SVAE_HD int compose_chunk(double* mem, int n, int s, int L, const double* pJ11, 
                           const double* pair_logZ, long long pair_stride_t, const double* node_J, const double* node_h,
                           const double* node_logZ, double* out_J11, double* out_J12, double* out_J22, double* out_logZ,
                           double* out_e1, double* out_e2) {
-  const int NP = compose_np(n);
+  constexpr int NP = 16;
   ComposeTile t = compose_tile(mem, n);
   double cc = 0.0;
   int bad = 0;
@@ -128,17 +135,33 @@ SVAE_HD int compose_chunk(double* mem, int n, int s, int L, const double* pJ11, 
         if (c == k) t.dinv[k] = pinv;
       } SVAE_PHASE_END
       SVAE_PHASE(c, n + 1) {
+        // loads first, stores last: the tile arrays share one allocation, so interleaved read-modify-writes would
+        // serialise on possible aliasing
+        double mu[16];
+        SVAE_UNROLL
+        for (int i = 0; i < 16; ++i) mu[i] = (i > k && i < n) ? t.mult[i] : 0.0;
         if (c < n) {
-          const double mk = t.M[k * NP + c], rk = t.R[k * NP + c], wk = t.W[k * NP + c];
-          for (int i = k + 1; i < n; ++i) {
-            const double m = t.mult[i];
-            if (c > k) t.M[i * NP + c] -= m * mk;
-            t.R[i * NP + c] -= m * rk;
-            t.W[i * NP + c] -= m * wk;
-          }
+          const double mk = (c > k) ? t.M[k * NP + c] : 0.0, rk = t.R[k * NP + c], wk = t.W[k * NP + c];
+          double vm[16], vr[16], vw[16];
+          SVAE_UNROLL
+          for (int i = 0; i < 16; ++i)
+            if (i < n) { vm[i] = t.M[i * NP + c]; vr[i] = t.R[i * NP + c]; vw[i] = t.W[i * NP + c]; }
+          SVAE_UNROLL
+          for (int i = 0; i < 16; ++i)
+            if (i < n) {
+              t.M[i * NP + c] = vm[i] - mu[i] * mk;
+              t.R[i * NP + c] = vr[i] - mu[i] * rk;
+              t.W[i * NP + c] = vw[i] - mu[i] * wk;
+            }
         } else {
           const double uk = t.u[k];
-          for (int i = k + 1; i < n; ++i) t.u[i] -= t.mult[i] * uk;
+          double vu[16];
+          SVAE_UNROLL
+          for (int i = 0; i < 16; ++i)
+            if (i < n) vu[i] = t.u[i];
+          SVAE_UNROLL
+          for (int i = 0; i < 16; ++i)
+            if (i < n) t.u[i] = vu[i] - mu[i] * uk;
         }
       } SVAE_PHASE_END
     }
@@ -147,29 +170,41 @@ SVAE_HD int compose_chunk(double* mem, int n, int s, int L, const double* pJ11, 
     cc += (pair_logZ ? pair_logZ[(size_t)(s + q) * lz_stride] : 0.0) + (node_logZ ? node_logZ[s + q] : 0.0) + 0.5 * quad - 0.5 * logdet;
     // products; the new L12' is staged in M (free now) because every lane still reads the old W
     SVAE_PHASE(c, n + 1) {
-      if (c < n) {
-        for (int i = 0; i < n; ++i) {
-          double a11 = 0.0, a12 = 0.0, a22 = 0.0;
-          for (int k = 0; k < n; ++k) {
-            const double wd = t.W[k * NP + c] * t.dinv[k], rd = t.R[k * NP + c] * t.dinv[k];
-            a11 += t.W[k * NP + i] * wd;
-            a12 += t.R[k * NP + i] * wd;
-            a22 += t.R[k * NP + i] * rd;
+      // lane c < n: column c of the three products; lane n: the two vectors.  Own scaled column in registers, the
+      // other operand broadcast from the tile; results collected in registers and stored after the last load.
+      double wd[16], rd[16];
+      SVAE_UNROLL
+      for (int k = 0; k < 16; ++k) {
+        const double dk = (k < n) ? t.dinv[k] : 0.0;
+        wd[k] = (k < n) ? (c < n ? t.W[k * NP + c] : t.u[k]) * dk : 0.0;
+        rd[k] = (k < n && c < n) ? t.R[k * NP + c] * dk : 0.0;
+      }
+      // destinations are disjoint from everything read in this phase: say so, or every store fences the next loads
+      const double* __restrict__ Wt = t.W;
+      const double* __restrict__ Rt = t.R;
+      double* __restrict__ L11 = t.L11;
+      double* __restrict__ Mst = t.M;
+      double* __restrict__ L22 = t.L22;
+      double* __restrict__ e1 = t.e1;
+      double* __restrict__ e2 = t.e2;
+      const double* __restrict__ J22 = t.J22;
+      for (int i = 0; i < n; ++i) {
+        double a11 = 0.0, a12 = 0.0, a22 = 0.0;
+        SVAE_UNROLL
+        for (int k = 0; k < 16; ++k)
+          if (k < n) {
+            const double wki = Wt[k * NP + i], rki = Rt[k * NP + i];
+            a11 = fma(wki, wd[k], a11);
+            a12 = fma(rki, wd[k], a12);
+            a22 = fma(rki, rd[k], a22);
           }
-          t.L11[i * NP + c] -= a11;
-          t.M[i * NP + c] = -a12;
-          t.L22[i * NP + c] = t.J22[i * NP + c] - a22;
-        }
-      } else {
-        for (int i = 0; i < n; ++i) {
-          double a1 = 0.0, a2 = 0.0;
-          for (int k = 0; k < n; ++k) {
-            const double ud = t.u[k] * t.dinv[k];
-            a1 += t.W[k * NP + i] * ud;
-            a2 += t.R[k * NP + i] * ud;
-          }
-          t.e1[i] -= a1;
-          t.e2[i] = -a2;
+        if (c < n) {
+          L11[i * NP + c] -= a11;
+          Mst[i * NP + c] = -a12;
+          L22[i * NP + c] = J22[i * NP + c] - a22;
+        } else {
+          e1[i] -= a11;      // W' D^-1 u
+          e2[i] = -a12;      // -R' D^-1 u
         }
       }
     } SVAE_PHASE_END

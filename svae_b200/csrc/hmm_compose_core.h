@@ -104,21 +104,32 @@ SVAE_HD void hmm_compose_chunk(double* mem, int K, int s, int L, const double* l
   } SVAE_PHASE_END
 }
 
-SVAE_HD int hmm_chain_tile_doubles(int K) { return 4 * K; }
+// chain tile: two K x K matrix buffers (row stride 33: column reads of the forward sweep and row reads of the backward
+// sweep are both at most 2-way bank conflicted) + four K-vectors
+constexpr int kChainRow = 33;
+SVAE_HD int hmm_chain_tile_doubles(int /*K*/) { return 2 * 32 * kChainRow + 4 * 32; }
 
 // Boundary chain of one sequence: C chunk matrices P_c (K,K) with log scales, initial log pi, and the node potential
 // of the LAST time step.  Writes, for every boundary c = 0..C:
 //   log_alpha[c][j] = log p(z_{s_c} = j, node potentials before s_c) + const  (normalised: logsumexp = 0)
 //   log_beta[c][j]  = log p(node potentials from s_c on | z_{s_c} = j) + const (max = 0)
 // (both clamped below at kLogFloor so they can be added to node potentials), and the total log-normaliser.
+// One warp walks the C matrices twice; the next matrix streams into the other tile buffer (cp.async) while the
+// current vector-matrix product runs, so a step costs its ~100 instructions, not a global-memory round trip.
 SVAE_HD void hmm_chain_messages(double* mem, int K, int C, const double* log_pi, const double* P, const double* logscale,
                                 const double* node_last, double* log_alpha, double* log_beta, double* out_logZ) {
   const double kLogFloor = -700.0;
-  double* a = mem;        // current forward vector (normalised)
-  double* b = mem + K;    // current backward vector
-  double* tmp = mem + 2 * K;
-  double* red = mem + 3 * K;
-  SVAE_PHASE(j, K) { tmp[j] = log_pi[j]; } SVAE_PHASE_END
+  double* buf0 = mem;
+  double* buf1 = mem + 32 * kChainRow;
+  double* a = buf1 + 32 * kChainRow;   // current forward vector (normalised)
+  double* b = a + 32;                  // current backward vector
+  double* tmp = b + 32;
+  double* red = tmp + 32;
+  SVAE_PHASE(j, K) {
+    tmp[j] = log_pi[j];
+    for (int i = 0; i < K; ++i) SVAE_COPY_ASYNC8(&buf0[i * kChainRow + j], &P[(size_t)i * K + j]);
+    SVAE_COPY_COMMIT();
+  } SVAE_PHASE_END
   double m = tmp[0];
   for (int j = 1; j < K; ++j) m = fmax(m, tmp[j]);
   SVAE_PHASE(j, K) { a[j] = exp(tmp[j] - m); } SVAE_PHASE_END
@@ -129,16 +140,28 @@ SVAE_HD void hmm_chain_messages(double* mem, int K, int C, const double* log_pi,
     a[j] /= sum;
     log_alpha[j] = fmax(log(a[j]), kLogFloor);
   } SVAE_PHASE_END
+  double ls_cur = logscale[0];
   for (int c = 0; c < C; ++c) {
-    const double* Pc = P + (size_t)c * K * K;
+    const double* cur = (c & 1) ? buf1 : buf0;
+    double* nxt = (c & 1) ? buf0 : buf1;
+    const double ls_next = (c + 1 < C) ? logscale[c + 1] : 0.0;
     SVAE_PHASE(j, K) {
+      SVAE_COPY_WAIT_ALL();                       // my share of P_c has landed; the barrier publishes everyone's
+    } SVAE_PHASE_END
+    SVAE_PHASE(j, K) {
+      if (c + 1 < C) {
+        const double* Pn = P + (size_t)(c + 1) * K * K;
+        for (int i = 0; i < K; ++i) SVAE_COPY_ASYNC8(&nxt[i * kChainRow + j], &Pn[(size_t)i * K + j]);
+        SVAE_COPY_COMMIT();
+      }
       double acc = 0.0;
-      for (int i = 0; i < K; ++i) acc = fma(a[i], Pc[i * K + j], acc);
+      for (int i = 0; i < K; ++i) acc = fma(a[i], cur[i * kChainRow + j], acc);
       tmp[j] = acc;
     } SVAE_PHASE_END
     sum = 0.0;
     for (int j = 0; j < K; ++j) sum += tmp[j];
-    logZ += logscale[c] + log(sum);
+    logZ += ls_cur + log(sum);
+    ls_cur = ls_next;
     SVAE_PHASE(j, K) {
       a[j] = tmp[j] / sum;
       log_alpha[(size_t)(c + 1) * K + j] = fmax(log(a[j]), kLogFloor);
@@ -156,11 +179,21 @@ SVAE_HD void hmm_chain_messages(double* mem, int K, int C, const double* log_pi,
   sum = 0.0;
   for (int j = 0; j < K; ++j) sum += red[j];
   logZ += m + log(sum);
+  // backward: P_{C-1} is still in its buffer; stream P_{c-1} while P_c is used
   for (int c = C - 1; c >= 0; --c) {
-    const double* Pc = P + (size_t)c * K * K;
+    const double* cur = (c & 1) ? buf1 : buf0;
+    double* nxt = (c & 1) ? buf0 : buf1;
+    SVAE_PHASE(j, K) {
+      SVAE_COPY_WAIT_ALL();
+    } SVAE_PHASE_END
     SVAE_PHASE(i, K) {
+      if (c > 0) {
+        const double* Pn = P + (size_t)(c - 1) * K * K;
+        for (int r = 0; r < K; ++r) SVAE_COPY_ASYNC8(&nxt[r * kChainRow + i], &Pn[(size_t)r * K + i]);
+        SVAE_COPY_COMMIT();
+      }
       double acc = 0.0;
-      for (int j = 0; j < K; ++j) acc = fma(Pc[i * K + j], b[j], acc);
+      for (int j = 0; j < K; ++j) acc = fma(cur[i * kChainRow + j], b[j], acc);
       tmp[i] = acc;
     } SVAE_PHASE_END
     m = tmp[0];

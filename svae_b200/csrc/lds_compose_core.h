@@ -34,6 +34,21 @@
 #define SVAE_PHASE_END }
 #endif
 
+// Asynchronous global -> tile copies (prefetch of the next step's operands while this step computes): cp.async on the
+// device, a plain copy on the host.  A thread waits for its own copies; the phase barrier publishes them to the warp.
+#if defined(__CUDA_ARCH__)
+#define SVAE_COPY_ASYNC8(dst, src)                                                                              \
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)),        \
+               "l"(__cvta_generic_to_global(src))                                                                \
+               : "memory")
+#define SVAE_COPY_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
+#define SVAE_COPY_WAIT_ALL() asm volatile("cp.async.wait_group 0;" ::: "memory")
+#else
+#define SVAE_COPY_ASYNC8(dst, src) (*(dst) = *(src))
+#define SVAE_COPY_COMMIT() ((void)0)
+#define SVAE_COPY_WAIT_ALL() ((void)0)
+#endif
+
 namespace svae {
 
 // tile row stride: a compile-time constant (SVAE_LDS_MAX_N) so that the unrolled loops below address shared memory
@@ -114,46 +129,41 @@ SVAE_HD int compose_chunk(double* mem, int n, int s, int L, const double* pJ11, 
         }
       } SVAE_PHASE_END
     }
-    // augmented matrix [M | J12 | L12' | v]
-    SVAE_PHASE(c, n) {
-      for (int i = 0; i < n; ++i) {
-        t.M[i * NP + c] = t.L22[i * NP + c] + t.J11[i * NP + c] + (i == c ? -2.0 * node_J[o + c] : 0.0);
-        t.R[i * NP + c] = t.J12[i * NP + c];
-        t.W[i * NP + c] = t.L12T[i * NP + c];
+    // Lane roles.  With 3n+1 <= 32 the three n-column blocks of the augmented matrix [M | J12 | L12' | v] get their
+    // own lanes (lane = role*n + column, lane 3n = the vector): a third of the work per lane and phase.  Otherwise
+    // lane c < n carries column c of all three blocks and lane n the vector.
+    const int roles = (3 * n + 1 <= 32) ? 3 : 1;
+    const int vlane = roles * n;
+    SVAE_PHASE(l, vlane + 1) {
+      const int r = l / n, c = l - r * n;
+      if (l == vlane) {
+        for (int i = 0; i < n; ++i) t.u[i] = t.e2[i] + node_h[o + i];
+      } else {
+        for (int i = 0; i < n; ++i) {
+          if (roles == 1 || r == 0) t.M[i * NP + c] = t.L22[i * NP + c] + t.J11[i * NP + c] + (i == c ? -2.0 * node_J[o + c] : 0.0);
+          if (roles == 1 || r == 1) t.R[i * NP + c] = t.J12[i * NP + c];
+          if (roles == 1 || r == 2) t.W[i * NP + c] = t.L12T[i * NP + c];
+        }
       }
-      t.u[c] = t.e2[c] + node_h[o + c];
     } SVAE_PHASE_END
-    // elimination without pivoting: afterwards R = L^-1 J12, W = L^-1 L12', u = L^-1 v, pivots D
-    double logdet = 0.0;
+    // elimination without pivoting, ONE phase per pivot: the multipliers of pivot k are row k of the (symmetric)
+    // trailing block, left in the tile by the previous phase, times 1/pivot computed by every lane for itself.
+    // Afterwards R = L^-1 J12, W = L^-1 L12', u = L^-1 v, pivots D.
+    double det = 1.0, logdet = 0.0;      // one log per step, not per pivot (rescued if the product leaves range)
     for (int k = 0; k < n; ++k) {
       const double piv = t.M[k * NP + k];
       if (!(piv > 0.0) && !bad) bad = s + q + 1;
       const double pinv = 1.0 / piv;
-      logdet += log(piv);
-      SVAE_PHASE(c, n) {
-        if (c > k) t.mult[c] = t.M[k * NP + c] * pinv;     // M symmetric: row k of the trailing block = column k
-        if (c == k) t.dinv[k] = pinv;
-      } SVAE_PHASE_END
-      SVAE_PHASE(c, n + 1) {
+      det *= piv;
+      if (!(det > 1e-200 && det < 1e200)) { logdet += log(det); det = 1.0; }
+      SVAE_PHASE(l, vlane + 1) {
+        const int r = l / n, c = l - r * n;
         // loads first, stores last: the tile arrays share one allocation, so interleaved read-modify-writes would
         // serialise on possible aliasing
         double mu[16];
         SVAE_UNROLL
-        for (int i = 0; i < 16; ++i) mu[i] = (i > k && i < n) ? t.mult[i] : 0.0;
-        if (c < n) {
-          const double mk = (c > k) ? t.M[k * NP + c] : 0.0, rk = t.R[k * NP + c], wk = t.W[k * NP + c];
-          double vm[16], vr[16], vw[16];
-          SVAE_UNROLL
-          for (int i = 0; i < 16; ++i)
-            if (i < n) { vm[i] = t.M[i * NP + c]; vr[i] = t.R[i * NP + c]; vw[i] = t.W[i * NP + c]; }
-          SVAE_UNROLL
-          for (int i = 0; i < 16; ++i)
-            if (i < n) {
-              t.M[i * NP + c] = vm[i] - mu[i] * mk;
-              t.R[i * NP + c] = vr[i] - mu[i] * rk;
-              t.W[i * NP + c] = vw[i] - mu[i] * wk;
-            }
-        } else {
+        for (int i = 0; i < 16; ++i) mu[i] = (i > k && i < n) ? t.M[k * NP + i] * pinv : 0.0;
+        if (l == vlane) {
           const double uk = t.u[k];
           double vu[16];
           SVAE_UNROLL
@@ -161,55 +171,69 @@ SVAE_HD int compose_chunk(double* mem, int n, int s, int L, const double* pJ11, 
             if (i < n) vu[i] = t.u[i];
           SVAE_UNROLL
           for (int i = 0; i < 16; ++i)
-            if (i < n) t.u[i] = vu[i] - mu[i] * uk;
+            if (i > k && i < n) t.u[i] = vu[i] - mu[i] * uk;
+          t.dinv[k] = pinv;
+        } else {
+          for (int rr = 0; rr < 3; ++rr) {
+            if (roles == 3 && rr != r) continue;
+            if (rr == 0 && c <= k) continue;         // the eliminated columns of M are never read again
+            double* X = rr == 0 ? t.M : (rr == 1 ? t.R : t.W);
+            const double xk = X[k * NP + c];
+            double vx[16];
+            SVAE_UNROLL
+            for (int i = 0; i < 16; ++i)
+              if (i < n) vx[i] = X[i * NP + c];
+            SVAE_UNROLL
+            for (int i = 0; i < 16; ++i)
+              if (i > k && i < n) X[i * NP + c] = vx[i] - mu[i] * xk;
+          }
         }
       } SVAE_PHASE_END
     }
     double quad = 0.0;
     for (int k = 0; k < n; ++k) quad += t.u[k] * t.u[k] * t.dinv[k];
+    logdet += log(det);
     cc += (pair_logZ ? pair_logZ[(size_t)(s + q) * lz_stride] : 0.0) + (node_logZ ? node_logZ[s + q] : 0.0) + 0.5 * quad - 0.5 * logdet;
-    // products; the new L12' is staged in M (free now) because every lane still reads the old W
-    SVAE_PHASE(c, n + 1) {
-      // lane c < n: column c of the three products; lane n: the two vectors.  Own scaled column in registers, the
-      // other operand broadcast from the tile; results collected in registers and stored after the last load.
-      double wd[16], rd[16];
-      SVAE_UNROLL
-      for (int k = 0; k < 16; ++k) {
-        const double dk = (k < n) ? t.dinv[k] : 0.0;
-        wd[k] = (k < n) ? (c < n ? t.W[k * NP + c] : t.u[k]) * dk : 0.0;
-        rd[k] = (k < n && c < n) ? t.R[k * NP + c] * dk : 0.0;
-      }
-      // destinations are disjoint from everything read in this phase: say so, or every store fences the next loads
+    // products.  Destinations (L11, L12T, L22, e1, e2) are disjoint from everything read here (W, R, u, dinv, J22).
+    SVAE_PHASE(l, vlane + 1) {
+      const int r = l / n, c = l - r * n;
       const double* __restrict__ Wt = t.W;
       const double* __restrict__ Rt = t.R;
       double* __restrict__ L11 = t.L11;
-      double* __restrict__ Mst = t.M;
+      double* __restrict__ L12T = t.L12T;
       double* __restrict__ L22 = t.L22;
       double* __restrict__ e1 = t.e1;
       double* __restrict__ e2 = t.e2;
       const double* __restrict__ J22 = t.J22;
+      const bool vec = l == vlane;
+      double wd[16], rd[16];              // own column (or u) scaled by D^-1
+      SVAE_UNROLL
+      for (int k = 0; k < 16; ++k) {
+        const double dk = (k < n) ? t.dinv[k] : 0.0;
+        wd[k] = (k < n) ? (vec ? t.u[k] : Wt[k * NP + c]) * dk : 0.0;
+        rd[k] = (k < n && !vec) ? Rt[k * NP + c] * dk : 0.0;
+      }
+      const bool do11 = vec || roles == 1 || r == 0;      // W' D^-1 (W col | u)
+      const bool do12 = vec || roles == 1 || r == 1;      // R' D^-1 (W col | u)
+      const bool do22 = !vec && (roles == 1 || r == 2);   // R' D^-1 (R col)
       for (int i = 0; i < n; ++i) {
         double a11 = 0.0, a12 = 0.0, a22 = 0.0;
         SVAE_UNROLL
         for (int k = 0; k < 16; ++k)
           if (k < n) {
-            const double wki = Wt[k * NP + i], rki = Rt[k * NP + i];
-            a11 = fma(wki, wd[k], a11);
-            a12 = fma(rki, wd[k], a12);
-            a22 = fma(rki, rd[k], a22);
+            if (do11) a11 = fma(Wt[k * NP + i], wd[k], a11);
+            if (do12) a12 = fma(Rt[k * NP + i], wd[k], a12);
+            if (do22) a22 = fma(Rt[k * NP + i], rd[k], a22);
           }
-        if (c < n) {
-          L11[i * NP + c] -= a11;
-          Mst[i * NP + c] = -a12;
-          L22[i * NP + c] = J22[i * NP + c] - a22;
+        if (vec) {
+          e1[i] -= a11;
+          e2[i] = -a12;
         } else {
-          e1[i] -= a11;      // W' D^-1 u
-          e2[i] = -a12;      // -R' D^-1 u
+          if (do11) L11[i * NP + c] -= a11;
+          if (do12) L12T[i * NP + c] = -a12;
+          if (do22) L22[i * NP + c] = J22[i * NP + c] - a22;
         }
       }
-    } SVAE_PHASE_END
-    SVAE_PHASE(c, n) {
-      for (int i = 0; i < n; ++i) t.L12T[i * NP + c] = t.M[i * NP + c];
     } SVAE_PHASE_END
   }
 

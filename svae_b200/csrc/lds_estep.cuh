@@ -77,7 +77,7 @@ __host__ __device__ inline int lds_record_stride(int N, int S, bool save) {
 // parameters) and the backward sweep (stash ring, C) never overlap in time, so they share storage.
 __host__ __device__ inline int lds_tile_filter_doubles(int N, int S, bool inhomog) {
   const int NP = lds_np(N);
-  return 2 * N * NP /*Lr, Lt*/ + 2 * (2 + S) * NP /*node ring*/ + (inhomog ? 2 * N * NP : 0);
+  return 2 * N * NP /*Lr, Lt*/ + 2 * (2 + S) * NP /*node ring*/ + (inhomog ? 5 * N * NP /*tJ12, tJ22, pair stage*/ : 0);
 }
 __host__ __device__ inline int lds_tile_backward_doubles(int N, int S) {
   return 2 * lds_stash_stride(N, S) /*stash ring*/ + N * lds_np(N) /*Cs*/;
@@ -154,6 +154,7 @@ __global__ void SVAE_LDS_BOUNDS(N, CPL) lds_estep_fwd_kernel(const LdsFwdParams 
   double* nring = Lt + N * NP;    // 2 x { J_node row | h_node row | eps rows }
   double* tJ12 = nring + 2 * NODE;  // per-tile pair parameters (INHOMOG only)
   double* tJ22 = tJ12 + N * NP;
+  double* pstage = tJ22 + N * NP;   // raw J11 | J12 | J22 of the NEXT step, prefetched with cp.async (INHOMOG only)
   // backward sweep
   double* ring = uni;             // 2 stash records
   double* Cs = ring + 2 * SS;     // Cs[k*NP+i] = C[i][k]
@@ -197,6 +198,27 @@ __global__ void SVAE_LDS_BOUNDS(N, CPL) lds_estep_fwd_kernel(const LdsFwdParams 
     cp_async_commit();
   };
 
+  // INHOMOG: the pair parameters of step t stream into `pstage` one step ahead; every lane copies and later reads
+  // only its own column, so the staging needs no barrier of its own (the group is retired by the step's
+  // cp_async_wait<0>).  Without it a short batch pays a global-memory round trip at the top of every step.
+  auto stage_pair = [&](int t) {
+    if (INHOMOG) {
+      const size_t off = (size_t)t * p.pair_stride_t + (size_t)b * p.pair_stride_b;
+#pragma unroll
+      for (int cl = 0; cl < CPL; ++cl) {
+        if (mat[cl]) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            cp_async8(pstage + i * NP + c[cl], p.J11 + off + i * N + c[cl]);
+            cp_async8(pstage + (N + i) * NP + c[cl], p.J12 + off + i * N + c[cl]);
+            cp_async8(pstage + (2 * N + i) * NP + c[cl], p.J22 + off + i * N + c[cl]);
+          }
+        }
+      }
+      cp_async_commit();
+    }
+  };
+
   double lacc = 0.0;   // per-lane partial of lognorm (reduced over the tile at the end)
   double lq[CPL];      // sum_t sum_k z_k^2 / d_k accumulated by every slot, only the vec slot's is used
 #pragma unroll
@@ -204,6 +226,7 @@ __global__ void SVAE_LDS_BOUNDS(N, CPL) lds_estep_fwd_kernel(const LdsFwdParams 
   int badbits = 0;     // OR of the pivots' high words: the sign bit flags a non-positive-definite M_t
   double dprod = 1.0;  // running product of this lane's pivots (log taken every few steps)
 
+  if (T > 1) stage_pair(0);
   stage_node(0);
   if (T > 1) stage_node(1); else cp_async_commit();
   cp_async_wait<1>();
@@ -232,18 +255,18 @@ __global__ void SVAE_LDS_BOUNDS(N, CPL) lds_estep_fwd_kernel(const LdsFwdParams 
   for (int t = 0; t < T; ++t) {
     const bool last = (t == T - 1);
     if (INHOMOG && !last) {
-      const size_t off = (size_t)t * p.pair_stride_t + (size_t)b * p.pair_stride_b;
 #pragma unroll
       for (int cl = 0; cl < CPL; ++cl) {
         if (mat[cl]) {
 #pragma unroll
           for (int i = 0; i < N; ++i) {
-            a[cl][i] += -2.0 * p.J11[off + i * N + c[cl]];
-            tJ12[i * NP + c[cl]] = -p.J12[off + i * N + c[cl]];
-            tJ22[i * NP + c[cl]] = -2.0 * p.J22[off + i * N + c[cl]];
+            a[cl][i] += -2.0 * pstage[i * NP + c[cl]];
+            tJ12[i * NP + c[cl]] = -pstage[(N + i) * NP + c[cl]];
+            tJ22[i * NP + c[cl]] = -2.0 * pstage[(2 * N + i) * NP + c[cl]];
           }
         }
       }
+      if (t + 1 < T - 1) stage_pair(t + 1);   // lands during this step; retired by its cp_async_wait<0>
       __syncwarp();
     }
     const double* nd = nring + (t & 1) * NODE;

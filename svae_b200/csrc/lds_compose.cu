@@ -20,6 +20,7 @@ struct ComposeParams {
   int* status;
 };
 
+template <int N>
 __global__ void __launch_bounds__(32 * kWarps) lds_compose_kernel(const ComposeParams p) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5;
@@ -28,15 +29,33 @@ __global__ void __launch_bounds__(32 * kWarps) lds_compose_kernel(const ComposeP
   const int b = (int)(tile / p.C), c = (int)(tile % p.C);
   const int s = c * p.Lc;
   const int L = min(p.Lc, p.T - 1 - s);
-  const int n = p.n, nn = n * n;
+  constexpr int n = N, nn = N * N;
   const size_t bt = (size_t)b * p.T;
   const size_t pb = (size_t)b * p.stride_b;
-  const int bad = svae::compose_chunk(
-      smem + (size_t)warp * svae::compose_tile_doubles(n), n, s, L, p.J11 + pb, p.J12 + pb, p.J22 + pb,
-      p.pair_logZ ? p.pair_logZ + pb / nn : nullptr, p.stride_t, p.node_J + bt * n, p.node_h + bt * n, p.node_logZ ? p.node_logZ + bt : nullptr, p.cJ11 + tile * nn,
-      p.cJ12 + tile * nn, p.cJ22 + tile * nn, p.clogZ + tile, p.ce1 + tile * n, p.ce2 + tile * n);
+  const int bad = svae::compose_chunk<N>(
+      smem + (size_t)warp * svae::compose_tile_doubles(n), s, L, p.J11 + pb, p.J12 + pb, p.J22 + pb,
+      p.pair_logZ ? p.pair_logZ + pb / nn : nullptr, p.stride_t, p.node_J + bt * n, p.node_h + bt * n,
+      p.node_logZ ? p.node_logZ + bt : nullptr, p.cJ11 + tile * nn, p.cJ12 + tile * nn, p.cJ22 + tile * nn, p.clogZ + tile,
+      p.ce1 + tile * n, p.ce2 + tile * n);
   if (bad && p.status && (threadIdx.x & 31) == 0) atomicCAS(p.status, 0, b + 1);
 }
+
+template <int N>
+cudaError_t launch_compose(const ComposeParams& p, cudaStream_t stream) {
+  const size_t smem = sizeof(double) * (size_t)kWarps * svae::compose_tile_doubles(N);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(lds_compose_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const long long tiles = (long long)p.B * p.C;
+  lds_compose_kernel<N><<<(unsigned)((tiles + kWarps - 1) / kWarps), 32 * kWarps, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+typedef cudaError_t (*compose_fn)(const ComposeParams&, cudaStream_t);
+const compose_fn kCompose[SVAE_LDS_MAX_N + 1] = {
+    nullptr, launch_compose<1>, launch_compose<2>, launch_compose<3>, launch_compose<4>, launch_compose<5>,
+    launch_compose<6>, launch_compose<7>, launch_compose<8>, launch_compose<9>, launch_compose<10>, launch_compose<11>,
+    launch_compose<12>, launch_compose<13>, launch_compose<14>, launch_compose<15>, launch_compose<16>};
 }  // namespace
 
 extern "C" int svae_lds_compose_num_chunks(int T, int chunk_len) {
@@ -63,13 +82,7 @@ extern "C" int svae_lds_compose_chunks(int B, int T, int n, int chunk_len, const
   p.node_J = node_J; p.node_h = node_h; p.node_logZ = node_logZ;
   p.cJ11 = chunk_J11; p.cJ12 = chunk_J12; p.cJ22 = chunk_J22; p.clogZ = chunk_logZ; p.ce1 = chunk_e1; p.ce2 = chunk_e2;
   p.status = status;
-  const size_t smem = sizeof(double) * (size_t)kWarps * svae::compose_tile_doubles(n);
-  cudaError_t e = cudaSuccess;
-  if (smem > 48 * 1024) e = cudaFuncSetAttribute(lds_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return SVAE_ERR_CUDA;
-  const long long tiles = (long long)B * p.C;
-  const unsigned grid = (unsigned)((tiles + kWarps - 1) / kWarps);
-  lds_compose_kernel<<<grid, 32 * kWarps, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  const cudaError_t e = kCompose[n](p, static_cast<cudaStream_t>(stream));
   g_svae_launches.fetch_add(1);
-  return cudaGetLastError() == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
+  return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
 }

@@ -88,26 +88,38 @@ SVAE_HD ComposeTile compose_tile(double* mem, int n) {
 // Time-inhomogeneous pair parameters: pair_stride_t doubles between consecutive steps' (n,n) blocks (0 = homogeneous);
 // pJ11/pJ12/pJ22 point at this sequence's step 0 and pair_logZ (or null) at its step-0 entry with stride
 // pair_stride_t / (n*n), exactly the addressing of the fused kernel (lds_estep.cuh).
-SVAE_HD int compose_chunk(double* mem, int n, int s, int L, const double* pJ11, const double* pJ12, const double* pJ22,
+//
+// N is a template parameter like in the fused kernels: every loop below has a static trip count, every tile address
+// is an immediate (the first, runtime-n version of this function spent 8 700 warp-instructions per step, most of
+// them predicates and address arithmetic; ncu: profiles/r01_lds_compose_summary.txt).
+// Lane roles: with 3N+1 <= 32 the three N-column blocks of the augmented matrix [M | J12 | L12' | v] get their own
+// lanes (lane = role*N + column, lane 3N = the vector); otherwise lane c < N carries column c of all three blocks
+// and lane N the vector.
+template <int N>
+SVAE_HD int compose_chunk(double* mem, int s, int L, const double* pJ11, const double* pJ12, const double* pJ22,
                           const double* pair_logZ, long long pair_stride_t, const double* node_J, const double* node_h,
                           const double* node_logZ, double* out_J11, double* out_J12, double* out_J22, double* out_logZ,
                           double* out_e1, double* out_e2) {
-  constexpr int NP = 16;
+  constexpr int NP = 16, n = N;
+  constexpr int ROLES = (3 * N + 1 <= 32) ? 3 : 1;
+  constexpr int VL = ROLES * N;           // the vector lane
   ComposeTile t = compose_tile(mem, n);
   double cc = 0.0;
   int bad = 0;
   const long long lz_stride = pair_stride_t / ((long long)n * n);
-  SVAE_PHASE(c, n) {
+  SVAE_PHASE(c, N) {
     const size_t po = (size_t)s * pair_stride_t;
-    for (int i = 0; i < n; ++i) {
+    SVAE_UNROLL
+    for (int i = 0; i < N; ++i) {
       t.J11[i * NP + c] = -2.0 * pJ11[po + i * n + c];
       t.J12[i * NP + c] = -pJ12[po + i * n + c];
       t.J22[i * NP + c] = -2.0 * pJ22[po + i * n + c];
     }
   } SVAE_PHASE_END
   // first step: the element of node_s . pair
-  SVAE_PHASE(c, n) {
-    for (int i = 0; i < n; ++i) {
+  SVAE_PHASE(c, N) {
+    SVAE_UNROLL
+    for (int i = 0; i < N; ++i) {
       t.L11[i * NP + c] = t.J11[i * NP + c] + (i == c ? -2.0 * node_J[(size_t)s * n + c] : 0.0);
       t.L12T[i * NP + c] = t.J12[c * NP + i];
       t.L22[i * NP + c] = t.J22[i * NP + c];
@@ -120,29 +132,29 @@ SVAE_HD int compose_chunk(double* mem, int n, int s, int L, const double* pJ11, 
   for (int q = 1; q < L; ++q) {
     const size_t o = (size_t)(s + q) * n;
     if (pair_stride_t != 0) {   // this step's pair potential
-      SVAE_PHASE(c, n) {
+      SVAE_PHASE(c, N) {
         const size_t po = (size_t)(s + q) * pair_stride_t;
-        for (int i = 0; i < n; ++i) {
+        SVAE_UNROLL
+        for (int i = 0; i < N; ++i) {
           t.J11[i * NP + c] = -2.0 * pJ11[po + i * n + c];
           t.J12[i * NP + c] = -pJ12[po + i * n + c];
           t.J22[i * NP + c] = -2.0 * pJ22[po + i * n + c];
         }
       } SVAE_PHASE_END
     }
-    // Lane roles.  With 3n+1 <= 32 the three n-column blocks of the augmented matrix [M | J12 | L12' | v] get their
-    // own lanes (lane = role*n + column, lane 3n = the vector): a third of the work per lane and phase.  Otherwise
-    // lane c < n carries column c of all three blocks and lane n the vector.
-    const int roles = (3 * n + 1 <= 32) ? 3 : 1;
-    const int vlane = roles * n;
-    SVAE_PHASE(l, vlane + 1) {
-      const int r = l / n, c = l - r * n;
-      if (l == vlane) {
-        for (int i = 0; i < n; ++i) t.u[i] = t.e2[i] + node_h[o + i];
+    // augmented matrix [M | J12 | L12' | v]
+    SVAE_PHASE(l, VL + 1) {
+      const int r = l / N, c = l - r * N;
+      if (l == VL) {
+        SVAE_UNROLL
+        for (int i = 0; i < N; ++i) t.u[i] = t.e2[i] + node_h[o + i];
       } else {
-        for (int i = 0; i < n; ++i) {
-          if (roles == 1 || r == 0) t.M[i * NP + c] = t.L22[i * NP + c] + t.J11[i * NP + c] + (i == c ? -2.0 * node_J[o + c] : 0.0);
-          if (roles == 1 || r == 1) t.R[i * NP + c] = t.J12[i * NP + c];
-          if (roles == 1 || r == 2) t.W[i * NP + c] = t.L12T[i * NP + c];
+        const double nj = (ROLES == 1 || r == 0) ? -2.0 * node_J[o + c] : 0.0;
+        SVAE_UNROLL
+        for (int i = 0; i < N; ++i) {
+          if (ROLES == 1 || r == 0) t.M[i * NP + c] = t.L22[i * NP + c] + t.J11[i * NP + c] + (i == c ? nj : 0.0);
+          if (ROLES == 1 || r == 1) t.R[i * NP + c] = t.J12[i * NP + c];
+          if (ROLES == 1 || r == 2) t.W[i * NP + c] = t.L12T[i * NP + c];
         }
       }
     } SVAE_PHASE_END
@@ -150,95 +162,103 @@ SVAE_HD int compose_chunk(double* mem, int n, int s, int L, const double* pJ11, 
     // trailing block, left in the tile by the previous phase, times 1/pivot computed by every lane for itself.
     // Afterwards R = L^-1 J12, W = L^-1 L12', u = L^-1 v, pivots D.
     double det = 1.0, logdet = 0.0;      // one log per step, not per pivot (rescued if the product leaves range)
-    for (int k = 0; k < n; ++k) {
+    SVAE_UNROLL
+    for (int k = 0; k < N; ++k) {
       const double piv = t.M[k * NP + k];
       if (!(piv > 0.0) && !bad) bad = s + q + 1;
       const double pinv = 1.0 / piv;
       det *= piv;
       if (!(det > 1e-200 && det < 1e200)) { logdet += log(det); det = 1.0; }
-      SVAE_PHASE(l, vlane + 1) {
-        const int r = l / n, c = l - r * n;
+      SVAE_PHASE(l, VL + 1) {
+        const int r = l / N, c = l - r * N;
         // loads first, stores last: the tile arrays share one allocation, so interleaved read-modify-writes would
         // serialise on possible aliasing
-        double mu[16];
+        double mu[N];
         SVAE_UNROLL
-        for (int i = 0; i < 16; ++i) mu[i] = (i > k && i < n) ? t.M[k * NP + i] * pinv : 0.0;
-        if (l == vlane) {
+        for (int i = k + 1; i < N; ++i) mu[i] = t.M[k * NP + i] * pinv;
+        if (l == VL) {
           const double uk = t.u[k];
-          double vu[16];
+          double vu[N];
           SVAE_UNROLL
-          for (int i = 0; i < 16; ++i)
-            if (i < n) vu[i] = t.u[i];
+          for (int i = k + 1; i < N; ++i) vu[i] = t.u[i];
           SVAE_UNROLL
-          for (int i = 0; i < 16; ++i)
-            if (i > k && i < n) t.u[i] = vu[i] - mu[i] * uk;
+          for (int i = k + 1; i < N; ++i) t.u[i] = vu[i] - mu[i] * uk;
           t.dinv[k] = pinv;
         } else {
-          for (int rr = 0; rr < 3; ++rr) {
-            if (roles == 3 && rr != r) continue;
-            if (rr == 0 && c <= k) continue;         // the eliminated columns of M are never read again
-            double* X = rr == 0 ? t.M : (rr == 1 ? t.R : t.W);
+          SVAE_UNROLL
+          for (int rr = 0; rr < (ROLES == 1 ? 3 : 1); ++rr) {
+            const int role = (ROLES == 1) ? rr : r;
+            if (role == 0 && c <= k) continue;       // the eliminated columns of M are never read again
+            double* X = role == 0 ? t.M : (role == 1 ? t.R : t.W);
             const double xk = X[k * NP + c];
-            double vx[16];
+            double vx[N];
             SVAE_UNROLL
-            for (int i = 0; i < 16; ++i)
-              if (i < n) vx[i] = X[i * NP + c];
+            for (int i = k + 1; i < N; ++i) vx[i] = X[i * NP + c];
             SVAE_UNROLL
-            for (int i = 0; i < 16; ++i)
-              if (i > k && i < n) X[i * NP + c] = vx[i] - mu[i] * xk;
+            for (int i = k + 1; i < N; ++i) X[i * NP + c] = vx[i] - mu[i] * xk;
           }
         }
       } SVAE_PHASE_END
     }
     double quad = 0.0;
-    for (int k = 0; k < n; ++k) quad += t.u[k] * t.u[k] * t.dinv[k];
+    SVAE_UNROLL
+    for (int k = 0; k < N; ++k) quad += t.u[k] * t.u[k] * t.dinv[k];
     logdet += log(det);
     cc += (pair_logZ ? pair_logZ[(size_t)(s + q) * lz_stride] : 0.0) + (node_logZ ? node_logZ[s + q] : 0.0) + 0.5 * quad - 0.5 * logdet;
-    // products.  Destinations (L11, L12T, L22, e1, e2) are disjoint from everything read here (W, R, u, dinv, J22).
-    SVAE_PHASE(l, vlane + 1) {
-      const int r = l / n, c = l - r * n;
+    // products  A' D^-1 b  with (A, b, destination) by role:
+    //   role 0: W' D^-1 W[:,c]  -> L11[:,c] -=      role 1: R' D^-1 W[:,c] -> L12'[:,c] = -
+    //   role 2: R' D^-1 R[:,c]  -> L22[:,c] = J22 - vector lane: W' D^-1 u -> e1 -= ,  R' D^-1 u -> e2 = -
+    // Destinations are disjoint from everything read here (W, R, u, dinv, J22): said with __restrict__.
+    SVAE_PHASE(l, VL + 1) {
+      const int r = l / N, c = l - r * N;
       const double* __restrict__ Wt = t.W;
       const double* __restrict__ Rt = t.R;
+      const double* __restrict__ J22 = t.J22;
       double* __restrict__ L11 = t.L11;
       double* __restrict__ L12T = t.L12T;
       double* __restrict__ L22 = t.L22;
       double* __restrict__ e1 = t.e1;
       double* __restrict__ e2 = t.e2;
-      const double* __restrict__ J22 = t.J22;
-      const bool vec = l == vlane;
-      double wd[16], rd[16];              // own column (or u) scaled by D^-1
+      const bool vec = l == VL;
       SVAE_UNROLL
-      for (int k = 0; k < 16; ++k) {
-        const double dk = (k < n) ? t.dinv[k] : 0.0;
-        wd[k] = (k < n) ? (vec ? t.u[k] : Wt[k * NP + c]) * dk : 0.0;
-        rd[k] = (k < n && !vec) ? Rt[k * NP + c] * dk : 0.0;
-      }
-      const bool do11 = vec || roles == 1 || r == 0;      // W' D^-1 (W col | u)
-      const bool do12 = vec || roles == 1 || r == 1;      // R' D^-1 (W col | u)
-      const bool do22 = !vec && (roles == 1 || r == 2);   // R' D^-1 (R col)
-      for (int i = 0; i < n; ++i) {
-        double a11 = 0.0, a12 = 0.0, a22 = 0.0;
+      for (int pass = 0; pass < ((ROLES == 1) ? 3 : 2); ++pass) {
+        const int role = (ROLES == 1 || vec) ? pass : r;
+        if (ROLES == 3 && !vec && pass > 0) continue;
+        if (vec && pass > 1) continue;
+        // vector lane: pass 0 = (W, u), pass 1 = (R, u)
+        const double* A = vec ? (pass == 0 ? Wt : Rt) : (role == 0 ? Wt : Rt);
+        const double* bs = vec ? t.u : ((role == 2 ? Rt : Wt) + c);
+        const int bstr = vec ? 1 : NP;
+        double bd[N];
         SVAE_UNROLL
-        for (int k = 0; k < 16; ++k)
-          if (k < n) {
-            if (do11) a11 = fma(Wt[k * NP + i], wd[k], a11);
-            if (do12) a12 = fma(Rt[k * NP + i], wd[k], a12);
-            if (do22) a22 = fma(Rt[k * NP + i], rd[k], a22);
+        for (int k = 0; k < N; ++k) bd[k] = bs[k * bstr] * t.dinv[k];
+        double acc[N];
+        SVAE_UNROLL
+        for (int i = 0; i < N; ++i) acc[i] = 0.0;
+        SVAE_UNROLL
+        for (int k = 0; k < N; ++k) {
+          SVAE_UNROLL
+          for (int i = 0; i < N; ++i) acc[i] = fma(A[k * NP + i], bd[k], acc[i]);
+        }
+        SVAE_UNROLL
+        for (int i = 0; i < N; ++i) {
+          if (vec) {
+            if (pass == 0) e1[i] -= acc[i]; else e2[i] = -acc[i];
+          } else if (role == 0) {
+            L11[i * NP + c] -= acc[i];
+          } else if (role == 1) {
+            L12T[i * NP + c] = -acc[i];
+          } else {
+            L22[i * NP + c] = J22[i * NP + c] - acc[i];
           }
-        if (vec) {
-          e1[i] -= a11;
-          e2[i] = -a12;
-        } else {
-          if (do11) L11[i * NP + c] -= a11;
-          if (do12) L12T[i * NP + c] = -a12;
-          if (do22) L22[i * NP + c] = J22[i * NP + c] - a22;
         }
       }
     } SVAE_PHASE_END
   }
 
-  SVAE_PHASE(c, n) {
-    for (int i = 0; i < n; ++i) {
+  SVAE_PHASE(c, N) {
+    SVAE_UNROLL
+    for (int i = 0; i < N; ++i) {
       // symmetrise the diagonal blocks against rounding drift; natural-form output
       out_J11[i * n + c] = -0.25 * (t.L11[i * NP + c] + t.L11[c * NP + i]);
       out_J22[i * n + c] = -0.25 * (t.L22[i * NP + c] + t.L22[c * NP + i]);
@@ -250,5 +270,23 @@ SVAE_HD int compose_chunk(double* mem, int n, int s, int L, const double* pJ11, 
   } SVAE_PHASE_END
   return bad;
 }
+
+// runtime-n dispatch (host harness and kernel)
+#define SVAE_COMPOSE_CASE(NN) case NN: return compose_chunk<NN>(mem, s, L, pJ11, pJ12, pJ22, pair_logZ, pair_stride_t, \
+                                                                node_J, node_h, node_logZ, out_J11, out_J12, out_J22,   \
+                                                                out_logZ, out_e1, out_e2);
+SVAE_HD int compose_chunk_n(int n, double* mem, int s, int L, const double* pJ11, const double* pJ12, const double* pJ22,
+                            const double* pair_logZ, long long pair_stride_t, const double* node_J, const double* node_h,
+                            const double* node_logZ, double* out_J11, double* out_J12, double* out_J22, double* out_logZ,
+                            double* out_e1, double* out_e2) {
+  switch (n) {
+    SVAE_COMPOSE_CASE(1) SVAE_COMPOSE_CASE(2) SVAE_COMPOSE_CASE(3) SVAE_COMPOSE_CASE(4) SVAE_COMPOSE_CASE(5)
+    SVAE_COMPOSE_CASE(6) SVAE_COMPOSE_CASE(7) SVAE_COMPOSE_CASE(8) SVAE_COMPOSE_CASE(9) SVAE_COMPOSE_CASE(10)
+    SVAE_COMPOSE_CASE(11) SVAE_COMPOSE_CASE(12) SVAE_COMPOSE_CASE(13) SVAE_COMPOSE_CASE(14) SVAE_COMPOSE_CASE(15)
+    SVAE_COMPOSE_CASE(16)
+    default: return -1;
+  }
+}
+#undef SVAE_COMPOSE_CASE
 
 }  // namespace svae

@@ -17,7 +17,7 @@ extern "C" int compose_chunks_host(int B, int T, int n, int chunk_len, const dou
       const long long tile = (long long)b * C + c;
       const int s = c * chunk_len, L = std::min(chunk_len, T - 1 - s);
       const size_t pb = (size_t)b * stride_b;
-      const int bad = svae::compose_chunk(mem.data(), n, s, L, J11 + pb, J12 + pb, J22 + pb,
+      const int bad = svae::compose_chunk_n(n, mem.data(), s, L, J11 + pb, J12 + pb, J22 + pb,
                                           pair_logZ ? pair_logZ + pb / (n * n) : nullptr, stride_t,
                                           node_J + (size_t)b * T * n, node_h + (size_t)b * T * n,
                                           node_logZ ? node_logZ + (size_t)b * T : nullptr, cJ11 + tile * n * n,

@@ -266,21 +266,19 @@ __global__ void SVAE_LDS_BOUNDS(N, CPL) lds_estep_fwd_kernel(const LdsFwdParams 
           }
         }
       }
-      if (t + 1 < T - 1) stage_pair(t + 1);   // lands during this step; retired by its cp_async_wait<0>
       __syncwarp();
     }
     const double* nd = nring + (t & 1) * NODE;
 
     if (p.msg_J_pred || p.in_J_filt || p.node_J_dense || (p.term_J && last)) {
       // cold path: the three-primitive interface of the reference (messages out / messages in)
-      const size_t off = (size_t)t * p.pair_stride_t + (size_t)b * p.pair_stride_b;
       const size_t bt = (size_t)b * T + t;
 #pragma unroll
       for (int cl = 0; cl < CPL; ++cl) {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           if (mat[cl]) {
-            const double j11 = last ? 0.0 : (INHOMOG ? -2.0 * p.J11[off + i * N + c[cl]]
+            const double j11 = last ? 0.0 : (INHOMOG ? -2.0 * pstage[i * NP + c[cl]]   // still this step's J11
                                                      : shJ11[i * NP + c[cl]] - shJ22[i * NP + c[cl]]);
             if (p.msg_J_pred && valid) p.msg_J_pred[bt * NN + i * N + c[cl]] = -0.5 * (a[cl][i] - j11);
             if (p.in_J_filt) a[cl][i] = -2.0 * p.in_J_filt[bt * NN + i * N + c[cl]] + j11;
@@ -293,6 +291,10 @@ __global__ void SVAE_LDS_BOUNDS(N, CPL) lds_estep_fwd_kernel(const LdsFwdParams 
         }
       }
     }
+
+    // the staging buffer is consumed: stream the next step's pair parameters into it; they land during this step
+    // and are retired by its cp_async_wait<0>
+    if (INHOMOG && t + 1 < T - 1) stage_pair(t + 1);
 
     // right-hand sides: r = J12 column (mat), q = identity column (mat -> M^-1 column)
     double r[CPL][N], q[CPL][N];

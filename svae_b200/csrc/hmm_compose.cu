@@ -11,16 +11,14 @@ extern std::atomic<uint64_t> g_svae_launches;
 namespace {
 constexpr int kWarps = 2;
 
-__global__ void __launch_bounds__(32 * kWarps) hmm_compose_kernel(int B, int T, int K, int Lc, int C, const double* log_A,
-                                                                  const double* node, double* P, double* logscale) {
+__global__ void __launch_bounds__(32 * svae::kHmmWarps) hmm_compose_kernel(int B, int T, int K, int Lc, int C,
+                                                                           const double* log_A, const double* node, double* P,
+                                                                           double* logscale) {
   extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5;
-  const long long tile = (long long)blockIdx.x * kWarps + warp;
-  if (tile >= (long long)B * C) return;   // warp-uniform
+  const long long tile = blockIdx.x;      // one CTA per (sequence, chunk)
   const int b = (int)(tile / C), c = (int)(tile % C);
   const int s = c * Lc, L = min(Lc, T - 1 - s);
-  svae::hmm_compose_chunk(smem + (size_t)warp * svae::hmm_compose_tile_doubles(K), K, s, L, log_A,
-                          node + (size_t)b * T * K, P + tile * K * K, logscale + tile);
+  svae::hmm_compose_chunk(smem, K, s, L, log_A, node + (size_t)b * T * K, P + tile * K * K, logscale + tile);
 }
 
 __global__ void __launch_bounds__(32 * kWarps) hmm_chain_kernel(int B, int K, int C, const double* log_pi, const double* P,
@@ -41,12 +39,9 @@ extern "C" int svae_hmm_compose_chunks(int B, int T, int K, int chunk_len, const
   if (B <= 0 || T < 2 || K <= 0 || chunk_len < 1 || !log_A || !node || !chunk_P || !chunk_logscale) return SVAE_ERR_BAD_ARG;
   if (K > SVAE_HMM_MAX_K) return SVAE_ERR_UNSUPPORTED;
   const int C = svae_lds_compose_num_chunks(T, chunk_len);
-  const size_t smem = sizeof(double) * (size_t)kWarps * svae::hmm_compose_tile_doubles(K);
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(hmm_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return SVAE_ERR_CUDA;
+  const size_t smem = sizeof(double) * (size_t)svae::hmm_compose_tile_doubles(K);
   const long long tiles = (long long)B * C;
-  hmm_compose_kernel<<<(unsigned)((tiles + kWarps - 1) / kWarps), 32 * kWarps, smem, static_cast<cudaStream_t>(stream)>>>(
+  hmm_compose_kernel<<<(unsigned)tiles, 32 * svae::kHmmWarps, smem, static_cast<cudaStream_t>(stream)>>>(
       B, T, K, chunk_len, C, log_A, node, chunk_P, chunk_logscale);
   g_svae_launches.fetch_add(1);
   return cudaGetLastError() == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;

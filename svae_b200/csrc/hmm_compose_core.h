@@ -28,80 +28,109 @@ namespace svae {
 //   PDt [k*kHmmRow + i]       (P D)^T, double-buffered: row k = column k of P times d_k, contiguous in i so the product
 //                             loop reads it with 128-bit broadcasts; row stride 34 keeps rows 16-byte aligned and the
 //                             per-lane row stores at a 4-way bank conflict instead of 32-way.
+// One CTA of kHmmWarps warps per chunk: thread (w, j) owns rows [8w, 8w+8) of column j of the running product, so a
+// step's 32 x 32 x 32 product is spread over four warp schedulers (a single warp is bounded by the FP64 issue rate of
+// its scheduler: 1024 DFMA at one per two cycles).
 constexpr int kHmmRow = 34;
-SVAE_HD int hmm_compose_tile_doubles(int /*K*/) { return 32 * 32 + 2 * 32 * kHmmRow + 3 * 32; }
+constexpr int kHmmWarps = 4;
+constexpr int kHmmRows = 32 / kHmmWarps;   // rows per thread
+SVAE_HD int hmm_compose_tile_doubles(int /*K*/) { return 32 * 32 + 2 * 32 * kHmmRow + 32 * kHmmWarps + 3 * 32; }
 
 // log_A (K,K) row = from-state; node (T,K) of this sequence.  Writes P (K,K) row-major with max entry 1 and
 // *logscale such that Psi = P * exp(*logscale).
 SVAE_HD void hmm_compose_chunk(double* mem, int K, int s, int L, const double* log_A, const double* node, double* out_P,
                                double* out_logscale) {
+  constexpr int TH = 32 * kHmmWarps;
   double* A = mem;
   double* PDt0 = mem + 32 * 32;
   double* PDt1 = PDt0 + 32 * kHmmRow;
-  double* colmax = PDt1 + 32 * kHmmRow;
+  double* tmax = PDt1 + 32 * kHmmRow;   // per-thread maxima (TH)
+  double* colmax = tmax + TH;
   double* d = colmax + 32;
   double* nd = d + 32;
-  SVAE_PHASE(j, K) {
+  SVAE_BPHASE(j, K) {
     double m = log_A[j];
     for (int k = 1; k < K; ++k) m = fmax(m, log_A[k * K + j]);
     colmax[j] = m;
     nd[j] = node[(size_t)s * K + j];
-  } SVAE_PHASE_END
+    if (L > 1) d[j] = node[(size_t)(s + 1) * K + j];
+  } SVAE_BPHASE_END
   double amax = colmax[0], nmax = nd[0];
   for (int j = 1; j < K; ++j) {
     amax = fmax(amax, colmax[j]);
     nmax = fmax(nmax, nd[j]);
   }
-  // P = I, so (P D_s)^T row k = d_k e_k
-  SVAE_PHASE(j, K) {
-    for (int k = 0; k < K; ++k) A[k * 32 + j] = exp(log_A[k * K + j] - amax);
-    const double dj = exp(nd[j] - nmax);
-    for (int i = 0; i < 32; ++i) PDt0[j * kHmmRow + i] = (i == j) ? dj : 0.0;   // entries i >= K stay exactly zero
-    if (L > 1) nd[j] = node[(size_t)(s + 1) * K + j];
-  } SVAE_PHASE_END
+  // P = I, so (P D_s)^T row k = d_k e_k; columns and rows beyond K stay exactly zero
+  SVAE_BPHASE(t, TH) {
+    const int w = t >> 5, j = t & 31;
+    if (w == 0 && j < K) {
+      for (int k = 0; k < K; ++k) A[k * 32 + j] = exp(log_A[k * K + j] - amax);
+    }
+    const double dj = (j < K) ? exp(nd[j] - nmax) : 0.0;
+    SVAE_UNROLL
+    for (int ii = 0; ii < kHmmRows; ++ii) {
+      const int i = w * kHmmRows + ii;
+      PDt0[j * kHmmRow + i] = (i == j) ? dj : 0.0;
+      PDt1[j * kHmmRow + i] = 0.0;
+    }
+  } SVAE_BPHASE_END
+  // node potentials ride a two-slot ring: slot (q+1)&1 holds step s+q+1 at iteration q (slot 0 = nd, slot 1 = d)
   double logscale = (double)L * amax + nmax;
   double inv = 1.0;                      // 1 / max of the previous (unscaled) product, folded into the A operand
   for (int q = 0; q < L; ++q) {
     const double* cur = (q & 1) ? PDt1 : PDt0;
     double* nxt = (q & 1) ? PDt0 : PDt1;
     const bool more = q + 1 < L;
+    const double* ndc = ((q + 1) & 1) ? d : nd;     // node potentials of step s+q+1
+    double* ndn = ((q + 1) & 1) ? nd : d;           // free slot (held step s+q): receives step s+q+2
     double nmax2 = 0.0;
     if (more) {
-      nmax2 = nd[0];
-      for (int j = 1; j < K; ++j) nmax2 = fmax(nmax2, nd[j]);
+      nmax2 = ndc[0];
+      for (int j = 1; j < K; ++j) nmax2 = fmax(nmax2, ndc[j]);
     }
-    SVAE_PHASE(j, K) {
-      double acc[32];                      // fixed trip counts keep it in registers on the device
+    SVAE_BPHASE(t, TH) {
+      const int w = t >> 5, j = t & 31;
+      if (w == 0 && j < K && q + 2 < L) {  // streams in under the product; retired in the reduction phase below
+        SVAE_COPY_ASYNC8(&ndn[j], &node[(size_t)(s + q + 2) * K + j]);
+        SVAE_COPY_COMMIT();
+      }
+      double acc[kHmmRows];                // fixed trip counts keep it in registers on the device
       SVAE_UNROLL
-      for (int i = 0; i < 32; ++i) acc[i] = 0.0;
-      for (int k = 0; k < K; ++k) {
-        const double a = A[k * 32 + j] * inv;
-        const double* row = cur + k * kHmmRow;
-        SVAE_UNROLL
-        for (int i = 0; i < 32; ++i) acc[i] = fma(row[i], a, acc[i]);   // straight-line: the padding rows are zeros
+      for (int ii = 0; ii < kHmmRows; ++ii) acc[ii] = 0.0;
+      if (j < K) {
+        for (int k = 0; k < K; ++k) {
+          const double a = A[k * 32 + j] * inv;
+          const double* row = cur + k * kHmmRow + w * kHmmRows;
+          SVAE_UNROLL
+          for (int ii = 0; ii < kHmmRows; ++ii) acc[ii] = fma(row[ii], a, acc[ii]);   // padding rows are zeros
+        }
       }
       double m = 0.0;
-      const double dj = more ? exp(nd[j] - nmax2) : 1.0;
+      const double dj = (j < K) ? (more ? exp(ndc[j] - nmax2) : 1.0) : 0.0;
       SVAE_UNROLL
-      for (int i = 0; i < 32; ++i) {
-        m = fmax(m, acc[i]);
-        nxt[j * kHmmRow + i] = acc[i] * dj;   // row j of the next (P D)^T (or of P^T after the last step)
+      for (int ii = 0; ii < kHmmRows; ++ii) {
+        m = fmax(m, acc[ii]);
+        nxt[j * kHmmRow + w * kHmmRows + ii] = acc[ii] * dj;   // row j of the next (P D)^T (or of P^T after the last step)
       }
+      tmax[t] = m;
+    } SVAE_BPHASE_END
+    SVAE_BPHASE(j, 32) {
+      double m = tmax[j];
+      SVAE_UNROLL
+      for (int w = 1; w < kHmmWarps; ++w) m = fmax(m, tmax[w * 32 + j]);
       colmax[j] = m;
-    } SVAE_PHASE_END
+      SVAE_COPY_WAIT_ALL();
+    } SVAE_BPHASE_END
     double pmax = colmax[0];
-    for (int j = 1; j < K; ++j) pmax = fmax(pmax, colmax[j]);
+    for (int j = 1; j < 32; ++j) pmax = fmax(pmax, colmax[j]);
     inv = 1.0 / pmax;
     logscale += log(pmax) + (more ? nmax2 : 0.0);
-    if (q + 2 < L) {
-      SVAE_PHASE(j, K) { nd[j] = node[(size_t)(s + q + 2) * K + j]; } SVAE_PHASE_END
-    }
   }
   const double* fin = (L & 1) ? PDt1 : PDt0;
-  SVAE_PHASE(j, K) {
+  SVAE_BPHASE(j, K) {
     for (int i = 0; i < K; ++i) out_P[i * K + j] = fin[j * kHmmRow + i] * inv;
     if (j == 0) *out_logscale = logscale;
-  } SVAE_PHASE_END
+  } SVAE_BPHASE_END
 }
 
 // chain tile: two K x K matrix buffers (row stride 33: column reads of the forward sweep and row reads of the backward
@@ -154,12 +183,24 @@ SVAE_HD void hmm_chain_messages(double* mem, int K, int C, const double* log_pi,
         for (int i = 0; i < K; ++i) SVAE_COPY_ASYNC8(&nxt[i * kChainRow + j], &Pn[(size_t)i * K + j]);
         SVAE_COPY_COMMIT();
       }
-      double acc = 0.0;
-      for (int i = 0; i < K; ++i) acc = fma(a[i], cur[i * kChainRow + j], acc);
-      tmp[j] = acc;
+      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;   // four chains: the step is latency-, not throughput-bound
+      int i = 0;
+      for (; i + 3 < K; i += 4) {
+        p0 = fma(a[i], cur[i * kChainRow + j], p0);
+        p1 = fma(a[i + 1], cur[(i + 1) * kChainRow + j], p1);
+        p2 = fma(a[i + 2], cur[(i + 2) * kChainRow + j], p2);
+        p3 = fma(a[i + 3], cur[(i + 3) * kChainRow + j], p3);
+      }
+      for (; i < K; ++i) p0 = fma(a[i], cur[i * kChainRow + j], p0);
+      tmp[j] = (p0 + p1) + (p2 + p3);
     } SVAE_PHASE_END
-    sum = 0.0;
-    for (int j = 0; j < K; ++j) sum += tmp[j];
+    {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int j = 0;
+      for (; j + 3 < K; j += 4) { s0 += tmp[j]; s1 += tmp[j + 1]; s2 += tmp[j + 2]; s3 += tmp[j + 3]; }
+      for (; j < K; ++j) s0 += tmp[j];
+      sum = (s0 + s1) + (s2 + s3);
+    }
     logZ += ls_cur + log(sum);
     ls_cur = ls_next;
     SVAE_PHASE(j, K) {
@@ -192,9 +233,16 @@ SVAE_HD void hmm_chain_messages(double* mem, int K, int C, const double* log_pi,
         for (int r = 0; r < K; ++r) SVAE_COPY_ASYNC8(&nxt[r * kChainRow + i], &Pn[(size_t)r * K + i]);
         SVAE_COPY_COMMIT();
       }
-      double acc = 0.0;
-      for (int j = 0; j < K; ++j) acc = fma(cur[i * kChainRow + j], b[j], acc);
-      tmp[i] = acc;
+      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+      int j = 0;
+      for (; j + 3 < K; j += 4) {
+        p0 = fma(cur[i * kChainRow + j], b[j], p0);
+        p1 = fma(cur[i * kChainRow + j + 1], b[j + 1], p1);
+        p2 = fma(cur[i * kChainRow + j + 2], b[j + 2], p2);
+        p3 = fma(cur[i * kChainRow + j + 3], b[j + 3], p3);
+      }
+      for (; j < K; ++j) p0 = fma(cur[i * kChainRow + j], b[j], p0);
+      tmp[i] = (p0 + p1) + (p2 + p3);
     } SVAE_PHASE_END
     m = tmp[0];
     for (int j = 1; j < K; ++j) m = fmax(m, tmp[j]);

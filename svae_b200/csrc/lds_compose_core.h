@@ -34,6 +34,16 @@
 #define SVAE_PHASE_END }
 #endif
 
+// Block-wide phases (one CTA of `threads` threads per tile, __syncthreads around each phase): same discipline, for
+// tiles whose per-step work is worth more than one warp scheduler.
+#if defined(__CUDA_ARCH__)
+#define SVAE_BPHASE(t, threads) { __syncthreads(); const int t = (int)threadIdx.x; if (t < (threads))
+#define SVAE_BPHASE_END __syncthreads(); }
+#else
+#define SVAE_BPHASE(t, threads) { for (int t = 0; t < (threads); ++t)
+#define SVAE_BPHASE_END }
+#endif
+
 // Asynchronous global -> tile copies (prefetch of the next step's operands while this step computes): cp.async on the
 // device, a plain copy on the host.  A thread waits for its own copies; the phase barrier publishes them to the warp.
 #if defined(__CUDA_ARCH__)

@@ -17,8 +17,10 @@
 
 #if defined(__CUDACC__)
 #define SVAE_UNROLL _Pragma("unroll")
+#define SVAE_UNROLL4 _Pragma("unroll 4")
 #else
 #define SVAE_UNROLL
+#define SVAE_UNROLL4
 #endif
 
 namespace svae {
@@ -98,6 +100,7 @@ SVAE_HD void hmm_compose_chunk(double* mem, int K, int s, int L, const double* l
       SVAE_UNROLL
       for (int ii = 0; ii < kHmmRows; ++ii) acc[ii] = 0.0;
       if (j < K) {
+        SVAE_UNROLL4                       // overlap the next rows' loads with this row's multiply-adds
         for (int k = 0; k < K; ++k) {
           const double a = A[k * 32 + j] * inv;
           const double* row = cur + k * kHmmRow + w * kHmmRows;

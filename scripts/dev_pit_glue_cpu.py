@@ -31,7 +31,7 @@ def fake_forward(init_params, pair_params, node_params, num_samples=1, eps=None,
     iJ, ih = N(T64(init_params[0])), N(T64(init_params[1]))
     ilZ = float(sum(init_params[2:])) if len(init_params) > 2 and iJ.ndim == 2 else 0.
     pair = tuple(N(T64(x)) for x in pair_params)
-    out = dict(B=B, T=T, n=n, S=S, batched=True)
+    out = dict(B=B, T=T, n=n, S=S, batched=True, status=torch.zeros(1, dtype=torch.int32))
     keys = ["lognorm", "E_node_xx", "E_node_x", "samples", "E_init_xx", "E_init_x", "E_pair_xx", "E_pair_xxn", "E_pair_xnxn",
             "Exx_t", "Exxn_t", "J_pred", "h_pred"]
     acc = {k: [] for k in keys}

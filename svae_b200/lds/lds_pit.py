@@ -51,6 +51,7 @@ def compose_chunks(pair_params, node_params, chunk_len):
                                      P(cJ11), P(cJ12), P(cJ22), P(clogZ), P(e1), P(e2),
                                      ctypes.c_void_p(status.data_ptr()), _lib.stream_ptr(device))
     _lib.check(code, "svae_lds_compose_chunks")
+    compose_chunks.last_status = status          # device word: 1 + first sequence with a non-positive pivot
     return (cJ11, cJ12, cJ22, clogZ), e1, e2
 
 
@@ -69,9 +70,12 @@ def _affine_suffix_scan(A, d):
     return d
 
 
-def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=None, chunk_len=None, generator=None):
+def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=None, chunk_len=None, generator=None,
+                                   check_status=False):
     """(samples, (E_init_stats, E_pair_stats, E_node_stats), lognorm): the contract of natural_lds_inference_general
-    (svae/lds/lds_inference.py:185-202), computed chunk-parallel.  chunk_len defaults to ~sqrt(T)."""
+    (svae/lds/lds_inference.py:185-202), computed chunk-parallel.  chunk_len defaults to ~sqrt(T).
+    check_status: synchronise and raise FloatingPointError if any stage met a non-positive-definite pivot (the
+    reference's asserts, svae/lds/gaussian.py:48,64)."""
     init_params, pair_params = natparam
     if any(torch.is_tensor(x) and x.requires_grad for x in node_params) and torch.is_grad_enabled():
         raise RuntimeError("natural_lds_inference_parallel is forward-only; use natural_lds_inference_general for gradients")
@@ -126,7 +130,7 @@ def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=Non
     hp[:, 1:] += e2                          # eta2 of chunk c-1 rode as node potential of boundary c
     mu = chain["E_node_x"]
     Sig = chain["Exx_t"] - mu[..., :, None] * mu[..., None, :]
-    Js = torch.linalg.inv(Sig[:, 1:])
+    Js = torch.linalg.inv_ex(Sig[:, 1:])[0]        # _ex: no host sync, no exception on a failed sequence
     Js = 0.5 * (Js + Js.transpose(-1, -2))
     tJ = -0.5 * Js - Jp[:, 1:]               # terminal node potential of chunk c: smoothed / predicted at its end
     th = torch.einsum('bcij,bcj->bci', Js, mu[:, 1:]) - hp[:, 1:]
@@ -142,7 +146,7 @@ def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=Non
     x_start = torch.empty((B, C, S, n), **f64) if S else None       # kernel paths at the chunk ends, and G_{s->e}
     x_end = torch.empty((B, C, S, n), **f64) if S else None
     R_start = torch.empty((B, C, n, n), **f64) if S else None
-    per_group = []
+    per_group, statuses = [], []
     for c0, cnt, L in groups:
         Q = B * cnt
         t0, t1 = c0 * Lc, c0 * Lc + cnt * L
@@ -190,12 +194,13 @@ def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=Non
                 cols.append(ps[..., 1:, :] - ps[..., :1, :])
                 done += k
             D = torch.cat(cols, -2).transpose(-1, -2)                      # (B,cnt,L+1,n,n): column j = probe j
-            Rt = D @ torch.linalg.inv(D[:, :, L])[:, :, None]              # G_{t->e}
+            Rt = D @ torch.linalg.inv_ex(D[:, :, L])[0][:, :, None]              # G_{t->e}
             x_start[:, c0:c0 + cnt], x_end[:, c0:c0 + cnt] = xk[:, :, 0], xk[:, :, L]
             R_start[:, c0:c0 + cnt] = Rt[:, :, 0]
         else:
             o = K.lds_estep_forward(sub_init, sub_pair, sub_node, 0, None, term_J=sub_term, per_t_pair_stats=not homog)
             xk = Rt = None
+        statuses.append(o["status"])
         if homog:
             for k, key in enumerate(("E_pair_xx", "E_pair_xxn", "E_pair_xnxn")):
                 E_pair[k] += o[key].reshape(B, cnt, n, n).sum(1)
@@ -226,6 +231,10 @@ def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=Non
             if t1 == T - 1:
                 samples[:, -1] = fixed[:, -1, L]
 
+    if check_status:
+        bad = int(compose_chunks.last_status.item()) or int(chain["status"].item()) or max(int(x.item()) for x in statuses)
+        if bad:
+            raise FloatingPointError("parallel-in-time LDS E-step: non-positive-definite pivot (stage-local sequence %d)" % (bad - 1))
     o = dict(B=B, T=T, n=n, S=S, batched=batched, lognorm=lognorm, samples=samples, E_node_xx=E_node_xx, E_node_x=E_node_x,
              E_init_xx=E_init[0], E_init_x=E_init[1], E_pair_xx=E_pair[0], E_pair_xxn=E_pair[1], E_pair_xnxn=E_pair[2],
              Exx_t=Exx_t, Exxn_t=Exxn_t)

@@ -123,3 +123,13 @@ def test_time_inhomogeneous_pair_parameters(per_seq, n, T, B, S, Lc):
         assert rel_err(c(E_init[k]), cat(lambda w: w[1][0][k])) < RTOL
     if S:
         assert rel_err(c(samples), cat(lambda w: w[0])) < 1e-8
+
+
+def test_non_positive_definite_is_reported():
+    from svae_b200.lds import lds_pit
+    n, T, B = 4, 40, 3
+    init, pair, node, eps = _problem(n, T, B, 1, 9)
+    bad = node[0].copy(); bad[1, 17] = +50.0              # a large negative precision in one sequence
+    with pytest.raises(FloatingPointError):
+        lds_pit.natural_lds_inference_parallel((_g(init), _g(pair)), (_gpu(bad), _gpu(node[1])), 0, chunk_len=6, check_status=True)
+    lds_pit.natural_lds_inference_parallel((_g(init), _g(pair)), _g(node), 0, chunk_len=6, check_status=True)   # clean: no raise

@@ -7,7 +7,8 @@ Same contract and numbers as hmm_estep (svae/hmm/hmm_inference.py:21-41), from t
   3. svae_hmm_estep on all B x C chunks as independent sequences: forward message added to the chunk's first node
      potential, backward message in place of its last one, log pi = 0 -- so every chunk's forward-backward returns
      the exact posterior marginals and expected transition counts of its steps.
-Forward values only.
+hmm_logZ_parallel is differentiable: the VJP of logZ IS the E-step (cython_hmm_inference.pyx:126-166), which the
+same three launches return.
 """
 from __future__ import annotations
 import math
@@ -56,3 +57,27 @@ def hmm_estep_parallel(natparam, chunk_len=None):
     if not batched:
         return logZ[0], (Ez0[0], Etrans[0], Ez[0])
     return logZ, (Ez0, Etrans, Ez)
+
+
+class _HmmLogZParallelFn(torch.autograd.Function):
+    """logZ with the reference's VJP, g * (E[z_0], E[trans], E[z_t]) (cython_hmm_inference.pyx:126-166), both
+    computed chunk-parallel."""
+
+    @staticmethod
+    def forward(ctx, lp, lA, node, chunk_len):
+        logZ, (Ez0, Etrans, Ez) = hmm_estep_parallel((lp, lA, node), chunk_len)
+        ctx.save_for_backward(Ez0, Etrans, Ez)
+        return logZ
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        Ez0, Etrans, Ez = ctx.saved_tensors
+        return (g[:, None] * Ez0).sum(0), (g[:, None, None] * Etrans).sum(0), g[:, None, None] * Ez, None
+
+
+def hmm_logZ_parallel(natparam, chunk_len=None):
+    """hmm_logZ (svae/hmm/hmm_inference.py:12-18, 44-51) for few long sequences; differentiable in all three params."""
+    lp, lA, node, batched, _ = H._canon(natparam)
+    logZ = _HmmLogZParallelFn.apply(lp, lA, node, chunk_len)
+    return logZ if batched else logZ[0]

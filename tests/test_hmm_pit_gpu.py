@@ -40,3 +40,19 @@ def test_long_sequence_against_the_sequential_kernel_and_unbatched():
     c = lambda x: x.cpu().numpy()
     assert rel_err(c(b_logZ), c(a_logZ)) < 1e-11
     assert rel_err(c(bz), c(az)) < 1e-8 and rel_err(c(bt), c(at)) < 1e-8 and rel_err(c(b0), c(a0)) < 1e-8
+
+
+def test_logZ_parallel_is_differentiable():
+    """VJP of logZ = E-step statistics, against the sequential kernel's autograd path."""
+    from svae_b200.hmm import hmm_pit, hmm_inference as H
+    rng = np.random.default_rng(2)
+    K, T, B = 6, 90, 3
+    lp, lA = HO.rand_hmm_natparam(K, rng)
+    w = _gpu(rng.standard_normal(B))
+    grads = []
+    for fn in (H.hmm_logZ, lambda nat: hmm_pit.hmm_logZ_parallel(nat, chunk_len=8)):
+        nat = tuple(_gpu(x).requires_grad_(True) for x in (lp, lA, rng.standard_normal((B, T, K)) * 0 + 1.5 * np.sin(np.arange(B * T * K).reshape(B, T, K))))
+        (fn(nat) * w).sum().backward()
+        grads.append([x.grad.cpu().numpy() for x in nat])
+    for a, b in zip(*grads):
+        assert rel_err(b, a) < 1e-9

@@ -65,7 +65,7 @@ namespace svae {
 // with immediates instead of an integer multiply per access
 SVAE_HD int compose_np(int /*n*/) { return 16; }
 // doubles of tile memory one chunk needs
-SVAE_HD int compose_tile_doubles(int n) { const int NP = compose_np(n); return 9 * n * NP + 8 * NP; }
+SVAE_HD int compose_tile_doubles(int n) { const int NP = compose_np(n); return 9 * n * NP + 4 * NP; }
 #if defined(__CUDACC__)
 #define SVAE_UNROLL _Pragma("unroll")
 #else
@@ -77,7 +77,7 @@ struct ComposeTile {
   double *M, *R, *W;          // elimination workspace: M | J12 | L12'
   double *L11, *L12T, *L22;   // running element (L12T = L12 transposed)
   double *J11, *J12, *J22;    // pair potential, information form
-  double *e1, *e2, *u, *mult, *dinv, *nJ, *nh, *acc;   // vectors (NP each)
+  double *e1, *e2, *u, *dinv;   // vectors (NP each)
 };
 
 SVAE_HD ComposeTile compose_tile(double* mem, int n) {
@@ -86,8 +86,7 @@ SVAE_HD ComposeTile compose_tile(double* mem, int n) {
   t.M = mem; t.R = mem + MM; t.W = mem + 2 * MM; t.L11 = mem + 3 * MM; t.L12T = mem + 4 * MM; t.L22 = mem + 5 * MM;
   t.J11 = mem + 6 * MM; t.J12 = mem + 7 * MM; t.J22 = mem + 8 * MM;
   double* v = mem + 9 * MM;
-  t.e1 = v; t.e2 = v + NP; t.u = v + 2 * NP; t.mult = v + 3 * NP; t.dinv = v + 4 * NP; t.nJ = v + 5 * NP; t.nh = v + 6 * NP;
-  t.acc = v + 7 * NP;
+  t.e1 = v; t.e2 = v + NP; t.u = v + 2 * NP; t.dinv = v + 3 * NP;
   return t;
 }
 

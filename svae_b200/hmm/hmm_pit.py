@@ -15,13 +15,14 @@ import math
 import torch
 from .. import _lib
 from . import hmm_inference as H
+from ..lds.lds_pit import default_chunk_len
 
 
 def hmm_estep_parallel(natparam, chunk_len=None):
     """(logZ, (E[z_0], E[transition counts], E[z_t]))."""
     lp, lA, node, batched, dev = H._canon(natparam)
     B, T, K = node.shape
-    Lc = int(chunk_len) if chunk_len else max(2, int(round(math.sqrt(max(T - 1, 1)))))
+    Lc = int(chunk_len) if chunk_len else default_chunk_len(T)
     if T < 4 or Lc >= T - 1:
         return H.hmm_estep(natparam)
     L = _lib.lib()

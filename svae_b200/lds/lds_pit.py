@@ -55,16 +55,28 @@ def compose_chunks(pair_params, node_params, chunk_len):
     return (cJ11, cJ12, cJ22, clogZ), e1, e2
 
 
+def default_chunk_len(T):
+    """~sqrt(T-1), nudged to a divisor of T-1 when one is within a factor 1.5: no ragged tail chunk means one launch
+    group instead of two (the driver's cost at moderate T is its launch count)."""
+    target = max(2, int(round(math.sqrt(max(T - 1, 1)))))
+    best = None
+    for L in range(max(2, int(target / 1.5)), int(target * 1.5) + 1):
+        if (T - 1) % L == 0 and (best is None or abs(L - target) < abs(best - target)):
+            best = L
+    return best or target
+
+
 def _affine_suffix_scan(A, d):
     """delta_c = d_c + A_c delta_{c+1}, delta beyond the end = 0.  A (B,C,n,n), d (B,C,S,n) -> delta (B,C,S,n).
     Hillis-Steele doubling over the chunk axis: ceil(log2 C) rounds of batched products."""
     C = A.shape[1]
-    A, d = A.clone(), d.clone()
     k = 1
+    pad = torch.nn.functional.pad
     while k < C:
-        d_sh = torch.zeros_like(d); d_sh[:, :C - k] = d[:, k:]
-        A_sh = torch.zeros_like(A); A_sh[:, :C - k] = A[:, k:]
-        d = d + torch.einsum('bcij,bcsj->bcsi', A, d_sh)
+        d_sh = pad(d[:, k:], (0, 0, 0, 0, 0, k))           # shift along the chunk axis, zeros beyond the end
+        A_sh = pad(A[:, k:], (0, 0, 0, 0, 0, k))
+        d = torch.baddbmm(d.reshape(-1, d.shape[2], d.shape[3]), d_sh.reshape(-1, d.shape[2], d.shape[3]),
+                          A.reshape(-1, A.shape[2], A.shape[3]).transpose(1, 2)).reshape(d.shape)
         A = A @ A_sh
         k *= 2
     return d
@@ -85,7 +97,7 @@ def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=Non
         raise ValueError("parallel-in-time driver: diagonal node potentials only")
     B, T, n = nh.shape
     S = int(num_samples) if num_samples else 0
-    Lc = int(chunk_len) if chunk_len else max(2, int(round(math.sqrt(max(T - 1, 1)))))
+    Lc = int(chunk_len) if chunk_len else default_chunk_len(T)
     if T < 4 or Lc >= T - 1:
         return K.natural_lds_inference_general(natparam, node_params, num_samples, eps, generator)
     if S > 0:

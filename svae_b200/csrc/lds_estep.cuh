@@ -513,8 +513,8 @@ __global__ void SVAE_LDS_BOUNDS(N, CPL) lds_estep_fwd_kernel(const LdsFwdParams 
         if (!INHOMOG) {
           konst += (double)(T - 1) * p.pair_logZ[0];
         } else {
-          for (int t = 0; t < T - 1; ++t)
-            konst += p.pair_logZ[((size_t)t * p.pair_stride_t + (size_t)b * p.pair_stride_b) / NN];
+          const size_t lz0 = (size_t)b * p.pair_stride_b / NN, lzs = (size_t)p.pair_stride_t / NN;   // strides are multiples of NN
+          for (int t = 0; t < T - 1; ++t) konst += p.pair_logZ[lz0 + (size_t)t * lzs];
         }
       }
       if (p.node_logZ)

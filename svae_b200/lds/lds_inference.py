@@ -143,7 +143,7 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
             new(B, n, n, name="E_pair_xx"), new(B, n, n, name="E_pair_xxn"), new(B, n, n, name="E_pair_xnxn")
     if per_t_pair_stats or dense:
         out["Exx_t"] = new(B, T, n, n)
-    if per_t_pair_stats:
+    if per_t_pair_stats and per_t_pair_stats != "xx":     # "xx": the per-time second moments alone (boundary chain)
         out["Exxn_t"] = new(B, max(T - 1, 0), n, n)
     if messages_out:
         out["J_pred"], out["h_pred"] = new(B, T, n, n), new(B, T, n)

@@ -135,7 +135,7 @@ def natural_lds_inference_parallel(natparam, node_params, num_samples=1, eps=Non
     clZ = torch.zeros((B, C + 1), **f64)
     if nlogZ is not None:
         clZ[:, -1] = nlogZ[:, -1]
-    chain = K.lds_estep_forward(init_params, cpair, (cJ, ch, clZ), 0, None, per_t_pair_stats=True, want_stats=False,
+    chain = K.lds_estep_forward(init_params, cpair, (cJ, ch, clZ), 0, None, per_t_pair_stats="xx", want_stats=False,
                                 messages_out=True)
     lognorm = chain["lognorm"]
     Jp, hp = chain["J_pred"], chain["h_pred"].clone()

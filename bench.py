@@ -189,7 +189,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from oracle import lds_numpy as O          # synthetic-problem recipe only (host side, untimed)
+    from svae_b200 import synthetic as SY      # synthetic-problem recipe (host side, untimed); no oracle on this arm
     from svae_b200.lds import lds_inference as K
     from svae_b200 import _lib
 
@@ -203,7 +203,7 @@ def run_ours(args):
     n, T, B, S = D, T_LEN, BATCH, NUM_SAMPLES
 
     rng = np.random.default_rng(0)
-    init, pair = O.rand_lds_natparam(n, rng)
+    init, pair = SY.lds_natparam(n, rng)
     g = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float64, device=dev)
     gi, gp = tuple(g(x) for x in init), tuple(g(x) for x in pair)
     gen = torch.Generator(device=dev); gen.manual_seed(1000 + rank)
@@ -311,8 +311,7 @@ def run_ours(args):
             b_.record(); torch.cuda.synchronize()
             extra["lds_estep_fwd_plus_vjp_seq_per_s"] = B / (a.elapsed_time(b_) / 5 * 1e-3)
             from svae_b200.hmm import hmm_inference as HK
-            from oracle import hmm_numpy as HO
-            lp, lA = HO.rand_hmm_natparam(32, rng)
+            lp, lA = SY.hmm_natparam(32, rng)
             hnode = torch.randn(2048, 500, 32, dtype=torch.float64, device=dev, generator=gen)
             nat = (g(lp), g(lA), hnode)
             for _ in range(2):
@@ -325,7 +324,7 @@ def run_ours(args):
             extra["hmm_estep_K32_T500_B2048_seq_per_s"] = 2048 / (a.elapsed_time(b_) / 5 * 1e-3)
             # the other LDS shapes BASELINE.json lists (parity-test cases; reported for context only)
             for (n2, T2, B2) in ((8, 50, 256), (16, 200, 4096)):
-                i2, p2 = O.rand_lds_natparam(n2, rng)
+                i2, p2 = SY.lds_natparam(n2, rng)
                 gi2, gp2 = tuple(g(x) for x in i2), tuple(g(x) for x in p2)
                 J2 = -0.5 * torch.nn.functional.softplus(torch.randn(B2, T2, n2, dtype=torch.float64, device=dev, generator=gen))
                 h2 = torch.randn(B2, T2, n2, dtype=torch.float64, device=dev, generator=gen)

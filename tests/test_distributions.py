@@ -76,3 +76,17 @@ def test_mniw_expectedstats_is_grad_logZ(n):
 def test_categorical():
     nat = torch.randn(5, 4, dtype=t64)
     assert torch.allclose(categorical.expectedstats(nat), grad_logZ(categorical.logZ, nat)[0])
+
+
+def test_synthetic_recipe_matches_the_oracles():
+    """svae_b200/synthetic.py (benchmark inputs) draws exactly what the oracle's recipe draws."""
+    import numpy as np
+    from svae_b200 import synthetic as S
+    from oracle import lds_numpy as O, hmm_numpy as HO
+    a, b = S.lds_natparam(7, np.random.default_rng(3)), O.rand_lds_natparam(7, np.random.default_rng(3))
+    for x, y in zip(a[0] + a[1], b[0] + b[1]):
+        assert np.allclose(x, y, rtol=1e-13, atol=0)
+    for x, y in zip(S.node_potentials(2, 5, 3, np.random.default_rng(1)), O.rand_node_potentials(2, 5, 3, np.random.default_rng(1))):
+        assert np.array_equal(x, y)
+    for x, y in zip(S.hmm_natparam(4, np.random.default_rng(2)), HO.rand_hmm_natparam(4, np.random.default_rng(2))):
+        assert np.array_equal(x, y)

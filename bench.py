@@ -261,6 +261,9 @@ def run_ours(args):
     value = world * B / (ms_per_step * 1e-3)
 
     # ---- end-to-end through the public API with HOST buffers ------------------------------------
+    # piece sizes of the host pipeline: small first piece so the device-to-host stream (the bound) starts early;
+    # swept on a B200 in scripts/e2e_probe.py (profiles/r01_e2e_chunk_sweep.txt)
+    E2E_CHUNKS = K.ramp_schedule(B, 256, 1.5, 1024)
     h_nJ = sets[0][0].cpu().pin_memory(); h_nh = sets[0][1].cpu().pin_memory()
     out_host = dict(
         samples=torch.empty((B, T, S, n), dtype=torch.float64).pin_memory(),
@@ -270,7 +273,7 @@ def run_ours(args):
     acc_host = torch.empty((4 * n * n + n + 1,), dtype=torch.float64).pin_memory()
 
     def e2e_step(i):
-        acc = K.lds_estep_host((gi, gp), (h_nJ, h_nh), S, out_host, chunks=4, generator=gen, device=dev)
+        acc = K.lds_estep_host((gi, gp), (h_nJ, h_nh), S, out_host, chunks=E2E_CHUNKS, generator=gen, device=dev)
         if world > 1:
             dist.all_reduce(acc)
         acc_host.copy_(acc, non_blocking=True)
@@ -397,7 +400,7 @@ def run_ours(args):
                         step="fused filter+smoother+sampler kernel, 2-stage minibatch reduction of the global statistics"
                              + (", NCCL all-reduce of the %d-double accumulator" % (4 * n * n + n + 1) if world > 1 else "")),
             e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                     ms_per_step=e2e_ms, note="pinned host buffers, 4 chunks pipelined over 3 streams, persistent device buffers; noise drawn on device"),
+                     ms_per_step=e2e_ms, note="pinned host buffers; pieces of %s sequences pipelined (one copy stream per direction, kernels on 3 streams), persistent device buffers; noise drawn on device" % (E2E_CHUNKS,)),
             gpu_launches=int(launches),
             clocks=clk.summary(),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,

@@ -222,21 +222,36 @@ class LdsHostPipeline:
     """
 
     def __init__(self, B, T, n, S, chunks=3, device=None):
+        """chunks: an int (equal pieces) or a sequence of piece sizes summing to B.  The pipeline is bound by the
+        device-to-host copy (48 KB per sequence at n=10, T=200 against 32 KB in), which cannot start before the first
+        piece's kernel has finished: a small first piece and growing later ones (ramp_schedule) start it earlier."""
         self.device = device or torch.device("cuda", torch.cuda.current_device())
-        self.B, self.T, self.n, self.S, self.chunks = B, T, n, S, chunks
-        self.bounds = [(B * k) // chunks for k in range(chunks + 1)]
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(min(3, chunks))]
+        if isinstance(chunks, int):
+            sizes = [(B * (k + 1)) // chunks - (B * k) // chunks for k in range(chunks)]
+        else:
+            sizes = [int(x) for x in chunks]
+            if sum(sizes) != B or min(sizes) < 0:
+                raise ValueError("chunk sizes must be non-negative and sum to B")
+        self.B, self.T, self.n, self.S, self.chunks = B, T, n, S, len(sizes)
+        self.bounds = [0]
+        for x in sizes:
+            self.bounds.append(self.bounds[-1] + x)
+        mk = lambda: torch.cuda.Stream(device=self.device)
+        self.s_in, self.s_out = mk(), mk()                 # one copy stream per direction, kernels on rotating streams
+        self.streams = [mk() for _ in range(min(3, len(sizes)))]
+        self.ev_in = [torch.cuda.Event() for _ in sizes]
+        self.ev_done = [torch.cuda.Event() for _ in sizes]
         new = lambda *s: torch.empty(s, dtype=torch.float64, device=self.device)
         L = _lib.lib()
         self.bufs = []
-        for k in range(chunks):
-            b = self.bounds[k + 1] - self.bounds[k]
-            d = dict(J=new(b, T, n), h=new(b, T, n), eps=new(b, T, S, n) if S else None,
-                     lognorm=new(b), E_node_xx=new(b, T, n), E_node_x=new(b, T, n),
-                     samples=new(b, T, S, n) if S else None, E_init_xx=new(b, n, n), E_init_x=new(b, n),
-                     E_pair_xx=new(b, n, n), E_pair_xxn=new(b, n, n), E_pair_xnxn=new(b, n, n),
+        for b in sizes:
+            bb = max(b, 1)
+            d = dict(J=new(bb, T, n), h=new(bb, T, n), eps=new(bb, T, S, n) if S else None,
+                     lognorm=new(bb), E_node_xx=new(bb, T, n), E_node_x=new(bb, T, n),
+                     samples=new(bb, T, S, n) if S else None, E_init_xx=new(bb, n, n), E_init_x=new(bb, n),
+                     E_pair_xx=new(bb, n, n), E_pair_xxn=new(bb, n, n), E_pair_xnxn=new(bb, n, n),
                      status=torch.zeros(1, dtype=torch.int32, device=self.device),
-                     workspace=torch.empty(max(L.svae_lds_estep_workspace_bytes(b, T, n, S, 0), 16), dtype=torch.uint8,
+                     workspace=torch.empty(max(L.svae_lds_estep_workspace_bytes(bb, T, n, S, 0), 16), dtype=torch.uint8,
                                            device=self.device),
                      acc=new(4 * n * n + n + 1),
                      rwork=torch.empty(L.svae_lds_reduce_stats_workspace_bytes(n), dtype=torch.uint8, device=self.device))
@@ -251,30 +266,52 @@ class LdsHostPipeline:
         J_h, h_h = node_host
         cur = torch.cuda.current_stream(self.device)
         S = self.S
-        for k, d in enumerate(self.bufs):
-            lo, hi = self.bounds[k], self.bounds[k + 1]
-            if hi == lo:
-                continue
-            st = self.streams[k % len(self.streams)]
+        self.s_in.wait_stream(cur)
+        self.s_out.wait_stream(cur)
+        for st in self.streams:
             st.wait_stream(cur)
-            with torch.cuda.stream(st):
+        live = [k for k in range(self.chunks) if self.bounds[k + 1] > self.bounds[k]]
+        for k in live:
+            d, lo, hi = self.bufs[k], self.bounds[k], self.bounds[k + 1]
+            with torch.cuda.stream(self.s_in):
                 d["J"].copy_(J_h[lo:hi], non_blocking=True)
                 d["h"].copy_(h_h[lo:hi], non_blocking=True)
+                self.ev_in[k].record(self.s_in)
+            st = self.streams[k % len(self.streams)]
+            st.wait_event(self.ev_in[k])
+            with torch.cuda.stream(st):
                 if S:
                     d["eps"].normal_(generator=generator)
                 o = lds_estep_forward(init_params, pair_params, (d["J"], d["h"]), S, d["eps"], buffers=d)
                 lds_reduce_global_stats(o, out=d["acc"], work=d["rwork"])
+                self.ev_done[k].record(st)
+            self.s_out.wait_event(self.ev_done[k])
+            with torch.cuda.stream(self.s_out):
                 if S:
                     out_host["samples"][lo:hi].copy_(o["samples"], non_blocking=True)
                 out_host["E_node_xx"][lo:hi].copy_(o["E_node_xx"], non_blocking=True)
                 out_host["E_node_x"][lo:hi].copy_(o["E_node_x"], non_blocking=True)
                 out_host["lognorm"][lo:hi].copy_(o["lognorm"], non_blocking=True)
         self.acc.zero_()
-        for k, d in enumerate(self.bufs):
-            if self.bounds[k + 1] > self.bounds[k]:
-                cur.wait_stream(self.streams[k % len(self.streams)])
-                self.acc += d["acc"]
+        cur.wait_stream(self.s_out)
+        for st in self.streams:
+            cur.wait_stream(st)
+        for k in live:
+            self.acc += self.bufs[k]["acc"]
         return self.acc
+
+
+def ramp_schedule(B, first=256, growth=1.5, largest=1024):
+    """Piece sizes first, first*growth, ... capped at `largest`, summing to B (the last piece takes the remainder)."""
+    sizes, x, left = [], float(first), B
+    while left > 0:
+        b = min(left, int(min(x, largest)))
+        if left - b < first // 2:      # do not leave a sliver
+            b = left
+        sizes.append(b)
+        left -= b
+        x *= growth
+    return sizes
 
 
 def lds_estep_host(natparam, node_host, num_samples, out_host, chunks=3, generator=None, device=None, _plans={}):
@@ -282,7 +319,7 @@ def lds_estep_host(natparam, node_host, num_samples, out_host, chunks=3, generat
     B, T, n = node_host[1].shape
     S = int(num_samples) if num_samples else 0
     device = device or torch.device("cuda", torch.cuda.current_device())
-    key = (B, T, n, S, chunks, str(device))
+    key = (B, T, n, S, chunks if isinstance(chunks, int) else tuple(chunks), str(device))
     if key not in _plans:
         _plans[key] = LdsHostPipeline(B, T, n, S, chunks, device)
     return _plans[key].run(natparam, node_host, out_host, generator)

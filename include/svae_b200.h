@@ -235,6 +235,18 @@ int svae_hmm_chain_messages(int B, int C, int K, const double* log_pi, const dou
                             const double* chunk_logscale, const double* node_last, double* log_alpha,
                             double* log_beta, double* logZ, void* stream);
 
+/* Max-plus twins for the most likely state path (svae/hmm/hmm_inference.py:54-63) of few long sequences:
+ *   svae_hmm_compose_chunks_maxplus: chunk_V (B,C,K,K), V(i,j) = best summed log-potential of a path from z_s = i to
+ *       z_{s+L} = j through the chunk (node potentials s .. s+L-1 included);
+ *   svae_hmm_chain_viterbi: max-product recursion over the chunk matrices and back-tracking: boundary_states (B,C+1)
+ *       int32 = the optimal state at every chunk boundary (first maximal index on ties); delta_scratch (B,C+1,K).
+ * Stage 3 is svae_hmm_viterbi on the B*C chunks with both end states pinned by -1e300 penalties.  The phase code of both
+ * is pinned on CPU (tests/test_hmm_pit_cpu.py); their first GPU run is pending (tests/test_hmm_pit_gpu.py, xfail). */
+int svae_hmm_compose_chunks_maxplus(int B, int T, int K, int chunk_len, const double* log_A, const double* node,
+                                    double* chunk_V, void* stream);
+int svae_hmm_chain_viterbi(int B, int C, int K, const double* log_pi, const double* chunk_V,
+                           const double* node_last, double* delta_scratch, int* boundary_states, void* stream);
+
 /* Viterbi path (svae/hmm/hmm_inference.py:54-63, pyhsmm `viterbi`): path (B,T) int32, first maximal
  * index on ties.  workspace: svae_hmm_viterbi_workspace_bytes() bytes of device scratch (back-pointers). */
 size_t svae_hmm_viterbi_workspace_bytes(int B, int T, int K);

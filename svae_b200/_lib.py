@@ -37,6 +37,8 @@ _SIGNATURES = {
     "svae_lds_compose_num_chunks": (_I, [_I, _I]),
     "svae_hmm_compose_chunks": (_I, [_I] * 4 + [_P] * 4 + [_P]),
     "svae_hmm_chain_messages": (_I, [_I] * 3 + [_P] * 7 + [_P]),
+    "svae_hmm_compose_chunks_maxplus": (_I, [_I] * 4 + [_P] * 3 + [_P]),
+    "svae_hmm_chain_viterbi": (_I, [_I] * 3 + [_P] * 5 + [_P]),
     "svae_lds_compose_chunks": (_I, [_I] * 4 + [_P] * 4 + [_LL, _LL] + [_P] * 9 + [_P, _P]),
     "svae_lds_estep_bwd_ex": (_I, [_I] * 5 + [_P] * 17 + [_P, _SZ, _P]),
     "svae_lds_estep_bwd": (_I, [_I] * 5 + [_P] * 16 + [_P, _SZ, _P]),

@@ -258,3 +258,110 @@ SVAE_HD void hmm_chain_messages(double* mem, int K, int C, const double* log_pi,
 }
 
 }  // namespace svae
+
+// ---------------------------------------------------------------------------------------------------------------
+// Max-plus twins of the two stages above, for the most likely state path (svae/hmm/hmm_inference.py:54-63):
+// the chunk element is V(i, j) = max over interior paths of the summed log-potentials from z_s = i to z_{s+L} = j
+// (node potentials s .. s+L-1 included), the boundary chain runs the max-product recursion over the chunk matrices
+// and back-tracks the optimal state at every chunk boundary.  Stage 3 is svae_hmm_viterbi on all chunks with both end
+// states pinned (svae_b200/hmm/hmm_pit.py).  Validated on CPU through the host build (tests/test_hmm_pit_cpu.py).
+// ---------------------------------------------------------------------------------------------------------------
+namespace svae {
+
+constexpr double kHmmNever = -1e300;   // "impossible", finite so that sums of two of them stay finite
+
+SVAE_HD int hmm_maxplus_tile_doubles(int /*K*/) { return 32 * 32 + 2 * 32 * kHmmRow + 32; }
+
+SVAE_HD void hmm_compose_chunk_maxplus(double* mem, int K, int s, int L, const double* log_A, const double* node,
+                                       double* out_V) {
+  constexpr int TH = 32 * kHmmWarps;
+  double* A = mem;                       // log A, element (k, j) at [k*32 + j]
+  double* Vt0 = mem + 32 * 32;           // V transposed, row k = column k of V, contiguous in i
+  double* Vt1 = Vt0 + 32 * kHmmRow;
+  double* nd = Vt1 + 32 * kHmmRow;       // node potentials of the current step
+  SVAE_BPHASE(t, TH) {
+    const int w = t >> 5, j = t & 31;
+    if (w == 0 && j < K) {
+      for (int k = 0; k < K; ++k) A[k * 32 + j] = log_A[k * K + j];
+      nd[j] = node[(size_t)s * K + j];
+    }
+    SVAE_UNROLL
+    for (int ii = 0; ii < kHmmRows; ++ii) {
+      const int i = w * kHmmRows + ii;
+      Vt0[j * kHmmRow + i] = (i == j && j < K) ? 0.0 : kHmmNever;   // max-plus identity
+      Vt1[j * kHmmRow + i] = kHmmNever;
+    }
+  } SVAE_BPHASE_END
+  for (int q = 0; q < L; ++q) {
+    const double* cur = (q & 1) ? Vt1 : Vt0;
+    double* nxt = (q & 1) ? Vt0 : Vt1;
+    SVAE_BPHASE(t, TH) {
+      const int w = t >> 5, j = t & 31;
+      double acc[kHmmRows];
+      SVAE_UNROLL
+      for (int ii = 0; ii < kHmmRows; ++ii) acc[ii] = kHmmNever;
+      if (j < K) {
+        SVAE_UNROLL4
+        for (int k = 0; k < K; ++k) {
+          const double a = nd[k] + A[k * 32 + j];          // leave state k at this step, enter j at the next
+          const double* row = cur + k * kHmmRow + w * kHmmRows;
+          SVAE_UNROLL
+          for (int ii = 0; ii < kHmmRows; ++ii) acc[ii] = fmax(acc[ii], row[ii] + a);
+        }
+      }
+      SVAE_UNROLL
+      for (int ii = 0; ii < kHmmRows; ++ii) nxt[j * kHmmRow + w * kHmmRows + ii] = acc[ii];
+    } SVAE_BPHASE_END
+    if (q + 1 < L) {
+      SVAE_BPHASE(j, K) { nd[j] = node[(size_t)(s + q + 1) * K + j]; } SVAE_BPHASE_END
+    }
+  }
+  const double* fin = (L & 1) ? Vt1 : Vt0;
+  SVAE_BPHASE(j, K) {
+    for (int i = 0; i < K; ++i) out_V[i * K + j] = fin[j * kHmmRow + i];
+  } SVAE_BPHASE_END
+}
+
+SVAE_HD int hmm_chain_viterbi_tile_doubles(int /*K*/) { return 3 * 32; }
+
+// Boundary chain, max-product: delta (C+1, K) scratch receives the forward max-messages (delta[c][j] = best score of
+// any path ending in z_{s_c} = j, node potential at s_c excluded); zb (C+1) receives the optimal boundary states
+// (first maximal index on ties, like numpy.argmax).
+SVAE_HD void hmm_chain_viterbi(double* mem, int K, int C, const double* log_pi, const double* V, const double* node_last,
+                               double* delta, int* zb) {
+  double* a = mem;
+  double* cand = mem + 32;
+  double* tmp = mem + 64;
+  SVAE_PHASE(j, K) {
+    a[j] = log_pi[j];
+    delta[j] = a[j];
+  } SVAE_PHASE_END
+  for (int c = 0; c < C; ++c) {
+    const double* Vc = V + (size_t)c * K * K;
+    SVAE_PHASE(j, K) {
+      double m = kHmmNever * 4.0;
+      for (int i = 0; i < K; ++i) m = fmax(m, a[i] + Vc[i * K + j]);
+      tmp[j] = m;
+    } SVAE_PHASE_END
+    SVAE_PHASE(j, K) {
+      a[j] = tmp[j];
+      delta[(size_t)(c + 1) * K + j] = tmp[j];
+    } SVAE_PHASE_END
+  }
+  SVAE_PHASE(j, K) { cand[j] = a[j] + node_last[j]; } SVAE_PHASE_END
+  int z = 0;
+  for (int j = 1; j < K; ++j)
+    if (cand[j] > cand[z]) z = j;
+  SVAE_PHASE(j, 1) { zb[C] = z; } SVAE_PHASE_END
+  for (int c = C - 1; c >= 0; --c) {
+    const double* Vc = V + (size_t)c * K * K;
+    SVAE_PHASE(i, K) { cand[i] = delta[(size_t)c * K + i] + Vc[i * K + z]; } SVAE_PHASE_END
+    int zi = 0;
+    for (int i = 1; i < K; ++i)
+      if (cand[i] > cand[zi]) zi = i;
+    z = zi;
+    SVAE_PHASE(j, 1) { zb[c] = z; } SVAE_PHASE_END
+  }
+}
+
+}  // namespace svae

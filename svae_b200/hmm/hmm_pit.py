@@ -82,3 +82,44 @@ def hmm_logZ_parallel(natparam, chunk_len=None):
     lp, lA, node, batched, _ = H._canon(natparam)
     logZ = _HmmLogZParallelFn.apply(lp, lA, node, chunk_len)
     return logZ if batched else logZ[0]
+
+
+def hmm_viterbi_parallel(natparam, chunk_len=None):
+    """hmm_viterbi (svae/hmm/hmm_inference.py:54-63) for few long sequences: max-plus chunk matrices, back-tracked
+    boundary states, then the ordinary Viterbi kernel on every chunk with both end states pinned.  The optimal path is
+    unique for tie-free potentials, so the result equals the sequential one.
+    NOTE: stages 1-2 are validated on CPU through the host build of their phase code; first GPU run pending."""
+    lp, lA, node, batched, dev = H._canon(natparam)
+    B, T, K = node.shape
+    Lc = int(chunk_len) if chunk_len else default_chunk_len(T)
+    if T < 4 or Lc >= T - 1:
+        return H.hmm_viterbi(natparam)
+    L = _lib.lib()
+    C = L.svae_lds_compose_num_chunks(T, Lc)
+    V = torch.empty((B, C, K, K), dtype=torch.float64, device=dev)
+    delta = torch.empty((B, C + 1, K), dtype=torch.float64, device=dev)
+    zb = torch.empty((B, C + 1), dtype=torch.int32, device=dev)
+    ptr, st = _lib.ptr, _lib.stream_ptr(dev)
+    import ctypes
+    _lib.check(L.svae_hmm_compose_chunks_maxplus(B, T, K, Lc, ptr(lA), ptr(node), ptr(V), st), "svae_hmm_compose_chunks_maxplus")
+    last = node[:, -1].contiguous()
+    _lib.check(L.svae_hmm_chain_viterbi(B, C, K, ptr(lp), ptr(V), ptr(last), ptr(delta), ctypes.c_void_p(zb.data_ptr()), st),
+               "svae_hmm_chain_viterbi")
+    never = -1e300
+    pin = torch.full((B, C + 1, K), never, dtype=torch.float64, device=dev)
+    pin.scatter_(2, zb.long()[..., None], 0.0)                       # 0 at the optimal boundary state, "never" elsewhere
+    nfull = (T - 1) // Lc
+    tail = (T - 1) - nfull * Lc
+    path = torch.empty((B, T), dtype=torch.int32, device=dev)
+    zero_pi = torch.zeros(K, dtype=torch.float64, device=dev)
+    for c0, cnt, Ls in [(0, nfull, Lc)] + ([(nfull, 1, tail)] if tail else []):
+        t0, t1 = c0 * Lc, c0 * Lc + cnt * Ls
+        sub = torch.empty((B, cnt, Ls + 1, K), dtype=torch.float64, device=dev)
+        sub[:, :, :Ls] = node[:, t0:t1].reshape(B, cnt, Ls, K)
+        sub[:, :, 0] += pin[:, c0:c0 + cnt]
+        sub[:, :, Ls] = pin[:, c0 + 1:c0 + cnt + 1]
+        p = H.hmm_viterbi((zero_pi, lA, sub.reshape(B * cnt, Ls + 1, K))).reshape(B, cnt, Ls + 1)
+        path[:, t0:t1] = p[:, :, :Ls].reshape(B, cnt * Ls)
+        if t1 == T - 1:
+            path[:, -1] = p[:, -1, Ls]
+    return path if batched else path[0]

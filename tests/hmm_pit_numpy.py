@@ -79,3 +79,61 @@ def pit_estep(log_pi, log_A, node, Lc, stage12=stage12_numpy):
         Etrans += Et
         Ez[:, s:e + 1] = Ezc
     return logZ, (Ez[:, 0], Etrans, Ez)
+
+
+def viterbi_stage12_host(log_pi, log_A, node, Lc):
+    """Max-plus chunk matrices and optimal boundary states by the host build of the CUDA phase code."""
+    stage12_host(log_pi, log_A, node[:, :2] if node.shape[1] > 2 else node, 1)      # make sure the library is built
+    node = np.ascontiguousarray(node, dtype=np.float64)
+    B, T, K = node.shape
+    C = (T - 1 + Lc - 1) // Lc
+    P_ = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lp, lA = np.ascontiguousarray(log_pi, dtype=np.float64), np.ascontiguousarray(log_A, dtype=np.float64)
+    V = np.zeros((B, C, K, K))
+    _host.hmm_compose_chunks_maxplus_host(B, T, K, Lc, P_(lA), P_(node), P_(V))
+    delta = np.zeros((B, C + 1, K)); zb = np.zeros((B, C + 1), dtype=np.int32)
+    last = np.ascontiguousarray(node[:, -1])
+    _host.hmm_chain_viterbi_host(B, C, K, P_(lp), P_(V), P_(last), P_(delta), P_(zb))
+    return V, zb
+
+
+def viterbi_stage12_numpy(log_pi, log_A, node, Lc):
+    B, T, K = node.shape
+    C = (T - 1 + Lc - 1) // Lc
+    V = np.zeros((B, C, K, K))
+    for b in range(B):
+        for c in range(C):
+            s = c * Lc
+            L = min(Lc, T - 1 - s)
+            M = np.where(np.eye(K) > 0, 0.0, -1e300)
+            for t in range(s, s + L):
+                M = np.max(M[:, :, None] + (node[b, t][:, None] + log_A)[None], axis=1)
+            V[b, c] = M
+    delta = np.zeros((B, C + 1, K)); delta[:, 0] = log_pi
+    for c in range(C):
+        delta[:, c + 1] = np.max(delta[:, c][:, :, None] + V[:, c], axis=1)
+    zb = np.zeros((B, C + 1), dtype=np.int32)
+    zb[:, C] = np.argmax(delta[:, C] + node[:, -1], axis=1)
+    for c in range(C - 1, -1, -1):
+        zb[:, c] = np.argmax(delta[:, c] + V[np.arange(B), c, :, zb[:, c + 1]], axis=1)
+    return V, zb
+
+
+def pit_viterbi(log_pi, log_A, node, Lc, stage12=viterbi_stage12_numpy):
+    """Most likely path by chunks: boundary states from the max-plus chain, then the sequential oracle on every chunk
+    with both end states pinned."""
+    B, T, K = node.shape
+    C = (T - 1 + Lc - 1) // Lc
+    _, zb = stage12(log_pi, log_A, node, Lc)
+    path = np.zeros((B, T), dtype=np.int32)
+    never = -1e300
+    for c in range(C):
+        s = c * Lc
+        e = min(s + Lc, T - 1)
+        sub = node[:, s:e + 1].copy()
+        pin0 = np.full((B, K), never); pin0[np.arange(B), zb[:, c]] = 0.0
+        pin1 = np.full((B, K), never); pin1[np.arange(B), zb[:, c + 1]] = 0.0
+        sub[:, 0] += pin0
+        sub[:, -1] = pin1
+        path[:, s:e + 1] = HO.hmm_viterbi((np.zeros(K), log_A, sub))
+    return path

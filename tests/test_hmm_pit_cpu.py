@@ -29,3 +29,15 @@ def test_messages_of_the_phase_code_match_log_space_algebra():
     ha, hb, hz = HP.stage12_host(lp, lA, node, Lc)
     assert np.allclose(ha, la, atol=1e-12) and np.allclose(hz, lz, atol=1e-11)
     assert np.allclose(hb - hb.max(-1, keepdims=True), lb - lb.max(-1, keepdims=True), atol=1e-11)
+
+
+@pytest.mark.parametrize("stage12", [HP.viterbi_stage12_numpy, HP.viterbi_stage12_host])
+@pytest.mark.parametrize("K,T,B,Lc", [(3, 10, 2, 3), (8, 41, 3, 7), (32, 50, 2, 10), (5, 9, 2, 1), (32, 400, 1, 25)])
+def test_viterbi_pipeline_equals_sequential_oracle(stage12, K, T, B, Lc):
+    """Max-plus composition + boundary back-tracking + pinned chunk decodes give the sequential Viterbi path."""
+    rng = np.random.default_rng(100 + K + T)
+    lp, lA = HO.rand_hmm_natparam(K, rng)
+    node = 2.0 * rng.standard_normal((B, T, K))
+    want = HO.hmm_viterbi((lp, lA, node))
+    got = HP.pit_viterbi(lp, lA, node, Lc, stage12)
+    assert np.array_equal(got, want)

@@ -82,5 +82,5 @@ def test_viterbi_parallel_equals_sequential():
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([root, os.path.join(root, "tests"), os.environ.get("PYTHONPATH", "")]))
-    r = subprocess.run([sys.executable, "-c", _VITERBI_CHILD], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, "-c", _VITERBI_CHILD], cwd=root, env=env, capture_output=True, text=True, timeout=180)
     assert r.returncode == 0 and "viterbi parallel ok" in r.stdout, (r.stdout + r.stderr)[-2000:]

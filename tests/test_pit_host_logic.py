@@ -28,3 +28,14 @@ def test_default_chunk_length():
         if T in (201, 2001, 100001, 20001):                # T-1 has a divisor near sqrt(T-1): no ragged tail
             assert (T - 1) % L == 0
     assert lds_pit.default_chunk_len(100001) == 250 and lds_pit.default_chunk_len(200) == 14
+
+
+def test_ramp_schedule_of_the_host_pipeline():
+    from svae_b200.lds.lds_inference import ramp_schedule
+    for B in (1, 100, 255, 256, 257, 512, 4096, 5000, 100000):
+        for first, growth, largest in ((256, 1.5, 1024), (128, 2.0, 2048), (512, 1.5, 1024)):
+            s = ramp_schedule(B, first, growth, largest)
+            assert sum(s) == B and min(s) > 0
+            assert all(x <= max(largest, first) + first // 2 for x in s)          # last piece may absorb a sliver
+            assert all(a <= b for a, b in zip(s[:-2], s[1:-1]))                    # non-decreasing up to the remainder
+    assert ramp_schedule(4096, 256, 1.5, 1024) == [256, 384, 576, 864, 1024, 992]

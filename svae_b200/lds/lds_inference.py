@@ -383,23 +383,34 @@ class _LDSEStepFn(torch.autograd.Function):
         names = _OUT_PER_T if per_t else _OUT_HOMOG
         if o["dense"] and per_t:      # E_node_xx IS Exx_t: hand autograd the tensor once
             names = tuple(k for k in names if k != "E_node_xx")
-        ctx.o, ctx.names, ctx.has_logZ = o, names, nlogZ is not None
+        # Outputs must not be reachable from ctx except through save_for_backward: ctx -> output -> grad_fn -> ctx is
+        # a reference cycle the collector cannot break (every forward's outputs + eps + workspace would stay alive).
+        ctx.names, ctx.has_logZ = names, nlogZ is not None
+        ctx.state = {k: o[k] for k in ("B", "T", "n", "S", "dense", "eps", "workspace", "workspace_bytes")}
+        ctx.has_samples = o["samples"] is not None
         ctx.set_materialize_grads(False)
         outs = tuple(o[k] for k in ctx.names)
-        if o["samples"] is None:
+        if not ctx.has_samples:
             outs = (torch.empty(0, device=nh.device, dtype=torch.float64),) + outs[1:]
+        ctx.save_for_backward(o["E_node_x"], outs[0], o["lognorm"])
         return outs
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, *gs):
         g = dict(zip(ctx.names, gs))
-        if ctx.o["samples"] is None:
+        E_node_x, samples, lognorm = ctx.saved_tensors
+        o = dict(ctx.state, E_node_x=E_node_x, samples=samples if ctx.has_samples else None, lognorm=lognorm)
+        if not ctx.has_samples:
             g["samples"] = None
-        gJ, gh = lds_estep_backward(ctx.o, g)
+        B, T = o["B"], o["T"]
+        try:
+            gJ, gh = lds_estep_backward(o, g)
+        finally:
+            ctx.state = None      # single use, like the reference's intermediates; frees eps + workspace now
         g_logZ = None
         if ctx.has_logZ and g.get("lognorm") is not None:
-            g_logZ = g["lognorm"][:, None].expand(ctx.o["B"], ctx.o["T"]).contiguous()
+            g_logZ = g["lognorm"][:, None].expand(B, T).contiguous()
         return gJ, gh, g_logZ, None, None, None, None, None
 
 

@@ -6,7 +6,7 @@ so an optimiser loop written against the reference runs unchanged; torch.autogra
 autograd.value_and_grad over (loglike_params, recogn_params) (svae.py:28-30), the natural gradient of the PGM
 parameters is formed from the expected statistics the E-step returns (svae.py:31-34, no backprop into
 pgm_params), and with torch.distributed initialised the statistics / gradients of a sharded minibatch are
-summed with ONE all-reduce per step.
+summed with ONE all-reduce per step (a sum, not a mean: the shards partition the minibatch).
 """
 from __future__ import annotations
 import torch
@@ -62,9 +62,11 @@ def make_gradfun(run_inference, recognize, loglike, pgm_prior, data, batch_size,
             stats_flat = buf[:k]
             off = k
             for j, g in enumerate(grads):
-                grads[j] = buf[off:off + g.numel()].reshape(g.shape) / dist.get_world_size()
+                grads[j] = buf[off:off + g.numel()].reshape(g.shape)
                 off += g.numel()
-            val = buf[-1] / dist.get_world_size()
+            # loglike and local_kl are sums over the datapoints of a shard, so the minibatch gradient / objective is
+            # the SUM over ranks; global_kl (no NN dependence) sits in every rank's val and is counted once
+            val = buf[-1] - (dist.get_world_size() - 1) * torch.as_tensor(global_kl).detach().to(buf) / num_datapoints
         loglike_grad, recogn_grad = _rebuild((loglike_params, recogn_params), iter(grads))
         # natural gradient of the PGM parameters (svae.py:31-34)
         # (the PGM block may live on the host -- its exp-family maps are K tiny matrices -- while the statistics

@@ -44,6 +44,13 @@ def test_gmm_svae_step_cpu():
     assert float(flat(rc_grad).abs().max()) > 0
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _gloo_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -53,11 +60,12 @@ def _gloo_worker(rank, world, port, out):
     shard = lambda pots: tuple(p[rank * half:(rank + 1) * half] for p in pots)
     rec_shard = lambda rp, batch: recognize(rp, batch[rank * half:(rank + 1) * half])
     ll_shard = lambda lp, samples, batch: loglike(lp, samples, batch[rank * half:(rank + 1) * half])
-    gradfun = make_gradfun(run, rec_shard, ll_shard, pgm_prior, data, T, 4, natgrad_scale=1e2, callback=None,
-                           generator=torch.Generator().manual_seed(0))
+    vals = []
+    gradfun = make_gradfun(run, rec_shard, ll_shard, pgm_prior, data, T, 4, natgrad_scale=1e2,
+                           callback=lambda i, v, p, g: vals.append(v), generator=torch.Generator().manual_seed(0))
     natgrad, ll_grad, rc_grad = gradfun(params, 0)
     if rank == 0:
-        torch.save((flat(natgrad), flat(ll_grad), flat(rc_grad)), out)
+        torch.save((flat(natgrad), flat(ll_grad), flat(rc_grad), vals[0]), out)
     dist.destroy_process_group()
 
 
@@ -65,9 +73,9 @@ def test_data_parallel_allreduce_gloo_world2(tmp_path):
     """Two ranks, each with half of the minibatch: the all-reduced statistics must equal the sum of the
     per-shard statistics (the GMM label factor is per-datapoint, so shards are independent)."""
     out = str(tmp_path / "r0.pt")
-    port = 29500 + (os.getpid() % 2000)
+    port = _free_port()
     mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
-    nat2, ll2, rc2 = torch.load(out)
+    nat2, ll2, rc2, val2 = torch.load(out)
     # single process: run the two shards by hand and sum
     run, recognize, loglike, pgm_prior, data, params, T = _gmm_setup()
     from svae_b200.util import unbox
@@ -76,13 +84,29 @@ def test_data_parallel_allreduce_gloo_world2(tmp_path):
     batch = batches[0]
     half = T // 2
     stats_sum = 0
+    # the minibatch objective: loglike and local_kl are sums over the datapoints of both shards, global_kl counts once
+    from svae_b200.svae import _leaves, _rebuild
+    leaves = [l.detach().requires_grad_(True) for l in _leaves((params[1], params[2]))]
+    ll_p, rc_p = _rebuild((params[1], params[2]), iter(leaves))
+    N = get_num_datapoints(data)
+    ll_sum = kl_sum = 0
     for r in range(2):
-        pots = recognize(params[2], batch[r * half:(r + 1) * half])
-        _, stats, _, _ = run(pgm_prior, unbox(params[0]), pots, 4)
-        stats_sum = stats_sum + flat(stats)
-    want_nat = -1e2 / get_num_datapoints(data) * (flat(pgm_prior) + nb * stats_sum - flat(params[0]))
+        sl = slice(r * half, (r + 1) * half)
+        pots = recognize(rc_p, batch[sl])
+        samples, stats, global_kl, local_kl = run(pgm_prior, unbox(params[0]), pots, 4)
+        stats_sum = stats_sum + flat(unbox(stats))
+        ll_sum = ll_sum + loglike(ll_p, samples, batch[sl])
+        kl_sum = kl_sum + local_kl
+    want_val = -(nb * ll_sum - global_kl - nb * kl_sum) / N
+    want_grads = torch.autograd.grad(want_val, leaves)
+    want_ll, want_rc = _rebuild((params[1], params[2]), iter(want_grads))
+    want_nat = -1e2 / N * (flat(pgm_prior) + nb * stats_sum - flat(params[0]))
     assert torch.allclose(nat2, want_nat, rtol=1e-10, atol=1e-12)
-    assert torch.isfinite(ll2).all() and torch.isfinite(rc2).all()
+    # NN gradients and the objective are SUMS over the shards (not means): same step whatever the world size
+    assert torch.allclose(ll2, flat(want_ll), rtol=1e-9, atol=1e-12)
+    assert torch.allclose(rc2, flat(want_rc), rtol=1e-9, atol=1e-12)
+    want_val = float(want_val.detach())
+    assert abs(val2 - want_val) <= 1e-9 * abs(want_val)
 
 
 @pytest.mark.gpu

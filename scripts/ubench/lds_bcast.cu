@@ -22,13 +22,13 @@ __global__ void lds_tput(const int* lane_off, int iters, long long* cyc, unsigne
       for (int j = 0; j < 16; ++j) {
         unsigned a, b, c, d;
         if (W == 16) {
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(base + j * 256));
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(base + j * 256 + ((it & 1) << 12)) : "memory");
           acc ^= a;
         } else if (W == 8) {
-          asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(base + j * 256));
+          asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(base + j * 256 + ((it & 1) << 12)) : "memory");
           acc ^= a;
         } else {
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(base + j * 256));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(base + j * 256 + ((it & 1) << 12)) : "memory");
           acc ^= a;
         }
       }
@@ -48,8 +48,8 @@ __global__ void sts_tput(const int* lane_off, int iters, long long* cyc, unsigne
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      if (W == 8) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(base + j * 256), "r"(it), "r"(j));
-      else asm volatile("st.shared.v4.u32 [%0], {%1,%2,%1,%2};" ::"r"(base + j * 256), "r"(it), "r"(j));
+      if (W == 8) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(base + j * 256 + ((it & 1) << 12)), "r"(it), "r"(j) : "memory");
+      else asm volatile("st.shared.v4.u32 [%0], {%1,%2,%1,%2};" ::"r"(base + j * 256 + ((it & 1) << 12)), "r"(it), "r"(j) : "memory");
     }
   }
   long long t1 = clock64();
@@ -109,7 +109,7 @@ __global__ void lds_fma(const int* lane_off, int iters, long long* cyc, double* 
 #pragma unroll
       for (int q = 0; q < 5; ++q) {
         double x, y;
-        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(base + (k * 5 + q) * 16));
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(base + (k * 5 + q) * 16 + ((it & 1) << 12)) : "memory");
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           acc[r][2 * q] = fma(x, z[r], acc[r][2 * q]);

@@ -1,6 +1,7 @@
 // One translation unit per latent dimension: compiled with -DSVAE_N=<n> for n = 1..SVAE_LDS_MAX_N so
 // the fully-unrolled kernels build in parallel.  Exposes svae::lds_fwd_launch_n<n>().
 #include "lds_estep.cuh"
+#include "lds_estep_packed.cuh"
 #include "launch.h"
 
 #ifndef SVAE_N
@@ -89,6 +90,43 @@ static cudaError_t launch_one(const LdsFwdParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// the packed mapping (lds_estep_packed.cuh): N lanes per sequence, 32/N sequences per warp
+template <int N, int S>
+static cudaError_t launch_packed(const LdsFwdParams& p, cudaStream_t stream) {
+  constexpr int SPW = lds_packed_spw(N);
+  const long long grid = ((long long)p.B + SPW - 1) / SPW;
+  const size_t smem = sizeof(double) * (3 * N * lds_np(N) + (size_t)SPW * lds_packed_tile_doubles(N, S));
+  auto kern = lds_estep_packed_kernel<N, S>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  if (p.T > 1) {
+    std::lock_guard<std::mutex> lock(g_const_mu);
+    LdsFwdParams q = p;
+    int slot = 0;
+    ConstSlots* cs = nullptr;
+    cudaError_t e = stage_const_J12<N>(p.J12, stream, &slot, &cs);
+    if (e != cudaSuccess) return e;
+    q.const_slot = slot;
+    kern<<<(unsigned)grid, 32, smem, stream>>>(q);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    cs->used[slot] = true;
+    cs->stream[slot] = stream;
+    return cudaEventRecord(cs->ev[slot], stream);
+  }
+  kern<<<(unsigned)grid, 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// the packed kernel covers the hot configuration only; everything else runs the general kernel
+static bool packed_eligible(const LdsFwdParams& p, bool inhomog) {
+  static const bool enabled = [] { const char* e = getenv("SVAE_LDS_PACKED"); return !(e && atoi(e) == 0); }();
+  return enabled && !inhomog && p.S <= 2 && !(p.flags & SVAE_LDS_FLAG_INIT_PER_SEQ) && !p.Exx_t && !p.Exxn_t &&
+         !p.msg_J_pred && !p.msg_h_pred && !p.in_J_filt && !p.in_h_filt && !p.node_J_dense && !p.term_J;
+}
+
 #define SVAE_CAT_(a, b) a##b
 #define SVAE_CAT(a, b) SVAE_CAT_(a, b)
 
@@ -104,6 +142,13 @@ static cudaError_t launch_if_fits(const LdsFwdParams& p, bool inhomog, cudaStrea
 // cpl: columns per lane (1 or 2); lps: lanes per sequence tile, with cpl * lps >= n + 1 + S
 cudaError_t SVAE_CAT(lds_fwd_launch_n, SVAE_N)(const LdsFwdParams& p, int cpl, int lps, bool inhomog, cudaStream_t stream) {
   constexpr int N = SVAE_N;
+  if (packed_eligible(p, inhomog)) {
+    switch (p.S) {
+      case 0: return launch_packed<N, 0>(p, stream);
+      case 1: return launch_packed<N, 1>(p, stream);
+      default: return launch_packed<N, 2>(p, stream);
+    }
+  }
 #ifdef SVAE_LDS_ENABLE_CPL2   // two column slots per lane: measured slower than CPL = 1 on B200
   if (cpl == 2) {
     switch (lps) {

@@ -33,8 +33,12 @@ static cudaError_t stage_const_J12(const double* J12, cudaStream_t stream, int* 
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
   ConstSlots& cs = g_const[dev];
+#ifdef SVAE_PACKED_SLOT0
+  const int slot = 0;
+#else
   const int slot = cs.next;
   cs.next = (cs.next + 1) % SVAE_LDS_CONST_SLOTS;
+#endif
   if (!cs.ev[slot]) {
     e = cudaEventCreateWithFlags(&cs.ev[slot], cudaEventDisableTiming);
     if (e != cudaSuccess) return e;
@@ -91,12 +95,12 @@ static cudaError_t launch_one(const LdsFwdParams& p, cudaStream_t stream) {
 }
 
 // the packed mapping (lds_estep_packed.cuh): N lanes per sequence, 32/N sequences per warp
-template <int N, int S>
+template <int N, int S, bool SAVE>
 static cudaError_t launch_packed(const LdsFwdParams& p, cudaStream_t stream) {
   constexpr int SPW = lds_packed_spw(N);
   const long long grid = ((long long)p.B + SPW - 1) / SPW;
-  const size_t smem = sizeof(double) * (3 * N * lds_np(N) + (size_t)SPW * lds_packed_tile_doubles(N, S));
-  auto kern = lds_estep_packed_kernel<N, S>;
+  const size_t smem = sizeof(double) * (3 * N * lds_np(N) + 2 + (size_t)SPW * lds_packed_tile_doubles(N, S));
+  auto kern = lds_estep_packed_kernel<N, S, SAVE>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -124,7 +128,9 @@ static cudaError_t launch_packed(const LdsFwdParams& p, cudaStream_t stream) {
 static bool packed_eligible(const LdsFwdParams& p, bool inhomog) {
   static const bool enabled = [] { const char* e = getenv("SVAE_LDS_PACKED"); return !(e && atoi(e) == 0); }();
   return enabled && !inhomog && p.S <= 2 && !(p.flags & SVAE_LDS_FLAG_INIT_PER_SEQ) && !p.Exx_t && !p.Exxn_t &&
-         !p.msg_J_pred && !p.msg_h_pred && !p.in_J_filt && !p.in_h_filt && !p.node_J_dense && !p.term_J;
+         !p.msg_J_pred && !p.msg_h_pred && !p.in_J_filt && !p.in_h_filt && !p.node_J_dense && !p.term_J &&
+         p.E_init_xx && p.E_init_x && p.E_pair_xx && p.E_pair_xxn && p.E_pair_xnxn && p.E_node_xx && p.E_node_x &&
+         p.lognorm && (p.S == 0 || p.samples);
 }
 
 #define SVAE_CAT_(a, b) a##b
@@ -143,10 +149,11 @@ static cudaError_t launch_if_fits(const LdsFwdParams& p, bool inhomog, cudaStrea
 cudaError_t SVAE_CAT(lds_fwd_launch_n, SVAE_N)(const LdsFwdParams& p, int cpl, int lps, bool inhomog, cudaStream_t stream) {
   constexpr int N = SVAE_N;
   if (packed_eligible(p, inhomog)) {
+    const bool save = (p.flags & SVAE_LDS_FLAG_SAVE) != 0;
     switch (p.S) {
-      case 0: return launch_packed<N, 0>(p, stream);
-      case 1: return launch_packed<N, 1>(p, stream);
-      default: return launch_packed<N, 2>(p, stream);
+      case 0: return save ? launch_packed<N, 0, true>(p, stream) : launch_packed<N, 0, false>(p, stream);
+      case 1: return save ? launch_packed<N, 1, true>(p, stream) : launch_packed<N, 1, false>(p, stream);
+      default: return save ? launch_packed<N, 2, true>(p, stream) : launch_packed<N, 2, false>(p, stream);
     }
   }
 #ifdef SVAE_LDS_ENABLE_CPL2   // two column slots per lane: measured slower than CPL = 1 on B200

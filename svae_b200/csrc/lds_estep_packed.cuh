@@ -27,19 +27,23 @@
 // broadcast operands are read by all lanes of a sequence with one 16-byte shared-memory load.
 #pragma once
 #include "lds_estep.cuh"
+#ifdef SVAE_PACKED_CLOCKS
+#include <cstdio>
+#endif
 
 namespace svae {
 
 __host__ __device__ constexpr int lds_packed_spw(int N) { return 32 / N; }
 
-// shared-memory doubles per sequence tile; padded so that consecutive tiles start 48 bytes apart modulo 128
-// (the same offset in the tiles of one warp falls into different banks)
+// shared-memory doubles per sequence tile; padded so that consecutive tiles start one ROW (NP doubles) apart modulo
+// 128 bytes: the rows the 32/N sequences of a warp touch with one instruction then sit side by side in bank space
+// (2 wavefronts for 3 x 80 bytes at n = 10 instead of the 4 that ncu counted with a 48-byte skew)
 __host__ __device__ constexpr int lds_packed_tile_doubles(int N, int S) {
   const int NP = lds_np(N);
   const int fa = 2 * N * NP + 2 * (2 + S) * NP;                 // Lr, Lt, node ring
   const int fb = 2 * (2 * N + 1 + S) * NP + N * NP;             // stash ring, Cs
-  const int raw = 2 /*mbarriers*/ + (3 + 2 * S) * NP /*hf, mu, sd, w, x*/ + (fa > fb ? fa : fb);
-  return raw + ((6 - raw % 16) + 16) % 16;
+  const int raw = (3 + 2 * S) * NP /*hf, mu, sd, w, x*/ + (fa > fb ? fa : fb);
+  return raw + ((NP % 16 - raw % 16) + 16) % 16;
 }
 
 // register budget: one warp per CTA; resident warps per SM chosen so that the metric batch is one wave
@@ -47,7 +51,27 @@ __host__ __device__ constexpr int lds_packed_tile_doubles(int N, int S) {
 #define SVAE_PACKED_MINB(N) ((N) <= 8 ? 16 : (N) <= 10 ? 12 : (N) <= 12 ? 10 : 8)
 #endif
 
-template <int N, int S>
+// dev instrumentation (-DSVAE_PACKED_CLOCKS): per-phase clock64 sums of block 0, printed at kernel end
+#ifdef SVAE_PACKED_CLOCKS
+#define SVAE_CLK(i) { const long long now_ = clock64(); clk_[i] += now_ - tprev_; tprev_ = now_; }
+#else
+#define SVAE_CLK(i)
+#endif
+
+// reciprocal square root: hardware seed + two Newton steps (pivots are positive, O(1) numbers; the library routine
+// spends ~20 instructions on special cases that cannot occur past the sign check on the pivot)
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
+
+template <int N, int S, bool SAVE>
 __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kernel(const LdsFwdParams p) {
   constexpr int NP = lds_np(N);
   constexpr int NN = N * N;
@@ -61,6 +85,9 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x;
   const int T = p.T;
+#ifdef SVAE_PACKED_CLOCKS
+  long long clk_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev_ = clock64();
+#endif
 
   // ---- CTA-shared homogeneous pair parameters, information form ------------------------------
   double* shJ11 = smem;            // J22 + J11: what every non-terminal prediction lands in
@@ -81,12 +108,13 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
   const long long seq = (long long)blockIdx.x * SPW + sub;
   const bool valid = seq < p.B;
   const long long b = valid ? seq : (long long)p.B - 1;
-  const bool save = (p.flags & SVAE_LDS_FLAG_SAVE) != 0;
-  const int RS = lds_record_stride(N, S, save);
+  constexpr bool save = SAVE;
+  constexpr int RS = (SAVE ? 4 * N + 1 + S : 2 * N + 1 + S) * NP;   // == lds_record_stride(N, S, SAVE)
 
-  double* tile = shJ22 + N * NP + (size_t)sub * TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tile);
-  double* hfv = tile + 2;          // h_filtered of this step (broadcast operand)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(shJ22 + N * NP);   // 2 warp-level mbarriers (stash ring slots)
+  double* tile0 = shJ22 + N * NP + 2;
+  double* tile = tile0 + (size_t)sub * TILE;
+  double* hfv = tile;              // h_filtered of this step (broadcast operand)
   double* mu_s = hfv + NP;         // mu_{t+1} during the backward sweep
   double* sdv = mu_s + NP;         // sqrt(d_k)
   double* wv = sdv + NP;           // sqrt(d_k) eps_k per sample path
@@ -98,7 +126,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
   double* ring = uni;              // backward sweep: 2 stash records
   double* Cs = ring + 2 * SS;      // Cs[k*NP+i] = C[i][k]
 
-  if (c == 0) {
+  if (lane == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_fence_init();
@@ -106,17 +134,21 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
   __syncwarp(MASK);
 
   double* stash = p.stash + (size_t)b * T * RS;
-  const double* nJ = p.node_J + (size_t)b * T * N;
-  const double* nh = p.node_h + (size_t)b * T * N;
-  const double* eps = S > 0 ? p.eps + (size_t)b * T * S * N : nullptr;
+  const double* nJ = p.node_J + (size_t)b * T * N + c;
+  const double* nh = p.node_h + (size_t)b * T * N + c;
+  const double* eps = S > 0 ? p.eps + (size_t)b * T * S * N + c : nullptr;
+  // per-time outputs, element c of this sequence (the packed launcher requires every output buffer)
+  double* oEx = p.E_node_x + (size_t)b * T * N + c;
+  double* oExx = p.E_node_xx + (size_t)b * T * N + c;
+  double* oSmp = S > 0 ? p.samples + (size_t)b * T * S * N + c : nullptr;
 
   // node potentials (+ noise) of time t -> ring slot t&1; every lane copies and later reads its own element only
   auto stage_node = [&](int t) {
     double* dst = nring + (t & 1) * NODE;
-    cp_async8(dst + c, nJ + (size_t)t * N + c);
-    cp_async8(dst + NP + c, nh + (size_t)t * N + c);
+    cp_async8(dst + c, nJ + t * N);
+    cp_async8(dst + NP + c, nh + t * N);
 #pragma unroll
-    for (int s = 0; s < S; ++s) cp_async8(dst + (2 + s) * NP + c, eps + ((size_t)t * S + s) * N + c);
+    for (int s = 0; s < S; ++s) cp_async8(dst + (2 + s) * NP + c, eps + (t * S + s) * N);
     cp_async_commit();
   };
 
@@ -143,6 +175,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
 
   // =========================== forward in time: information filter ===========================
   for (int t = 0; t < T; ++t) {
+    SVAE_CLK(0)
     const bool last = (t == T - 1);
     const double* nd = nring + (t & 1) * NODE;
     const double ndJ = nd[c];
@@ -177,25 +210,29 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
       badbits |= __double2hiint(row[k]);
       const double ik = fast_rcp(row[k]);
       const double ta = v * ik, tr = r[k] * ik, tq = q[k] * ik;
-      Lt[c * NP + k] = ta;
 #pragma unroll
       for (int j = k + 1; j < N; ++j) {
         a[j] = fma(-ta, row[j], a[j]);
         r[j] = fma(-tr, row[j], r[j]);
         q[j] = fma(-tq, row[j], q[j]);
       }
+      a[k] = ta;                     // L~[c][k] (k < c; the rest of the row is never read)
       r[k] = tr;
       q[k] = tq;
     }
+    // row c of the unit lower factor, one 16-byte store per pair (a column store per pivot costs 6 wavefronts each)
+#pragma unroll
+    for (int q2 = 0; q2 < NP / 2; ++q2) st2(&Lt[c * NP + 2 * q2], a[2 * q2], (2 * q2 + 1 < N) ? a[2 * q2 + 1] : 0.0);
+    SVAE_CLK(1)
     {
       const double dc = Lr[c * NP + c];             // this lane's pivot (its own store)
       dprod *= dc;
-      if ((t & 3) == 3 || last) {
+      if ((t & 7) == 7 || last) {     // pivots are O(1): eight of them cannot leave the double range
         lacc -= 0.5 * log(dprod);
         dprod = 1.0;
       }
       if (S > 0 || save) {
-        const double sd = dc * rsqrt(dc);
+        const double sd = dc * fast_rsqrt(dc);
         if (save) sdv[c] = sd;
 #pragma unroll
         for (int s = 0; s < S; ++s) wv[s * NP + c] = sd * ec[s];
@@ -227,6 +264,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
         }
       }
     }
+    SVAE_CLK(2)
     // ---- back substitution with the unit upper factor L~', column-oriented (independent accumulators) ----
 #pragma unroll
     for (int i = N - 1; i >= 1; --i) {
@@ -241,6 +279,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
         }
       }
     }
+    SVAE_CLK(3)
     // r = Y[:,c] = -G[:,c],  q = M^-1[:,c].   m_c = <q, h_f>,  (J12' m)_c = <r, h_f>
     double m, hq;
     {
@@ -275,6 +314,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
 #pragma unroll
       for (int s = 0; s < S; ++s) st[(2 * N + 1 + s) * NP + c] = bs[s];
     }
+    SVAE_CLK(4)
     if (!last) {
       cp_async_wait<0>();            // own elements of step t+1 have landed (no cross-lane reads of the ring)
       if (t + 2 < T) stage_node(t + 2);
@@ -282,7 +322,11 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
       const double* pm = (t + 1 == T - 1) ? shJ22 : shJ11;
 #pragma unroll
       for (int i = 0; i < N; ++i) a[i] = pm[i * NP + c];
+#ifdef SVAE_PACKED_SLOT0     // experiment: compile-time constant bank address (immediate operands instead of LDCU)
+      const double* cj12 = c_J12[0];
+#else
       const double* cj12 = c_J12[p.const_slot];
+#endif
 #pragma unroll
       for (int k = 0; k < N; ++k) {
 #pragma unroll
@@ -298,6 +342,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
       for (int s = 0; s < S; ++s) x[s] = bs[s];
     }
     __syncwarp(MASK);                // hfv / wv / Lr / Lt are rewritten by the next step
+    SVAE_CLK(5)
   }
   double (&z)[N] = a;                // backward-sweep state: column c of Sigma_t
 
@@ -306,7 +351,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
     const double part = fma(0.5, lq, lacc);
     hfv[c] = part;
     __syncwarp(MASK);
-    if (c == 0 && valid && p.lognorm) {
+    if (c == 0 && valid) {
       double tot = 0.0;
 #pragma unroll
       for (int i = 0; i < N; ++i) tot += hfv[i];
@@ -324,11 +369,21 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
   __threadfence_block();             // stash records were written through the generic proxy
   fence_proxy_async();
   __syncwarp(MASK);
+  // One lane issues the bulk copies of ALL the warp's sequences onto one warp-level mbarrier: every address below is
+  // a function of blockIdx and compile-time constants, so the copies run on the uniform datapath back to back (a
+  // copy per sequence issued by that sequence's own lane costs an ELECT / R2UR loop over the lanes instead).
+  constexpr int ring_off = (3 + 2 * S) * NP;   // == ring - tile
   auto fetch = [&](int t, int j) {   // j-th backward step (t = T-2-j) -> ring slot j&1
 #if SVAE_LDS_TMA
-    if (c == 0) {
-      mbar_arrive_expect_tx(&bars[j & 1], (uint32_t)(SS * sizeof(double)));
-      tma_load_1d(ring + (j & 1) * SS, stash + (size_t)t * RS, (uint32_t)(SS * sizeof(double)), &bars[j & 1]);
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars[j & 1], (uint32_t)(SPW * SS * sizeof(double)));
+#pragma unroll
+      for (int s2 = 0; s2 < SPW; ++s2) {
+        long long bs = (long long)blockIdx.x * SPW + s2;
+        if (bs >= p.B) bs = (long long)p.B - 1;
+        tma_load_1d(tile0 + s2 * TILE + ring_off + (j & 1) * SS, p.stash + ((size_t)bs * T + t) * RS,
+                    (uint32_t)(SS * sizeof(double)), &bars[j & 1]);
+      }
     }
 #else
     double* dst = ring + (j & 1) * SS;
@@ -345,6 +400,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
   double mun = 0.0;                  // mu_{t+1}[c]
 
   for (int t = T - 1; t >= 0; --t) {
+    SVAE_CLK(6)
     if (t < T - 1) {
       const int j = T - 2 - t;
       const double* rec = ring + (j & 1) * SS;
@@ -353,6 +409,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
 #else
       __syncwarp(MASK);
 #endif
+      SVAE_CLK(7)
       const double* G = rec;                    // G[k*NP+i] = G_t[i][k]
       const double* Minv = rec + N * NP;
       // C[:,c] = G Sigma_{t+1}[:,c]
@@ -403,6 +460,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
         xnew[s] += e0;
       }
       __syncwarp(MASK);              // Cs complete; every lane is done with mu_{t+1}, x_{t+1}
+      SVAE_CLK(8)
       // Sigma_t[:,c] = M^-1[:,c] + C G'[:,c]
 #pragma unroll
       for (int i = 0; i < N; ++i) z[i] = Minv[i * NP + c];
@@ -420,13 +478,13 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
 #pragma unroll
       for (int s = 0; s < S; ++s) x[s] = xnew[s];
     }
+    SVAE_CLK(9)
     mu_s[c] = mu;
 #pragma unroll
     for (int s = 0; s < S; ++s) xs[s * NP + c] = x[s];
     __syncwarp(MASK);                // also: every lane is done with ring slot j&1
 
     // ---- emit statistics for time t -----------------------------------------------------------
-    const size_t bt = (size_t)b * T + t;
     const bool first = (t == 0), lastt = (t == T - 1);
     if (save && valid) {
       double* sg = stash + (size_t)t * RS + (3 * N + 1 + S) * NP;
@@ -461,27 +519,32 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
         if (!lastt) acc_xxn[i] = fma(mi, mun, acc_xxn[i]);
         if (valid) {
           const size_t o = (size_t)b * NN + i * N + c;
-          if (lastt && p.E_pair_xnxn) p.E_pair_xnxn[o] = (T > 1) ? exx : 0.0;
+          if (lastt) p.E_pair_xnxn[o] = (T > 1) ? exx : 0.0;
           if (first) {
-            if (p.E_init_xx) p.E_init_xx[o] = exx;
-            if (p.E_pair_xx) p.E_pair_xx[o] = (T > 1) ? acc_mid[i] + exx : 0.0;
-            if (p.E_pair_xxn) p.E_pair_xxn[o] = acc_xxn[i];
-            if (p.E_pair_xnxn && T > 1) p.E_pair_xnxn[o] = (lastt ? 0.0 : p.E_pair_xnxn[o]) + acc_mid[i];
+            p.E_init_xx[o] = exx;
+            p.E_pair_xx[o] = (T > 1) ? acc_mid[i] + exx : 0.0;
+            p.E_pair_xxn[o] = acc_xxn[i];
+            if (T > 1) p.E_pair_xnxn[o] = (lastt ? 0.0 : p.E_pair_xnxn[o]) + acc_mid[i];
           }
         }
       }
-      if (first && valid && p.E_init_x) p.E_init_x[(size_t)b * N + c] = mu;
+      if (first && valid) p.E_init_x[(size_t)b * N + c] = mu;
     }
     if (valid) {
-      if (p.E_node_x) p.E_node_x[bt * N + c] = mu;
-      if (p.E_node_xx) p.E_node_xx[bt * N + c] = diag;
-      if (S > 0 && p.samples) {
+      oEx[t * N] = mu;
+      oExx[t * N] = diag;
 #pragma unroll
-        for (int s = 0; s < S; ++s) p.samples[(bt * S + s) * N + c] = x[s];
-      }
+      for (int s = 0; s < S; ++s) oSmp[(t * S + s) * N] = x[s];
     }
     if (t >= 2 && t < T - 1) fetch(t - 2, T - t);   // the slot just consumed is free: prefetch
+    SVAE_CLK(10)
   }
+#ifdef SVAE_PACKED_CLOCKS
+  if (blockIdx.x == 0 && lane == 0)
+    printf("[clk N=%d S=%d B=%d T=%d] per step: top %lld | ldl %lld | dc/xi %lld | backsub %lld | m/stash %lld | predict %lld || "
+           "loop %lld | mbar %lld | Cgz+vec %lld | sigma %lld | emit %lld\n", N, S, p.B, T, clk_[0] / T, clk_[1] / T, clk_[2] / T,
+           clk_[3] / T, clk_[4] / T, clk_[5] / T, clk_[6] / T, clk_[7] / T, clk_[8] / T, clk_[9] / T, clk_[10] / T);
+#endif
 }
 
 }  // namespace svae

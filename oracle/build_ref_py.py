@@ -21,6 +21,8 @@ and puts two shim packages next to them:
     exactly as autograd@0f026ab's primitive_with_aux does on the forward pass)
   * toolz.curry
 
+(and one numpy-1.x rule, linalg.solve with a stack of vectors, see the shim source)
+
 The compiled Cython kernels of oracle/_ref (oracle/build_ref.py) are linked into the staged package so that
 svae.lds.lds_inference and svae.hmm import them exactly as the reference does.  pyhsmm (hmm_estep's backend,
 svae/hmm/hmm_inference.py:8-10) is absent: hmm_inference.py is NOT staged; callers get hmm_estep backed by the
@@ -90,18 +92,27 @@ TEXT_EDITS = {
 AUTOGRAD_SHIM = r'''
 """autograd -> numpy/scipy shim (no tape): see oracle/build_ref_py.py."""
 import sys, types
-import numpy, numpy.random, numpy.linalg, scipy, scipy.linalg, scipy.special
+import numpy as _numpy, numpy.random, numpy.linalg
+import scipy as _scipy, scipy.linalg, scipy.special
 
 def _mod(name, **attrs):
     m = types.ModuleType(name); m.__dict__.update(attrs); sys.modules[name] = m; return m
 
-sys.modules["autograd.numpy"] = numpy
-sys.modules["autograd.numpy.random"] = numpy.random
-sys.modules["autograd.numpy.linalg"] = numpy.linalg
-_sp = _mod("autograd.scipy", linalg=scipy.linalg, special=scipy.special)
-sys.modules["autograd.scipy.linalg"] = scipy.linalg
-sys.modules["autograd.scipy.special"] = scipy.special
-_sp.misc = _mod("autograd.scipy.misc", logsumexp=scipy.special.logsumexp)
+# autograd.numpy is numpy -- with ONE numpy-1.x rule restored: linalg.solve(a, b) treated b as a stack of VECTORS when
+# b.ndim == a.ndim - 1 (numpy 2 does so only for b.ndim == 1); the reference (2016) relies on it, e.g.
+# svae/distributions/gaussian.py:14 solve(J (T,N,N), h (T,N)).
+def _solve_np1(a, b):
+    a, b = _numpy.asarray(a), _numpy.asarray(b)
+    if b.ndim == a.ndim - 1 and b.ndim > 1:
+        return _numpy.linalg.solve(a, b[..., None])[..., 0]
+    return _numpy.linalg.solve(a, b)
+_linalg = _mod("autograd.numpy.linalg", __getattr__=lambda name: getattr(_numpy.linalg, name), solve=_solve_np1)
+_np = _mod("autograd.numpy", __getattr__=lambda name: getattr(_numpy, name), linalg=_linalg, random=_numpy.random)
+sys.modules["autograd.numpy.random"] = _numpy.random
+_sp = _mod("autograd.scipy", linalg=_scipy.linalg, special=_scipy.special)
+sys.modules["autograd.scipy.linalg"] = _scipy.linalg
+sys.modules["autograd.scipy.special"] = _scipy.special
+_sp.misc = _mod("autograd.scipy.misc", logsumexp=_scipy.special.logsumexp)
 
 def _no_tape(*a, **k):
     raise NotImplementedError("autograd shim: no differentiation (values only)")
@@ -111,7 +122,7 @@ def _flatten(value):
     """autograd.util.flatten: (1-D vector, unflatten)."""
     if isinstance(value, (tuple, list)):
         parts = [_flatten(v) for v in value]
-        vec = numpy.concatenate([p[0] for p in parts]) if parts else numpy.zeros(0)
+        vec = _numpy.concatenate([p[0] for p in parts]) if parts else _numpy.zeros(0)
         sizes = [p[0].size for p in parts]
         def unflatten(v, parts=parts, sizes=sizes, kind=type(value)):
             out, o = [], 0
@@ -119,8 +130,8 @@ def _flatten(value):
                 out.append(un(v[o:o + s])); o += s
             return kind(out) if kind is list else tuple(out)
         return vec, unflatten
-    arr = numpy.asarray(value, dtype=float)
-    return arr.ravel(), (lambda v, shape=arr.shape: numpy.reshape(v, shape))
+    arr = _numpy.asarray(value, dtype=float)
+    return arr.ravel(), (lambda v, shape=arr.shape: _numpy.reshape(v, shape))
 
 _mod("autograd.util", flatten=_flatten, make_tuple=lambda *a: tuple(a))
 
@@ -136,7 +147,7 @@ class TupleNode(tuple): pass
 class ListNode(list): pass
 _mod("autograd.container_types", TupleNode=TupleNode, ListNode=ListNode)
 _mod("autograd.convenience_wrappers", grad_and_aux=lambda f, *a, **k: _no_tape, value_and_grad=value_and_grad)
-import numpy as numpy_  # `import autograd.numpy as np` resolves through sys.modules
+numpy, scipy = _np, _sp    # `import autograd.numpy as np` binds the package attribute
 '''
 
 TOOLZ_SHIM = r'''
@@ -217,10 +228,18 @@ def slds_functions(ref) -> types.SimpleNamespace:
     u = ref.util
     ns = dict(np=np, npr=np.random, sys=_sys, make_tuple=lambda *a: tuple(a), contract=u.contract, scale=u.scale, unbox=u.unbox,
               sub=u.sub, add=u.add, map=lambda *a: list(map(*a)), zip=lambda *a: list(zip(*a)), xrange=range,
-              print_function=None,
-              natural_lds_estep_general=ref.lds_inference.natural_lds_estep_general,
-              natural_lds_inference_general=ref.lds_inference.natural_lds_inference_general,
-              natural_lds_sample=ref.lds_inference.natural_lds_sample)
+              print_function=None, tuplify=u.tuplify, shape=u.shape, randn_like=u.randn_like, partial=__import__('functools').partial,
+              )
+    # slds_svae.py:13-16 binds these three names to the CYTHON drivers (lds_inference.py:196-202,232-237,260-264); the
+    # reference's own canonicalisers (lds_inference.py:62-82) are applied first, as its python drivers do, so that the
+    # 4-tuple init parameters the SLDS builds and (J, h) node potentials reach the kernels in the shape they read
+    li = ref.lds_inference
+    canon = lambda natparam, node: ((li._canonical_init_params(natparam[0]), natparam[1]), li._canonical_node_params(tuple(node)))
+    ns["natural_lds_estep_general"] = lambda natparam, node: li.cython_natural_lds_estep_general(*canon(natparam, node))
+    ns["natural_lds_inference_general"] = \
+        lambda natparam, node, num_samples=1: li.cython_natural_lds_inference_general(*canon(natparam, node), num_samples=num_samples)
+    ns["natural_lds_sample"] = \
+        lambda natparam, node, num_samples=1: li.cython_natural_lds_sample(*canon(natparam, node), num_samples=num_samples)
     _exec_ranges(ns, ref.slds_source, [(80, 83), (86, 89), (92, 103), (108, 115), (131, 147), (150, 154), (159, 175),
                                        (229, 243)])
     return types.SimpleNamespace(**{k: v for k, v in ns.items() if callable(v) or k == "np"}, _ns=ns)

@@ -71,15 +71,27 @@ def optimize_local_meanfield(global_natparam, node, init_eps, tol=1e-2, max_iter
     pair_stats = (out(x[:, :-1], x[:, :-1]), out(x[:, :-1], x[:, 1:]), out(x[:, 1:], x[:, 1:]))
     log_pi, log_A = dirichlet_expectedstats(dir_nat), dirichlet_expectedstats(mdir_nat)
     dense_init, dense_pair = all_local(lds_global)
-    vlb, iters = None, 0
-    for iters in range(1, max_iter + 1):
+    # every sequence stops on its own bound (frozen afterwards): B sequences == B reference calls (slds_svae.py:159-175)
+    active = np.ones(B, dtype=bool)
+    sel = lambda new, old: np.where(active.reshape((-1,) + (1,) * (np.ndim(new) - 1)), new, old)
+    tsel = lambda new, old: tuple(tsel(a, b) if isinstance(a, tuple) else sel(a, b) for a, b in zip(new, old))
+    cur, prev, iters = None, None, np.zeros(B, dtype=int)
+    for it in range(1, max_iter + 1):
         hnode = arhmm_node(lds_global, init_stats, pair_stats)
         hmm_vlb, hmm_stats = H.hmm_estep((log_pi, log_A, hnode))
         Ez = hmm_stats[2]
         init_param = tuple(np.tensordot(Ez[:, 0], p, 1) for p in dense_init)
         pair_params = tuple(np.tensordot(Ez[:, 1:], p, 1) for p in dense_pair)
-        lds_vlb, init_stats, pair_stats, E_node = lds_estep_perseq(init_param, pair_params, node)
-        vlb, prev = hmm_vlb + lds_vlb, vlb
-        if prev is not None and np.abs(vlb - prev).max() < tol:
-            break
-    return hmm_stats, (init_stats, pair_stats, E_node), (init_param, pair_params), (hmm_vlb, lds_vlb), iters
+        lds_vlb, init_stats_n, pair_stats_n, E_node = lds_estep_perseq(init_param, pair_params, node)
+        new = (tuple(hmm_stats), (init_stats_n, pair_stats_n, E_node), (init_param, pair_params), (hmm_vlb, lds_vlb))
+        cur = new if cur is None else tsel(new, cur)
+        iters[active] = it
+        vlb = cur[3][0] + cur[3][1]
+        if prev is not None:
+            active = active & ~(np.abs(vlb - prev) < tol)
+            if not active.any():
+                break
+        prev = vlb
+        init_stats, pair_stats = cur[1][0], cur[1][1]
+    hmm_stats, lds_all, nat, vlbs = cur
+    return hmm_stats, lds_all, nat, vlbs, (int(iters[0]) if B == 1 else iters)

@@ -4,8 +4,8 @@ Block mean field alternating the HMM E-step (csrc/hmm_estep.cu) and the LDS E-st
 per-sequence pair parameters (csrc/lds_estep.cuh, INHOMOG), then one differentiable LDS pass + hmm_logZ
 (slds_svae.py:289-310).  Batched over B sequences: node potentials (B,T,n); the discrete/continuous factors of
 different sequences are independent, global statistics are summed over B.  With B = 1 (or unbatched (T,n)
-input) this is the reference's algorithm step for step; with B > 1 the coordinate ascent stops when EVERY
-sequence's bound moved less than `tol` (the reference's rule applied to the slowest sequence).
+input) this is the reference's algorithm step for step; with B > 1 every sequence stops on its OWN bound (its factors
+are frozen from then on), so a batch reproduces B independent reference runs.
 
 Global natural parameters: (hmm_global, lds_global) with hmm_global = (dir_natparam (K,), mdir_natparam (K,K))
 and lds_global = [(niw_natparam packed (n+2,n+2), mniw_natparam (A,B,C,d))] * K  (slds_svae.py:26-75).
@@ -165,25 +165,46 @@ def initialize_local_meanfield(node_potentials, eps=None, generator=None, pit=Fa
     return init_stats, pair_stats
 
 
+def _tree_where(mask, new, old):
+    """Per-sequence select over nested tuples of (B, ...) tensors."""
+    if isinstance(new, (tuple, list)):
+        return tuple(_tree_where(mask, a, b) for a, b in zip(new, old))
+    if not torch.is_tensor(new) or new.dim() == 0 or new.shape[0] != mask.shape[0]:
+        return new
+    return torch.where(mask.reshape((-1,) + (1,) * (new.dim() - 1)), new, old)
+
+
 def optimize_local_meanfield(global_natparam, node_potentials, tol=1e-2, max_iter=100, init_eps=None, generator=None,
                              dense=None, parallel_in_time="auto"):
-    """slds_svae.py:159-175.  The per-mode expected parameters (K small NIW/MNIW maps, loop-invariant) are
-    evaluated once per call instead of once per sweep.  parallel_in_time: "auto" | True | False (use_parallel_in_time)."""
+    """slds_svae.py:159-175, batched: EVERY sequence follows the reference's rule on its own bound -- it stops (its
+    factors are frozen) after the first sweep that moved its bound by less than `tol`, so B sequences in one call
+    reproduce B reference calls whatever their sweep counts.  The per-mode expected parameters (K small NIW/MNIW
+    maps, loop-invariant) are evaluated once per call instead of once per sweep.
+    parallel_in_time: "auto" | True | False (use_parallel_in_time)."""
     hmm_global, lds_global = global_natparam
     dense = dense if dense is not None else get_all_lds_local_natparams(lds_global)
     hmm_local = get_hmm_local_natparam(hmm_global)
     pit = use_parallel_in_time(node_potentials[1].shape[0], node_potentials[1].shape[1], parallel_in_time) \
         and not (torch.is_grad_enabled() and any(p.requires_grad for p in node_potentials[:2]))
     lds_stats = initialize_local_meanfield(node_potentials, init_eps, generator, pit)
-    local_vlb = None
+    B = node_potentials[1].shape[0]
+    active = torch.ones(B, dtype=torch.bool, device=node_potentials[1].device)
+    cur, prev_vlb = None, None
     for _ in range(max_iter):
         hmm_natparam, hmm_stats, hmm_vlb = hmm_meanfield(hmm_global, lds_global, lds_stats, dense, hmm_local, pit)
-        lds_natparam, lds_stats, lds_vlb = lds_meanfield(lds_global, node_potentials, hmm_stats, dense, pit)
-        local_vlb, prev = hmm_vlb + lds_vlb, local_vlb
-        if prev is not None and float((local_vlb - prev).abs().max()) < tol:   # the one host sync per sweep
-            break
+        lds_natparam, lds_stats_new, lds_vlb = lds_meanfield(lds_global, node_potentials, hmm_stats, dense, pit)
+        new = (hmm_natparam, hmm_stats, hmm_vlb, lds_natparam, lds_stats_new, lds_vlb)
+        cur = new if cur is None else _tree_where(active, new, cur)
+        vlb = cur[2] + cur[5]
+        if prev_vlb is not None:
+            active = active & ~((vlb - prev_vlb).abs() < tol)
+            if not bool(active.any()):                      # the one host sync per sweep
+                break
+        prev_vlb = vlb
+        lds_stats = cur[4]
     else:
         print('iteration limit reached', file=sys.stderr)
+    hmm_natparam, hmm_stats, hmm_vlb, lds_natparam, lds_stats, lds_vlb = cur
     return (hmm_stats, lds_stats), (hmm_natparam, lds_natparam), (hmm_vlb, lds_vlb)
 
 

@@ -29,3 +29,19 @@ def golden_natparams(d):
     pair = (d["J11"], d["J12"], d["J22"], float(d["pair_logZ"]))
     node = (d["node_J"], d["node_h"], d["node_logZ"])
     return init, pair, node
+
+
+def rel_err_elem(a, b, floor=1e-9):
+    """max over elements of |a-b| / (|b| + floor * max|b|): a wrong SMALL element shows up (rel_err would hide it)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if b.size == 0:
+        return 0.0
+    return float((np.abs(a - b) / (np.abs(b) + floor * max(np.abs(b).max(), 1e-300))).max())
+
+
+def slds_global_from_fixture(d, which="glob"):
+    """((dir, mdir), [(niw packed, (A, B, C, d))] * K) from a tests/golden/slds_*.npz fixture (NumPy)."""
+    K = d[which + "_dir"].shape[0]
+    return ((d[which + "_dir"], d[which + "_mdir"]),
+            [(d[which + "_niw"][k], tuple(d[which + "_mniw_" + c][k] for c in "ABCd")) for k in range(K)])

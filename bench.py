@@ -18,7 +18,7 @@ duration; `cpu_baseline` times the reference's own compiled Cython kernels (orac
 cores.  `--impl reference` times that reference CPU path alone (rank 0 only).
 """
 from __future__ import annotations
-import argparse, json, os, subprocess, sys, threading, time
+import argparse, json, os, subprocess, sys, time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -48,35 +48,75 @@ def measured_peak_hbm():
 # --------------------------------------------------------------------------------------------------
 
 def _cpu_worker(args):
-    """Runs `count` sequences of the named shape through the reference primitives; returns seconds."""
-    seed, count, n, T, S = args
+    """One process of the reference CPU arm: runs `count` units of work of the named kind, returns seconds.
+    kinds: lds_fwd / lds_fwd_bwd / hmm (the reference's own compiled Cython, oracle/_ref), *_port (NumPy restatement
+    when oracle/_ref is not built), slds_port / gmm_port (oracle restatements pinned to the reference's Python by
+    tests/test_reference_py_fixtures.py -- the reference's Python layer itself cannot run on the GPU box)."""
+    kind, seed, count, shape = args
     os.environ["OMP_NUM_THREADS"] = "1"
     import numpy as np
-    from oracle import ref, lds_numpy as O
-    rng = np.random.default_rng(0)
-    init, pair = O.rand_lds_natparam(n, rng)           # same dynamics for every worker (seed 0)
+    rng0 = np.random.default_rng(0)
     rng = np.random.default_rng(1000 + seed)
-    J, h, logZ = O.rand_node_potentials(min(count, 64), T, n, rng)
-    ref.lds_estep_one(init, pair, (J[0], h[0], logZ[0]), S, seed=seed)   # warm-up / import
-    t0 = time.perf_counter()
-    for i in range(count):
-        k = i % J.shape[0]
-        ref.lds_estep_one(init, pair, (J[k], h[k], logZ[k]), S)
-    return time.perf_counter() - t0
-
-
-def _cpu_port_worker(args):
-    seed, count, n, T, S = args
-    import numpy as np
-    from oracle import lds_numpy as O
-    rng = np.random.default_rng(0)
-    init, pair = O.rand_lds_natparam(n, rng)
-    rng = np.random.default_rng(1000 + seed)
-    node = O.rand_node_potentials(count, T, n, rng)
-    eps = rng.standard_normal((count, T, S, n))
-    t0 = time.perf_counter()
-    O.natural_lds_inference_general((init, pair), node, eps)
-    return time.perf_counter() - t0
+    if kind in ("lds_fwd", "lds_fwd_bwd"):
+        from oracle import ref, lds_numpy as O
+        n, T, S = shape
+        init, pair = O.rand_lds_natparam(n, rng0)           # same dynamics for every worker (seed 0)
+        J, h, logZ = O.rand_node_potentials(min(count, 64), T, n, rng)
+        if kind == "lds_fwd":
+            run = lambda k: ref.lds_estep_one(init, pair, (J[k], h[k], logZ[k]), S)
+        else:
+            gs = rng.standard_normal((T, S, n))
+            gst = ((np.zeros((n, n)), np.zeros(n), 0., 0.), (np.zeros((n, n)),) * 3 + (0.,), (J[0], h[0], np.zeros(T)))
+            run = lambda k: ref.lds_vjp_one(init, pair, (J[k], h[k], logZ[k]), gs, gst, -1.0, num_samples=S)
+        run(0)                                              # warm-up / import
+        t0 = time.perf_counter()
+        for i in range(count):
+            run(i % J.shape[0])
+        return time.perf_counter() - t0
+    if kind == "lds_fwd_port":
+        from oracle import lds_numpy as O
+        n, T, S = shape
+        init, pair = O.rand_lds_natparam(n, rng0)
+        node = O.rand_node_potentials(count, T, n, rng)
+        eps = rng.standard_normal((count, T, S, n))
+        t0 = time.perf_counter()
+        O.natural_lds_inference_general((init, pair), node, eps)
+        return time.perf_counter() - t0
+    if kind == "hmm":
+        from oracle import ref, hmm_numpy as H
+        K, T = shape
+        lp, lA = H.rand_hmm_natparam(K, rng0)
+        node = rng.standard_normal((min(count, 16), T, K))
+        ref.hmm_estep_slow((lp, lA, node[0]))
+        t0 = time.perf_counter()
+        for i in range(count):
+            ref.hmm_estep_slow((lp, lA, node[i % node.shape[0]]))   # hmm_logZ + hmm_logZ_grad (hmm_inference.py:65)
+        return time.perf_counter() - t0
+    if kind == "slds_port":
+        from oracle import slds_numpy as SO, lds_numpy as O
+        from svae_b200 import synthetic as SY
+        K, n, T = shape
+        glob = SY.slds_global_natparam(K, n, rng0)
+        t0 = time.perf_counter()
+        for i in range(count):
+            node = O.rand_node_potentials(1, T, n, rng)[:2]
+            hmm, lds_all, nat, _, _ = SO.optimize_local_meanfield(glob, node, rng.standard_normal((1, T, 1, n)))
+            init3 = (nat[0][0][0], nat[0][1][0], nat[0][2][0] + nat[0][3][0])
+            O.natural_lds_inference_general((init3, tuple(p[0] for p in nat[1])), node + (np.zeros((1, T)),),
+                                            rng.standard_normal((1, T, 1, n)))
+        return time.perf_counter() - t0
+    if kind == "gmm_port":
+        from oracle import gmm_numpy as G
+        from svae_b200 import synthetic as SY
+        K, N, T = shape
+        glob = SY.gmm_global_natparam(K, N, rng0)
+        t0 = time.perf_counter()
+        for i in range(count):
+            node = (-0.5 * np.log1p(np.exp(rng.standard_normal((T, N)))), 2.0 * rng.standard_normal((T, N)))
+            init = rng.random((T, K)); init /= init.sum(-1, keepdims=True)
+            G.local_meanfield(glob, node, init)
+        return time.perf_counter() - t0
+    raise ValueError(kind)
 
 
 def usable_cores():
@@ -91,27 +131,70 @@ def usable_cores():
     return n
 
 
-def cpu_reference_rate(n, T, S, target_seconds=4.0, cores=None):
-    """sequences/s of the reference CPU path using all host cores (one sequence stream per process)."""
-    import multiprocessing as mp
-    from oracle import ref
-    cores = cores or usable_cores()
-    kind = "reference" if ref.available() else "port"
-    worker = _cpu_worker if kind == "reference" else _cpu_port_worker
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        # calibrate on one core, then size the sample for ~target_seconds of wall time on all cores
-        t_one = worker((0, 8, n, T, S)) / 8
-        per_proc = max(8, int(target_seconds / max(t_one, 1e-6)))
+class CpuArm:
+    """The reference CPU path on all usable host cores: one spawn pool, one stream of work units per process."""
+
+    def __init__(self, cores=None):
+        import multiprocessing as mp
+        self.cores = cores or usable_cores()
+        self.pool = mp.get_context("spawn").Pool(self.cores)
+
+    def close(self):
+        self.pool.close(); self.pool.join()
+
+    def rate(self, kind, shape, unit_name, target_seconds=4.0, calib=4):
+        """units/s; a bounded sample sized for ~target_seconds of wall time."""
+        from oracle import ref
+        label = "reference"
+        if kind in ("lds_fwd", "lds_fwd_bwd", "hmm") and not ref.available():
+            if kind != "lds_fwd":
+                raise RuntimeError("oracle/_ref is not built")
+            kind, label = "lds_fwd_port", "port"
+        if kind.endswith("_port"):
+            label = "port"
+        t_one = self.pool.apply(_cpu_worker, ((kind, 0, calib, shape),)) / calib
+        per_proc = max(2, int(target_seconds / max(t_one, 1e-6)))
         t0 = time.perf_counter()
-        times = pool.map(worker, [(i, per_proc, n, T, S) for i in range(cores)])
+        times = self.pool.map(_cpu_worker, [(kind, i, per_proc, shape) for i in range(self.cores)])
         wall = time.perf_counter() - t0
-    total = per_proc * cores
-    # rate from the slowest worker's compute time (excludes process start-up and imports)
-    rate = total / max(times)
-    return dict(value=rate, unit=UNIT, cores=cores, kind=kind,
-                sample="%d sequences (d=%d,T=%d,S=%d) = %d per process x %d processes, %.1f s wall; "
-                       "single-core %.1f seq/s" % (total, n, T, S, per_proc, cores, wall, 1.0 / t_one))
+        total = per_proc * self.cores
+        return dict(value=total / max(times), unit=unit_name, cores=self.cores, kind=label,
+                    sample="%d units %s%s = %d per process x %d processes, %.1f s wall; single-core %.2f /s"
+                           % (total, kind, tuple(shape), per_proc, self.cores, wall, 1.0 / t_one))
+
+
+def cpu_reference_rate(n, T, S, target_seconds=4.0, cores=None):
+    """sequences/s of the reference CPU E-step (filter + smoother + sampler) using all host cores."""
+    arm = CpuArm(cores)
+    try:
+        return arm.rate("lds_fwd", (n, T, S), UNIT, target_seconds, calib=8)
+    finally:
+        arm.close()
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's threads (and so its first-touch pinned host buffers) to the NUMA node of its GPU: ranks on the
+    far socket otherwise push every PCIe copy across the inter-socket link.  Returns a short description."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return "numa: node %d has no allowed cpu" % node
+        os.sched_setaffinity(0, allowed)
+        return "numa: gpu %d (%s) -> node %d, %d cpus" % (index, bus, node, len(allowed))
+    except Exception as e:  # pragma: no cover
+        return "numa: not bound (%r)" % (e,)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -161,6 +244,9 @@ class ClockSampler:
 # main arms
 # --------------------------------------------------------------------------------------------------
 
+WORKLOAD = "LDS-SVAE E-step d=%d T=%d batch=%d per GPU S=%d" % (D, T_LEN, BATCH, NUM_SAMPLES)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -168,21 +254,87 @@ def run_reference(args):
     n, T, S = D, T_LEN, NUM_SAMPLES
     vals = []
     info = None
-    for i in range(args.warmup + args.steps):
-        # each step: a bounded sample of the workload on all host cores
-        info = cpu_reference_rate(n, T, S, target_seconds=max(1.0, min(4.0, 60.0 / (args.warmup + args.steps))))
-        if i >= args.warmup:
-            vals.append(info["value"])
+    arm = CpuArm()
+    try:
+        for i in range(args.warmup + args.steps):
+            # each step: a bounded sample of the workload on all host cores
+            info = arm.rate("lds_fwd", (n, T, S), UNIT, calib=8,
+                            target_seconds=max(1.0, min(4.0, 60.0 / (args.warmup + args.steps))))
+            if i >= args.warmup:
+                vals.append(info["value"])
+    finally:
+        arm.close()
     value = sum(vals) / len(vals)
     info["value"] = value
     line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=BATCH / value * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload="LDS-SVAE E-step d=%d T=%d batch=%d S=%d" % (n, T, BATCH, S),
+                config=dict(workload=WORKLOAD,
                             note="reference Cython kernels (oracle/_ref), one sequence per call, all host cores"),
                 cpu_baseline=info,
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
+
+
+def _time_gpu(torch, fn, iters=5, warm=2):
+    """ms per call (CUDA events on the current stream)."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def _roof(bytes_per_launch, ms, peak, flops=None):
+    r = dict(bound="hbm", achieved=bytes_per_launch / (ms * 1e-3) / 1e9, peak=peak, unit="GB/s",
+             frac=bytes_per_launch / (ms * 1e-3) / 1e9 / peak, kernel_ms=ms, algorithmic_bytes_per_launch=bytes_per_launch)
+    if flops is not None:
+        pk = 148 * 64 * 2 * 1.965e9
+        r["fp64"] = dict(achieved_tflops=flops / (ms * 1e-3) / 1e12, peak_tflops=pk / 1e12, frac=flops / (ms * 1e-3) / pk)
+    return r
+
+
+def run_parity(torch, K, ref_natparam, dev, n, T, S, nseq=8):
+    """the GPU path against the compiled reference (oracle/_ref; the NumPy port if it is not
+    built) on an `nseq`-sequence sub-batch IN THIS RUN, same inputs, same noise.  The oracle is the checker only."""
+    import numpy as np
+    from oracle import ref, lds_numpy as O
+    init, pair = ref_natparam
+    rng = np.random.default_rng(7)
+    J, h, logZ = O.rand_node_potentials(nseq, T, n, rng)
+    want = {k: [] for k in ("samples", "lognorm", "E_node_xx", "E_node_x", "E_init_xx", "E_pair_xx", "E_pair_xxn", "E_pair_xnxn")}
+    if ref.available():
+        kind, eps = "reference", []
+        for b in range(nseq):
+            o = ref.lds_estep_one(init, pair, (J[b], h[b], logZ[b]), S, seed=100 + b)
+            eps.append(o["eps"])
+            for k, v in (("samples", o["samples"]), ("lognorm", o["lognorm"]), ("E_node_xx", o["E_node"][0]),
+                         ("E_node_x", o["E_node"][1]), ("E_init_xx", o["E_init"][0]), ("E_pair_xx", o["E_pair"][0]),
+                         ("E_pair_xxn", o["E_pair"][1]), ("E_pair_xnxn", o["E_pair"][2])):
+                want[k].append(np.asarray(v))
+        eps = np.stack(eps)
+        want = {k: np.stack(v) for k, v in want.items()}
+    else:
+        kind = "port"
+        eps = rng.standard_normal((nseq, T, S, n))
+        smp, (Ei, Ep, En), ln = O.natural_lds_inference_general((init, pair), (J, h, logZ), eps)
+        want = dict(samples=smp, lognorm=ln, E_node_xx=En[0], E_node_x=En[1], E_init_xx=Ei[0], E_pair_xx=Ep[0],
+                    E_pair_xxn=Ep[1], E_pair_xnxn=Ep[2])
+    g = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float64, device=dev)
+    o = K.lds_estep_forward(tuple(g(x) for x in init), tuple(g(x) for x in pair), (g(J), g(h), g(logZ)), S, g(eps))
+    errs = {}
+    for k, w in want.items():
+        got = o[k].cpu().numpy()
+        errs[k] = float(np.abs(got - w).max() / max(np.abs(w).max(), 1e-300))
+    tol = 1e-5
+    worst = max(errs.values())
+    assert worst <= tol, ("in-run parity against the %s failed" % kind, errs)
+    return dict(checker=kind, sequences=nseq, max_rel_err=worst, tolerance=tol, per_output=errs)
 
 
 def run_ours(args):
@@ -196,6 +348,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local)        # before any pinned allocation
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -207,13 +360,12 @@ def run_ours(args):
     g = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float64, device=dev)
     gi, gp = tuple(g(x) for x in init), tuple(g(x) for x in pair)
     gen = torch.Generator(device=dev); gen.manual_seed(1000 + rank)
+    rnd = lambda *s: torch.randn(*s, dtype=torch.float64, device=dev, generator=gen)
+    softplus = torch.nn.functional.softplus
     NSETS = 2   # rotate input sets; each set (node potentials + noise = 196 MB) exceeds the 126 MB L2
     sets = []
     for _ in range(NSETS):
-        nJ = -0.5 * torch.nn.functional.softplus(torch.randn(B, T, n, dtype=torch.float64, device=dev, generator=gen))
-        nh = torch.randn(B, T, n, dtype=torch.float64, device=dev, generator=gen)
-        eps = torch.randn(B, T, S, n, dtype=torch.float64, device=dev, generator=gen)
-        sets.append((nJ, nh, eps))
+        sets.append((-0.5 * softplus(rnd(B, T, n)), rnd(B, T, n), rnd(B, T, S, n)))
 
     def step(i, kev=None):
         nJ, nh, eps = sets[i % NSETS]
@@ -271,6 +423,8 @@ def run_ours(args):
         E_node_x=torch.empty((B, T, n), dtype=torch.float64).pin_memory(),
         lognorm=torch.empty((B,), dtype=torch.float64).pin_memory())
     acc_host = torch.empty((4 * n * n + n + 1,), dtype=torch.float64).pin_memory()
+    for v in out_host.values():
+        v.zero_()                                # first touch on this rank's NUMA node
 
     def e2e_step(i):
         acc = K.lds_estep_host((gi, gp), (h_nJ, h_nh), S, out_host, chunks=E2E_CHUNKS, generator=gen, device=dev)
@@ -294,86 +448,145 @@ def run_ours(args):
     e2e_ms = float(t.item()) / e2e_steps
     h2d = h_nJ.numel() * 8 + h_nh.numel() * 8
     d2h = sum(v.numel() * 8 for v in out_host.values()) + acc_host.numel() * 8
+    del h_nJ, h_nh, out_host
 
-    # ---- secondary numbers (not the headline): training E-step (forward + VJP), HMM config ------------
-    extra = {}
-    if rank == 0 and not args.no_extra:
+    peak, peak_src = measured_peak_hbm()
+    extra = {"numa": numa}
+
+    # ---- strong scaling (BASELINE.json configs[3]): a GLOBAL batch of 4096 sequences sharded over the ranks, same
+    #      step (kernel + minibatch reduction + the one all-reduce); measured at every N, max over ranks ----------
+    if not args.no_extra:
+        strong = {}
+        for (n2, T2, Bg) in ((16, 200, 4096), (10, 200, 4096)):
+            Bl = Bg // world
+            i2, p2 = SY.lds_natparam(n2, np.random.default_rng(n2))
+            gi2, gp2 = tuple(g(x) for x in i2), tuple(g(x) for x in p2)
+            J2, h2, e2 = -0.5 * softplus(rnd(Bl, T2, n2)), rnd(Bl, T2, n2), rnd(Bl, T2, 1, n2)
+
+            def sstep():
+                o = K.lds_estep_forward(gi2, gp2, (J2, h2), 1, e2)
+                acc = K.lds_reduce_global_stats(o)
+                if world > 1:
+                    dist.all_reduce(acc)
+            barrier()
+            ms = _time_gpu(torch, sstep, iters=10, warm=3)
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+            strong["lds_d%d_T%d_global_batch_%d" % (n2, T2, Bg)] = dict(
+                n_gpus=world, sequences_per_gpu=Bl, ms_per_step=ms, value=Bg / (ms * 1e-3), unit=UNIT, scaling="strong")
+            del J2, h2, e2
+        extra["strong_scaling"] = strong
+
+    # ---- the other BASELINE.json configs (rank 0, N = 1): each with its roofline and the reference CPU rate -----------
+    cpu = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample="skipped")
+    if rank == 0:
+        arm = None
         try:
-            nJ, nh, eps = sets[0]
-            w = torch.randn(B, T, S, n, dtype=torch.float64, device=dev, generator=gen)
-            def fb():
-                o = K.lds_estep_forward(gi, gp, (nJ, nh), S, eps, save_for_bwd=True)
-                K.lds_estep_backward(o, dict(samples=w, E_node_xx=nJ, E_node_x=nh, lognorm=-torch.ones(B, dtype=torch.float64, device=dev)))
-            for _ in range(2):
-                fb()
-            torch.cuda.synchronize()
-            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(5):
-                fb()
-            b_.record(); torch.cuda.synchronize()
-            extra["lds_estep_fwd_plus_vjp_seq_per_s"] = B / (a.elapsed_time(b_) / 5 * 1e-3)
-            from svae_b200.hmm import hmm_inference as HK
-            lp, lA = SY.hmm_natparam(32, rng)
-            hnode = torch.randn(2048, 500, 32, dtype=torch.float64, device=dev, generator=gen)
-            nat = (g(lp), g(lA), hnode)
-            for _ in range(2):
-                HK.hmm_estep(nat)
-            torch.cuda.synchronize()
-            a.record()
-            for _ in range(5):
-                HK.hmm_estep(nat)
-            b_.record(); torch.cuda.synchronize()
-            extra["hmm_estep_K32_T500_B2048_seq_per_s"] = 2048 / (a.elapsed_time(b_) / 5 * 1e-3)
-            # the other LDS shapes BASELINE.json lists (parity-test cases; reported for context only)
-            for (n2, T2, B2) in ((8, 50, 256), (16, 200, 4096)):
-                i2, p2 = SY.lds_natparam(n2, rng)
-                gi2, gp2 = tuple(g(x) for x in i2), tuple(g(x) for x in p2)
-                J2 = -0.5 * torch.nn.functional.softplus(torch.randn(B2, T2, n2, dtype=torch.float64, device=dev, generator=gen))
-                h2 = torch.randn(B2, T2, n2, dtype=torch.float64, device=dev, generator=gen)
-                e2 = torch.randn(B2, T2, 1, n2, dtype=torch.float64, device=dev, generator=gen)
-                for _ in range(2):
-                    K.lds_estep_forward(gi2, gp2, (J2, h2), 1, e2)
-                torch.cuda.synchronize()
-                a.record()
-                for _ in range(5):
-                    K.lds_estep_forward(gi2, gp2, (J2, h2), 1, e2)
-                b_.record(); torch.cuda.synchronize()
-                extra["lds_estep_d%d_T%d_B%d_seq_per_s" % (n2, T2, B2)] = B2 / (a.elapsed_time(b_) / 5 * 1e-3)
-            # small-batch / long-T regime: one sequence of 20000 steps, sequential vs
-            # parallel-in-time driver (same outputs, tests/test_lds_pit_gpu.py)
-            from svae_b200.lds import lds_pit
-            T3 = 20000
-            J3 = -0.5 * torch.nn.functional.softplus(torch.randn(1, T3, n, dtype=torch.float64, device=dev, generator=gen))
-            h3 = torch.randn(1, T3, n, dtype=torch.float64, device=dev, generator=gen)
-            e3 = torch.randn(1, T3, 1, n, dtype=torch.float64, device=dev, generator=gen)
-            for name, fn in (("sequential", lambda: K.natural_lds_inference_general((gi, gp), (J3, h3), 1, e3)),
-                             ("parallel_in_time", lambda: lds_pit.natural_lds_inference_parallel((gi, gp), (J3, h3), 1, e3))):
-                for _ in range(2):
-                    fn()
-                torch.cuda.synchronize()
-                a.record()
-                for _ in range(5):
-                    fn()
-                b_.record(); torch.cuda.synchronize()
-                extra["lds_estep_d%d_T%d_B1_%s_ms" % (n, T3, name)] = a.elapsed_time(b_) / 5
-            from svae_b200.hmm import hmm_pit
-            hnode1 = torch.randn(1, 100000, 32, dtype=torch.float64, device=dev, generator=gen)
-            nat1 = (g(lp), g(lA), hnode1)
-            for name, fn in (("sequential", lambda: HK.hmm_estep(nat1)), ("parallel_in_time", lambda: hmm_pit.hmm_estep_parallel(nat1))):
-                for _ in range(2):
-                    fn()
-                torch.cuda.synchronize()
-                a.record()
-                for _ in range(5):
-                    fn()
-                b_.record(); torch.cuda.synchronize()
-                extra["hmm_estep_K32_T100000_B1_%s_ms" % name] = a.elapsed_time(b_) / 5
+            if args.no_cpu_baseline:
+                raise RuntimeError("skipped (--no-cpu-baseline)")
+            arm = CpuArm()
+            cpu = arm.rate("lds_fwd", (n, T, S), UNIT, target_seconds=4.0, calib=8)
         except Exception as e:  # pragma: no cover
-            extra["error"] = repr(e)
+            cpu = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample=repr(e))
+
+        def cpu_rate(kind, shape, unit, secs=2.0, calib=2):
+            if arm is None:
+                return None
+            try:
+                return arm.rate(kind, shape, unit, target_seconds=secs, calib=calib)
+            except Exception as e:  # pragma: no cover
+                return dict(value=None, kind="unavailable", sample=repr(e))
+
+        if not args.no_cpu_baseline:
+            try:
+                extra["parity"] = run_parity(torch, K, (init, pair), dev, n, T, S)
+            except AssertionError:
+                raise
+            except Exception as e:  # pragma: no cover
+                extra["parity"] = dict(error=repr(e))
+        if world == 1 and not args.no_extra:
+            cfg = {}
+            try:
+                # LDS d=8 T=50 B=256 and d=16 T=200 B=4096 (forward E-step)
+                for (n2, T2, B2) in ((8, 50, 256), (16, 200, 4096)):
+                    i2, p2 = SY.lds_natparam(n2, np.random.default_rng(n2))
+                    gi2, gp2 = tuple(g(x) for x in i2), tuple(g(x) for x in p2)
+                    J2, h2, e2 = -0.5 * softplus(rnd(B2, T2, n2)), rnd(B2, T2, n2), rnd(B2, T2, 1, n2)
+                    ms = _time_gpu(torch, lambda: K.lds_estep_forward(gi2, gp2, (J2, h2), 1, e2), iters=10)
+                    cfg["lds_d%d_T%d_B%d" % (n2, T2, B2)] = dict(
+                        value=B2 / (ms * 1e-3), unit=UNIT, ms=ms,
+                        roofline=_roof((alg_bytes_per_seq(n2, T2) + 8 * T2 * n2) * B2, ms, peak,
+                                       flops=T2 * (12 * n2 ** 3 + 10 * n2 ** 2) * B2),
+                        cpu_baseline=cpu_rate("lds_fwd", (n2, T2, 1), UNIT))
+                    del J2, h2, e2
+                # training E-step: forward (saving for the VJP) + reverse-mode kernel
+                nJ, nh, eps = sets[0]
+                w = rnd(B, T, S, n)
+                gl = -torch.ones(B, dtype=torch.float64, device=dev)
+
+                def fb():
+                    o = K.lds_estep_forward(gi, gp, (nJ, nh), S, eps, save_for_bwd=True)
+                    K.lds_estep_backward(o, dict(samples=w, E_node_xx=nJ, E_node_x=nh, lognorm=gl))
+                ms = _time_gpu(torch, fb, iters=5)
+                cfg["lds_fwd_plus_vjp_d%d_T%d_B%d" % (n, T, B)] = dict(
+                    value=B / (ms * 1e-3), unit=UNIT, ms=ms,
+                    roofline=_roof((alg_bytes_per_seq(n, T) + 8 * T * n + 40 * T * n) * B, ms, peak),   # + cotangents in, gradients out
+                    cpu_baseline=cpu_rate("lds_fwd_bwd", (n, T, S), UNIT))
+                del w
+                # HMM K=32 T=500 B=2048
+                from svae_b200.hmm import hmm_inference as HK
+                Kh, Th, Bh = 32, 500, 2048
+                lp, lA = SY.hmm_natparam(Kh, rng)
+                nat = (g(lp), g(lA), rnd(Bh, Th, Kh))
+                ms = _time_gpu(torch, lambda: HK.hmm_estep(nat), iters=5)
+                cfg["hmm_K%d_T%d_B%d" % (Kh, Th, Bh)] = dict(
+                    value=Bh / (ms * 1e-3), unit=UNIT, ms=ms,
+                    roofline=_roof(8 * (2 * Th * Kh + Kh * Kh + Kh + 1) * Bh, ms, peak),
+                    cpu_baseline=cpu_rate("hmm", (Kh, Th), UNIT))
+                del nat
+                # SLDS K=8 d=10 T=200 B=1024: run_inference (mean-field fixed point + differentiable evaluation)
+                from svae_b200.models import slds_svae as SL
+                Ks, Bs = 8, 1024
+                tg = lambda x: g(x)
+                (dn, mn), lds_np = SY.slds_global_natparam(Ks, n, np.random.default_rng(0))
+                sglob = ((tg(dn), tg(mn)), [(tg(a), tuple(tg(x) for x in b)) for a, b in lds_np])
+                sJ, sh = -0.5 * softplus(rnd(Bs, T, n)), rnd(Bs, T, n)
+                ms = _time_gpu(torch, lambda: SL.run_inference(sglob, sglob, (sJ, sh), 1, generator=gen), iters=3, warm=1)
+                cfg["slds_K%d_d%d_T%d_B%d_run_inference" % (Ks, n, T, Bs)] = dict(
+                    value=Bs / (ms * 1e-3), unit=UNIT, ms=ms,
+                    roofline=_roof(8 * (3 * T * n) * Bs, ms, peak),       # node potentials in, one sample path out
+                    cpu_baseline=cpu_rate("slds_port", (Ks, n, T), UNIT, secs=3.0, calib=1))
+                del sJ, sh
+                # GMM K=10 N=2 T=50: local mean field (whole fixed point in one launch), 256 minibatches per call
+                from svae_b200.models import gmm as GM
+                from svae_b200.distributions import dirichlet as DD, niw as NW
+                Kg, Ng, Tg, Bg = 10, 2, 50, 256
+                dg, ng = SY.gmm_global_natparam(Kg, Ng, np.random.default_rng(0))
+                lg, gg = DD.expectedstats(tg(dg)), NW.expectedstats(tg(ng))
+                gJ, gh = -0.5 * softplus(rnd(Bg, Tg, Ng)), 2.0 * rnd(Bg, Tg, Ng)
+                li = torch.rand(Bg, Tg, Kg, dtype=torch.float64, device=dev, generator=gen)
+                li = li / li.sum(-1, keepdim=True)
+                ms = _time_gpu(torch, lambda: GM.meanfield_fixed_point_cuda(lg, gg, gJ, gh, li), iters=5)
+                cfg["gmm_K%d_N%d_T%d_x%d_minibatches" % (Kg, Ng, Tg, Bg)] = dict(
+                    value=Bg / (ms * 1e-3), unit="minibatches/s", ms=ms,
+                    roofline=_roof(8 * (2 * Tg * Ng + 2 * Tg * Kg) * Bg, ms, peak),
+                    cpu_baseline=cpu_rate("gmm_port", (Kg, Ng, Tg), "minibatches/s"))
+                # small-batch / long-T regime: one sequence, sequential vs parallel in time
+                from svae_b200.lds import lds_pit
+                T3 = 20000
+                J3, h3, e3 = -0.5 * softplus(rnd(1, T3, n)), rnd(1, T3, n), rnd(1, T3, 1, n)
+                cfg["lds_d%d_T%d_B1_ms" % (n, T3)] = dict(
+                    sequential=_time_gpu(torch, lambda: K.natural_lds_inference_general((gi, gp), (J3, h3), 1, e3), iters=3),
+                    parallel_in_time=_time_gpu(torch, lambda: lds_pit.natural_lds_inference_parallel((gi, gp), (J3, h3), 1, e3), iters=3))
+            except Exception as e:  # pragma: no cover
+                cfg["error"] = repr(e)
+            extra["configs"] = cfg
+        if arm is not None:
+            arm.close()
 
     if rank == 0:
-        peak, peak_src = measured_peak_hbm()
         ab = alg_bytes_per_seq(n, T) * B + 8 * T * S * n * B     # + injected noise read
         achieved = ab / (kern_ms * 1e-3) / 1e9
         traffic = None
@@ -383,36 +596,36 @@ def run_ours(args):
                 traffic = json.load(open(tp)).get("lds_estep_fwd_d10_T200_B4096")
             except Exception:
                 traffic = None
-        try:
-            if args.no_cpu_baseline:
-                raise RuntimeError("skipped (--no-cpu-baseline)")
-            cpu = cpu_reference_rate(n, T, S, target_seconds=4.0)
-        except Exception as e:  # pragma: no cover
-            cpu = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample=repr(e))
+        flops = T * (12 * n ** 3 + 10 * n ** 2) * B
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
             ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
             data="synthetic",
-            config=dict(workload="LDS-SVAE E-step d=%d T=%d batch=%d per GPU S=%d" % (n, T, B, S),
+            config=dict(workload=WORKLOAD,
                         global_batch=world * B, parallelism="dp%d" % world,
                         l2="inputs per step (196 MB node potentials+noise, 1.4 GB stash) exceed the 126 MB L2; "
                            "%d input sets rotated" % NSETS,
                         step="fused filter+smoother+sampler kernel, 2-stage minibatch reduction of the global statistics"
                              + (", NCCL all-reduce of the %d-double accumulator" % (4 * n * n + n + 1) if world > 1 else "")),
             e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                     ms_per_step=e2e_ms, note="pinned host buffers; pieces of %s sequences pipelined (one copy stream per direction, kernels on 3 streams), persistent device buffers; noise drawn on device" % (E2E_CHUNKS,)),
+                     ms_per_step=e2e_ms,
+                     note="pinned host buffers (allocated on the GPU's NUMA node); pieces of %s sequences pipelined (one copy "
+                          "stream per direction, kernels on 3 streams), persistent device buffers; noise drawn on device; "
+                          "floor = the %.0f MB device-to-host copy of a step (~4.0 ms at the ~50 GB/s PCIe 5 x16 delivers)"
+                          % (E2E_CHUNKS, d2h / 1e6)),
             gpu_launches=int(launches),
             clocks=clk.summary(),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                          traffic=traffic, peak_source=peak_src, kernel="lds_estep_fwd_kernel<10,16,false>",
+                          traffic=traffic, peak_source=peak_src, kernel="lds_estep_packed_kernel<10,1,false>",
                           kernel_ms=kern_ms, algorithmic_bytes_per_launch=ab,
-                          note="fp64 ALU / shared-memory bound at ~30 flop/B, not HBM bound (SURVEY.md 8d, DESIGN.md 3)",
+                          note="fp64 FMA / shared-memory-instruction / dependent-issue bound at ~30 flop/B, not HBM bound "
+                               "(SURVEY.md 8d, DESIGN.md 3)",
                           # the second roofline SURVEY.md 8d asks for: algorithmic flops T(12n^3+10n^2) per sequence
                           # (the REFERENCE's operation count; this kernel's own formulation needs ~30% fewer) over the
                           # fp64 FMA peak 148 SMs x 64 FMA/clk x 2 x 1.965 GHz
-                          fp64=dict(achieved_tflops=T * (12 * n ** 3 + 10 * n ** 2) * B / (kern_ms * 1e-3) / 1e12,
+                          fp64=dict(achieved_tflops=flops / (kern_ms * 1e-3) / 1e12,
                                     peak_tflops=148 * 64 * 2 * 1.965e9 / 1e12,
-                                    frac=T * (12 * n ** 3 + 10 * n ** 2) * B / (kern_ms * 1e-3) / (148 * 64 * 2 * 1.965e9))),
+                                    frac=flops / (kern_ms * 1e-3) / (148 * 64 * 2 * 1.965e9))),
             cpu_baseline=cpu, extra=extra)
         print(json.dumps(line))
     if world > 1:

@@ -37,3 +37,42 @@ def hmm_natparam(K, rng):
     pi = rng.dirichlet(np.ones(K))
     A = rng.dirichlet(np.ones(K), size=K)
     return np.log(pi), np.log(A)
+
+
+def _niw_natparam(S, m, kappa, nu):
+    """svae/distributions/niw.py:39-42 (packed dense (N+2, N+2): ((S + kappa m m', kappa m, 0), (0, kappa, 0), (0, 0, nu)))."""
+    N = m.shape[0]
+    out = np.zeros((N + 2, N + 2))
+    out[:N, :N] = S + kappa * np.outer(m, m)
+    out[:N, N] = kappa * m
+    out[N, N], out[N + 1, N + 1] = kappa, nu
+    return out
+
+
+def _mniw_natparam(nu, S, M, K):
+    """svae/distributions/mniw.py:25-31: (K^-1, K^-1 M', S + M K^-1 M', nu)."""
+    Kinv = np.linalg.inv(K)
+    B = Kinv @ M.T
+    return (Kinv, B, S + M @ B, nu)
+
+
+def gmm_global_natparam(K, N, rng, alpha=1.0, niw_conc=1.0, random_scale=3.0):
+    """GMM global natural parameters in the structure of svae/models/gmm.py:33-43: (dirichlet (K,), niw (K,N+2,N+2))."""
+    dirichlet = alpha * rng.random(K)
+    niw = np.stack([_niw_natparam((N + niw_conc) * np.eye(N), random_scale * rng.standard_normal(N), niw_conc, N + niw_conc)
+                    for _ in range(K)])
+    return dirichlet, niw
+
+
+def slds_global_natparam(K, n, rng):
+    """SLDS global natural parameters in the structure of svae/models/slds_svae.py:26-75:
+    ((dir (K,), mdir (K,K)), [(niw packed (n+2,n+2), mniw (A, B, C, d))] * K), K well-conditioned random modes."""
+    dir_nat = 1.0 + rng.random(K)
+    mdir_nat = 1.0 + rng.random((K, K)) + 2.0 * np.eye(K)
+    lds = []
+    for _ in range(K):
+        niw = _niw_natparam((n + rng.random()) * np.eye(n), rng.standard_normal(n), 1.0 + rng.random(), n + 4. + rng.random())
+        A = rng.standard_normal((n, n))
+        A = 0.9 * A / np.abs(np.linalg.eigvals(A)).max()
+        lds.append((niw, _mniw_natparam(n + 4. + rng.random(), (n + rng.random()) * np.eye(n), A, (n + rng.random()) * np.eye(n))))
+    return (dir_nat, mdir_nat), lds

@@ -129,6 +129,25 @@ int svae_lds_estep_fwd_ex(
     const double* node_J_dense, const double* term_J,
     int* status, void* workspace, size_t workspace_bytes, void* stream);
 
+/* svae_lds_estep_fwd_ex with a per-sequence mask: sequences with active[b] == 0 are skipped and every output row
+ * of theirs keeps its previous content (active == NULL: all sequences run).  Used by the SLDS mean field, where each
+ * sequence stops iterating once ITS bound has converged (svae/models/slds_svae.py:171-172) while the batch goes on. */
+int svae_lds_estep_fwd_masked(
+    int B, int T, int n, int S, int flags,
+    const double* init_J, const double* init_h, const double* init_logZ,
+    const double* J11, const double* J12, const double* J22, const double* pair_logZ,
+    long long pair_stride_t, long long pair_stride_b,
+    const double* node_J, const double* node_h, const double* node_logZ,
+    const double* eps,
+    double* E_init_xx, double* E_init_x,
+    double* E_pair_xx, double* E_pair_xxn, double* E_pair_xnxn,
+    double* E_node_xx, double* E_node_x,
+    double* samples, double* lognorm,
+    double* Exx_t, double* Exxn_t,
+    double* msg_J_pred, double* msg_h_pred, const double* in_J_filt, const double* in_h_filt,
+    const double* node_J_dense, const double* term_J, const int* active,
+    int* status, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Parallel-in-time stage 1 (small batch, long T).  Cuts every sequence into
  * C = svae_lds_compose_num_chunks(T, chunk_len) chunks of chunk_len steps (the last may be shorter) and integrates the
@@ -219,6 +238,34 @@ int svae_lds_reduce_stats(int B, int n, const double* E_init_xx, const double* E
 int svae_hmm_estep(int B, int T, int K, int flags, const double* log_pi, const double* log_A,
                    const double* node, double* logZ, double* Ez0, double* Etrans, double* Ez,
                    void* stream);
+
+/* svae_hmm_estep with a per-sequence mask (see svae_lds_estep_fwd_masked). */
+int svae_hmm_estep_masked(int B, int T, int K, int flags, const double* log_pi, const double* log_A,
+                          const double* node, const int* active, double* logZ, double* Ez0, double* Etrans,
+                          double* Ez, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SLDS local mean field: the two contractions that couple the HMM factor and the LDS factor, batched over
+ * (sequence, time).  K discrete modes with per-mode parameters stacked on a leading K axis:
+ *   init_J (K,n,n), init_h (K,n), init_c (K) [= the two constants of the packed NIW statistics added], and
+ *   J11, J12, J22 (K,n,n), pair_logZ (K): the expected MNIW statistics, i.e. LDS pair potentials per mode.
+ * svae_slds_mix_params   (svae/models/slds_svae.py:92-103): out_init_* (B,..) = sum_k Ez[b,0,k] init_k,
+ *                        out_J11/J12/J22 (B,T-1,n,n), out_pair_logZ (B,T-1): at t the mix with Ez[b,t+1,k].
+ * svae_slds_node_potentials (slds_svae.py:131-147): node (B,T,K), node[b,0,k] = <E[x0 x0'], init_J_k> + <E[x0], init_h_k>
+ *                        + init_c_k;  node[b,t,k] = <E[x_{t-1}x_{t-1}'], J11_k> + <E[x_{t-1}x_t'], J12_k> + <E[x_t x_t'], J22_k>
+ *                        + pair_logZ_k, from the per-time second moments Exx_t (B,T,n,n), Exxn_t (B,T-1,n,n) that
+ *                        svae_lds_estep_fwd writes with SVAE_LDS_PER_T_PAIR_STATS, and Ex0 (B,n) = E[x_0].
+ * active: optional (B,) mask as in svae_lds_estep_fwd_masked.  K <= 32; returns SVAE_ERR_UNSUPPORTED when the K parameter
+ * blocks do not fit in shared memory (4 K n^2 doubles). */
+int svae_slds_mix_params(int B, int T, int n, int K, const double* Ez, const double* init_J, const double* init_h,
+                         const double* init_c, const double* J11, const double* J12, const double* J22,
+                         const double* pair_logZ, const int* active, double* out_init_J, double* out_init_h,
+                         double* out_init_c, double* out_J11, double* out_J12, double* out_J22, double* out_pair_logZ,
+                         void* stream);
+int svae_slds_node_potentials(int B, int T, int n, int K, const double* Exx_t, const double* Exxn_t, const double* Ex0,
+                              const double* init_J, const double* init_h, const double* init_c, const double* J11,
+                              const double* J12, const double* J22, const double* pair_logZ, const int* active,
+                              double* node, void* stream);
 
 /* Parallel-in-time HMM E-step, stages 1 and 2 (the sequential recursion is
  * svae/hmm/hmm_inference.py:44-51, its reverse sweep svae/hmm/cython_hmm_inference.pyx:126-166).

@@ -34,6 +34,10 @@ _SIGNATURES = {
     "svae_lds_estep_workspace_bytes": (_SZ, [_I] * 5),
     "svae_lds_estep_fwd": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 15 + [_P, _P, _SZ, _P]),
     "svae_lds_estep_fwd_ex": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 21 + [_P, _P, _SZ, _P]),
+    "svae_lds_estep_fwd_masked": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 22 + [_P, _P, _SZ, _P]),
+    "svae_hmm_estep_masked": (_I, [_I] * 4 + [_P] * 8 + [_P]),
+    "svae_slds_mix_params": (_I, [_I] * 4 + [_P] * 16 + [_P]),
+    "svae_slds_node_potentials": (_I, [_I] * 4 + [_P] * 12 + [_P]),
     "svae_lds_compose_num_chunks": (_I, [_I, _I]),
     "svae_hmm_compose_chunks": (_I, [_I] * 4 + [_P] * 4 + [_P]),
     "svae_hmm_chain_messages": (_I, [_I] * 3 + [_P] * 7 + [_P]),

@@ -53,7 +53,7 @@ extern "C" size_t svae_lds_estep_workspace_bytes(int B, int T, int n, int S, int
   return sizeof(double) * (size_t)B * (size_t)T * (size_t)svae::lds_record_stride(n, S, save);
 }
 
-extern "C" int svae_lds_estep_fwd_ex(
+extern "C" int svae_lds_estep_fwd_masked(
     int B, int T, int n, int S, int flags,
     const double* init_J, const double* init_h, const double* init_logZ,
     const double* J11, const double* J12, const double* J22, const double* pair_logZ,
@@ -66,7 +66,7 @@ extern "C" int svae_lds_estep_fwd_ex(
     double* samples, double* lognorm,
     double* Exx_t, double* Exxn_t,
     double* msg_J_pred, double* msg_h_pred, const double* in_J_filt, const double* in_h_filt,
-    const double* node_J_dense, const double* term_J,
+    const double* node_J_dense, const double* term_J, const int* active,
     int* status, void* workspace, size_t workspace_bytes, void* stream) {
   if (B <= 0 || T <= 0 || n <= 0 || S < 0) return SVAE_ERR_BAD_ARG;
   if (!init_J || !init_h || !node_J || !node_h || !workspace) return SVAE_ERR_BAD_ARG;
@@ -92,13 +92,35 @@ extern "C" int svae_lds_estep_fwd_ex(
   const bool per_t = (flags & SVAE_LDS_PER_T_PAIR_STATS) != 0;
   p.Exx_t = per_t ? Exx_t : nullptr; p.Exxn_t = per_t ? Exxn_t : nullptr;
   p.msg_J_pred = msg_J_pred; p.msg_h_pred = msg_h_pred; p.in_J_filt = in_J_filt; p.in_h_filt = in_h_filt;
-  p.node_J_dense = node_J_dense; p.term_J = term_J;
+  p.node_J_dense = node_J_dense; p.term_J = term_J; p.active = active;
   p.status = status;
   p.stash = static_cast<double*>(workspace);
   const bool inhomog = (pair_stride_t != 0 || pair_stride_b != 0) && T > 1;
   cudaError_t e = kLdsFwd[n](p, cpl, lps, inhomog, static_cast<cudaStream_t>(stream));
   g_svae_launches.fetch_add(1);
   return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
+}
+
+extern "C" int svae_lds_estep_fwd_ex(
+    int B, int T, int n, int S, int flags,
+    const double* init_J, const double* init_h, const double* init_logZ,
+    const double* J11, const double* J12, const double* J22, const double* pair_logZ,
+    long long pair_stride_t, long long pair_stride_b,
+    const double* node_J, const double* node_h, const double* node_logZ,
+    const double* eps,
+    double* E_init_xx, double* E_init_x,
+    double* E_pair_xx, double* E_pair_xxn, double* E_pair_xnxn,
+    double* E_node_xx, double* E_node_x,
+    double* samples, double* lognorm,
+    double* Exx_t, double* Exxn_t,
+    double* msg_J_pred, double* msg_h_pred, const double* in_J_filt, const double* in_h_filt,
+    const double* node_J_dense, const double* term_J,
+    int* status, void* workspace, size_t workspace_bytes, void* stream) {
+  return svae_lds_estep_fwd_masked(B, T, n, S, flags, init_J, init_h, init_logZ, J11, J12, J22, pair_logZ, pair_stride_t,
+                                   pair_stride_b, node_J, node_h, node_logZ, eps, E_init_xx, E_init_x, E_pair_xx, E_pair_xxn,
+                                   E_pair_xnxn, E_node_xx, E_node_x, samples, lognorm, Exx_t, Exxn_t, msg_J_pred, msg_h_pred,
+                                   in_J_filt, in_h_filt, node_J_dense, term_J, nullptr, status, workspace, workspace_bytes,
+                                   stream);
 }
 
 extern "C" int svae_lds_estep_fwd(

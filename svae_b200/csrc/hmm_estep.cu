@@ -27,6 +27,7 @@ struct HmmParams {
   int B, T, K, flags;
   const double *log_pi, *log_A, *node;   // (K), (K,K) row = from, (B,T,K)
   double *logZ, *Ez0, *Etrans, *Ez;      // (B), (B,K), (B,K,K), (B,T,K)
+  const int* active;                     // optional (B,) mask: sequences with active[b] == 0 are left untouched
 };
 
 template <int LPS>
@@ -73,8 +74,8 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
   const int sub = lane / LPS, j = lane % LPS;
   const int K = p.K, T = p.T;
   const long long seq = (long long)blockIdx.x * SPW + sub;
-  const bool valid = seq < p.B;
-  const long long b = valid ? seq : (long long)p.B - 1;
+  const long long b = seq < p.B ? seq : (long long)p.B - 1;
+  const bool valid = seq < p.B && (!p.active || p.active[b] != 0);
   const bool act = j < K;
   const bool fwd_only = (p.flags & 1) != 0;
   const bool store = act && valid && !fwd_only;
@@ -347,9 +348,9 @@ cudaError_t hmm_viterbi_launch(const ViterbiParams& p, cudaStream_t s) {
 
 extern std::atomic<uint64_t> g_svae_launches;
 
-extern "C" int svae_hmm_estep(int B, int T, int K, int flags, const double* log_pi, const double* log_A,
-                              const double* node, double* logZ, double* Ez0, double* Etrans, double* Ez,
-                              void* stream) {
+extern "C" int svae_hmm_estep_masked(int B, int T, int K, int flags, const double* log_pi, const double* log_A,
+                                     const double* node, const int* active, double* logZ, double* Ez0,
+                                     double* Etrans, double* Ez, void* stream) {
   if (B <= 0 || T <= 0 || K <= 0) return SVAE_ERR_BAD_ARG;
   if (!log_pi || !log_A || !node) return SVAE_ERR_BAD_ARG;
   const bool fwd_only = (flags & SVAE_HMM_LOGZ_ONLY) != 0;
@@ -359,9 +360,16 @@ extern "C" int svae_hmm_estep(int B, int T, int K, int flags, const double* log_
   p.B = B; p.T = T; p.K = K; p.flags = fwd_only ? 1 : 0;
   p.log_pi = log_pi; p.log_A = log_A; p.node = node;
   p.logZ = logZ; p.Ez0 = Ez0; p.Etrans = Etrans; p.Ez = Ez;
+  p.active = active;
   cudaError_t e = svae::hmm_estep_launch(p, static_cast<cudaStream_t>(stream));
   g_svae_launches.fetch_add(1);
   return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
+}
+
+extern "C" int svae_hmm_estep(int B, int T, int K, int flags, const double* log_pi, const double* log_A,
+                              const double* node, double* logZ, double* Ez0, double* Etrans, double* Ez,
+                              void* stream) {
+  return svae_hmm_estep_masked(B, T, K, flags, log_pi, log_A, node, nullptr, logZ, Ez0, Etrans, Ez, stream);
 }
 
 extern "C" size_t svae_hmm_viterbi_workspace_bytes(int B, int T, int K) {

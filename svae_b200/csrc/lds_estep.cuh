@@ -57,6 +57,7 @@ struct LdsFwdParams {
   const double *in_J_filt, *in_h_filt;      // optional inputs: run the backward sweeps from GIVEN filtered messages
   const double *node_J_dense;               // optional input: dense node precisions (B,T,n,n), natural form (added to node_J)
   const double *term_J;                     // optional input: dense precision (B,n,n) added at the LAST step only
+  const int* active;                        // optional (B,) mask: sequences with active[b] == 0 are left untouched
   int* status;
   double* stash;
 };
@@ -116,8 +117,8 @@ __global__ void SVAE_LDS_BOUNDS(N, CPL) lds_estep_fwd_kernel(const LdsFwdParams 
   const int sub = lane / LPS, l = lane % LPS;
   const int S = p.S, T = p.T;
   const long long seq = ((long long)blockIdx.x * nwarps + warp) * SPW + sub;
-  const bool valid = seq < p.B;
-  const long long b = valid ? seq : (long long)p.B - 1;
+  const long long b = seq < p.B ? seq : (long long)p.B - 1;
+  const bool valid = seq < p.B && (!p.active || p.active[b] != 0);
   // the column slots of this lane
   int c[CPL], sx[CPL], cm[CPL];
   bool mat[CPL], vec[CPL], smp[CPL];

@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
 
   const int sub = lane / N, c = lane - sub * N;
   const long long seq = (long long)blockIdx.x * SPW + sub;
-  const bool valid = seq < p.B;
-  const long long b = valid ? seq : (long long)p.B - 1;
+  const long long b = seq < p.B ? seq : (long long)p.B - 1;
+  const bool valid = seq < p.B && (!p.active || p.active[b] != 0);
   constexpr bool save = SAVE;
   constexpr int RS = (SAVE ? 4 * N + 1 + S : 2 * N + 1 + S) * NP;   // == lds_record_stride(N, S, SAVE)
 

@@ -1,7 +1,7 @@
 """Packed-dense Gaussian exponential family -- torch mirror of svae/distributions/gaussian.py:11-57."""
 from __future__ import annotations
 import torch
-from ..util import T
+from ..util import T, inv, solve, cholesky
 
 
 def pack_dense(A, b, *args):
@@ -30,8 +30,8 @@ def expectedstats(natparam):
     """gaussian.py:11-17."""
     neghalfJ, h, _, _ = unpack_dense(natparam)
     J = -2 * neghalfJ
-    Ex = torch.linalg.solve(J, h[..., None])[..., 0]
-    ExxT = torch.linalg.inv(J) + Ex[..., None] * Ex[..., None, :]
+    Ex = solve(J, h[..., None])[..., 0]
+    ExxT = inv(J) + Ex[..., None] * Ex[..., None, :]
     En = torch.ones(J.shape[:-2], dtype=J.dtype, device=J.device)
     return pack_dense(ExxT, Ex, En, En)
 
@@ -40,8 +40,8 @@ def logZ(natparam):
     """gaussian.py:19-25."""
     neghalfJ, h, a, b = unpack_dense(natparam)
     J = -2 * neghalfJ
-    L = torch.linalg.cholesky(J)
-    return 0.5 * (h * torch.linalg.solve(J, h[..., None])[..., 0]).sum() \
+    L = cholesky(J)
+    return 0.5 * (h * solve(J, h[..., None])[..., 0]).sum() \
         - torch.log(torch.diagonal(L, dim1=-1, dim2=-2)).sum() + (a + b).sum()
 
 
@@ -49,8 +49,8 @@ def natural_sample(natparam, num_samples, eps=None, generator=None):
     """gaussian.py:27-33: samples (..., S, N); eps (..., N, S) injects the noise."""
     neghalfJ, h, _, _ = unpack_dense(natparam)
     J = -2 * neghalfJ
-    L = torch.linalg.cholesky(J)
+    L = cholesky(J)
     if eps is None:
         eps = torch.randn(h.shape + (num_samples,), dtype=h.dtype, device=h.device, generator=generator)
     noise = torch.linalg.solve_triangular(T(L), eps, upper=True)
-    return torch.linalg.solve(J, h[..., None])[..., 0][..., None, :] + T(noise)
+    return solve(J, h[..., None])[..., 0][..., None, :] + T(noise)

@@ -2,7 +2,7 @@
 from __future__ import annotations
 import math
 import torch
-from ..util import symmetrize, outer
+from ..util import symmetrize, outer, inv, solve, cholesky
 from .gaussian import pack_dense, unpack_dense
 
 
@@ -28,7 +28,7 @@ def expectedstats(natparam, fudge=1e-8):
     S, m, kappa, nu = natural_to_standard(natparam)
     d = m.shape[-1]
     eye = torch.eye(d, dtype=m.dtype, device=m.device)
-    E_J = nu[..., None, None] * symmetrize(torch.linalg.inv(S)) + fudge * eye
+    E_J = nu[..., None, None] * symmetrize(inv(S)) + fudge * eye
     E_h = (E_J @ m[..., None])[..., 0]
     E_hTJinvh = d / kappa + (m * E_h).sum(-1)
     ar = torch.arange(d, dtype=m.dtype, device=m.device)

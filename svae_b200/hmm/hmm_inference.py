@@ -32,19 +32,24 @@ def _canon(natparam):
     return lp, lA, node.contiguous(), batched, dev
 
 
-def hmm_estep_forward(lp, lA, node, logz_only=False):
-    """One launch of the scaled forward(-backward) kernel on canonical (contiguous CUDA fp64) inputs."""
+def hmm_estep_forward(lp, lA, node, logz_only=False, active=None, out=None):
+    """One launch of the scaled forward(-backward) kernel on canonical (contiguous CUDA fp64) inputs.
+    active: optional (B,) int32 mask -- sequences with 0 are skipped and keep what `out` = (logZ, Ez0, Etrans, Ez) held."""
     B, T, K = node.shape
     dev = node.device
     new = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)
-    logZ = new(B)
-    Ez0 = Etrans = Ez = None
-    if not logz_only:
-        Ez0, Etrans, Ez = new(B, K), new(B, K, K), new(B, T, K)
+    if out is not None:
+        logZ, Ez0, Etrans, Ez = out
+    else:
+        logZ = new(B)
+        Ez0 = Etrans = Ez = None
+        if not logz_only:
+            Ez0, Etrans, Ez = new(B, K), new(B, K, K), new(B, T, K)
     P = _lib.ptr
-    code = _lib.lib().svae_hmm_estep(B, T, K, _lib.SVAE_HMM_LOGZ_ONLY if logz_only else 0, P(lp), P(lA), P(node),
-                                     P(logZ), P(Ez0), P(Etrans), P(Ez), _lib.stream_ptr(dev))
-    _lib.check(code, "svae_hmm_estep")
+    code = _lib.lib().svae_hmm_estep_masked(B, T, K, _lib.SVAE_HMM_LOGZ_ONLY if logz_only else 0, P(lp), P(lA), P(node),
+                                            None if active is None else ctypes.c_void_p(active.data_ptr()),
+                                            P(logZ), P(Ez0), P(Etrans), P(Ez), _lib.stream_ptr(dev))
+    _lib.check(code, "svae_hmm_estep_masked")
     return logZ, Ez0, Etrans, Ez
 
 

@@ -88,13 +88,14 @@ def _canonical_pair_params(pair_params, B, T, n, device):
 
 def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=None,
                       per_t_pair_stats=False, want_stats=True, generator=None, check_status=False,
-                      save_for_bwd=False, buffers=None, messages_out=False, from_messages=None, term_J=None):
+                      save_for_bwd=False, buffers=None, messages_out=False, from_messages=None, term_J=None, active=None):
     """One launch of the fused filter + smoother + sampler kernel.  Returns a dict of raw tensors.
     With save_for_bwd the workspace keeps what lds_estep_backward needs (returned as out["workspace"]).
     messages_out: also return the prediction messages (out["J_pred"], out["h_pred"]).
     from_messages = (J_filt (B,T,n,n), h_filt (B,T,n)): run the backward sweeps from these filtered messages
     instead of the kernel's own (node_params must then be zero).
-    term_J (B,n,n): dense natural-form precision added to the last step's node potential (lds_pit.py)."""
+    term_J (B,n,n): dense natural-form precision added to the last step's node potential (lds_pit.py).
+    active (B,) int32: sequences with 0 are skipped; their rows of every output keep what `buffers` held."""
     h_any = node_params[1]
     device = h_any.device if torch.is_tensor(h_any) and h_any.is_cuda else torch.device("cuda", torch.cuda.current_device())
     nJ, nh, nlogZ, batched = _canonical_node_params(node_params, device)
@@ -142,9 +143,9 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
         out["E_pair_xx"], out["E_pair_xxn"], out["E_pair_xnxn"] = \
             new(B, n, n, name="E_pair_xx"), new(B, n, n, name="E_pair_xxn"), new(B, n, n, name="E_pair_xnxn")
     if per_t_pair_stats or dense:
-        out["Exx_t"] = new(B, T, n, n)
+        out["Exx_t"] = new(B, T, n, n, name="Exx_t")
     if per_t_pair_stats and per_t_pair_stats != "xx":     # "xx": the per-time second moments alone (boundary chain)
-        out["Exxn_t"] = new(B, max(T - 1, 0), n, n)
+        out["Exxn_t"] = new(B, max(T - 1, 0), n, n, name="Exxn_t")
     if messages_out:
         out["J_pred"], out["h_pred"] = new(B, T, n, n), new(B, T, n)
     inJ = inh = None
@@ -165,7 +166,7 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
         work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=device)
     g = out.get
     P = _lib.ptr
-    code = L.svae_lds_estep_fwd_ex(
+    code = L.svae_lds_estep_fwd_masked(
         B, T, n, S, flags,
         P(iJ), P(ih), P(ilogZ),
         P(J11), P(J12), P(J22), P(plogZ), st, sb,
@@ -176,9 +177,10 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
         P(out["samples"]), P(out["lognorm"]),
         P(g("Exx_t")), P(g("Exxn_t")),
         P(g("J_pred")), P(g("h_pred")), P(inJ), P(inh), P(nJd), P(term_J),
+        None if active is None else ctypes.c_void_p(active.data_ptr()),
         ctypes.c_void_p(status.data_ptr()), ctypes.c_void_p(work.data_ptr()), wbytes,
         _lib.stream_ptr(device))
-    _lib.check(code, "svae_lds_estep_fwd_ex")
+    _lib.check(code, "svae_lds_estep_fwd_masked")
     out["status"] = status
     out["dense"] = dense
     if dense:

@@ -54,16 +54,32 @@ def make_slds_global_natparam(num_states, state_dim, alpha=5., sticky_bias=0., r
 
 # ---- per-mode local parameters ----------------------------------------------------------------------
 
-def get_all_lds_local_natparams(lds_global_natparams):
+def stack_lds_global(lds_global_natparams):
+    """[(niw (n+2,n+2), (A, B, C, d))] * K  ->  niw (K,n+2,n+2), (A (K,n,n), B, C, d (K,)): the per-mode exp-family maps
+    then run batched over the modes (a handful of launches instead of ~40 per mode)."""
+    if isinstance(lds_global_natparams, StackedLdsGlobal):
+        return lds_global_natparams
+    niw_nat = torch.stack([a for a, _ in lds_global_natparams])
+    mniw_nat = tuple(torch.stack([torch.as_tensor(b[j], dtype=niw_nat.dtype, device=niw_nat.device) for _, b in lds_global_natparams])
+                     for j in range(4))
+    return StackedLdsGlobal((niw_nat, mniw_nat))
+
+
+class StackedLdsGlobal(tuple):
+    """(niw_stack, mniw_stack) marker type."""
+
+
+def lds_global_expectedstats(lds_global_natparams):
+    """(niw.expectedstats (K,n+2,n+2) packed, mniw.expectedstats 4-tuple of (K,...)) -- models/lds.py:22-24 for all modes."""
+    niw_nat, mniw_nat = stack_lds_global(lds_global_natparams)
+    return niw.expectedstats(niw_nat), mniw.expectedstats(mniw_nat)
+
+
+def get_all_lds_local_natparams(lds_global_natparams, expected=None):
     """slds_svae.py:86-89: dense stacks over the K modes: init (J (K,n,n), h (K,n), a (K,), b (K,)) and
     pair (J11, J12, J22 (K,n,n), logZ (K,))."""
-    inits, pairs = [], []
-    for niw_nat, mniw_nat in lds_global_natparams:
-        inits.append(gaussian.unpack_dense(niw.expectedstats(niw_nat)))
-        pairs.append(mniw.expectedstats(mniw_nat))
-    dense_init = tuple(torch.stack(x) for x in zip(*inits))
-    dense_pair = tuple(torch.stack(x) for x in zip(*pairs))
-    return dense_init, dense_pair
+    e_niw, e_mniw = expected if expected is not None else lds_global_expectedstats(lds_global_natparams)
+    return tuple(gaussian.unpack_dense(e_niw)), tuple(e_mniw)
 
 
 def get_var_lds_local_natparam(lds_global_natparams, hmm_expected_stats, dense=None):
@@ -144,8 +160,8 @@ def get_hmm_vlb(lds_global_natparam, hmm_local_natparam, lds_expected_stats, den
     return hmm_logZ((init_params, pair_params, node_params))
 
 
-def initialize_local_meanfield(node_potentials, eps=None, generator=None, pit=False):
-    """slds_svae.py:203-226: statistics of ONE sample path of a 0.9-random-walk LDS given the node potentials."""
+def initialize_sample_path(node_potentials, eps=None, generator=None, pit=False):
+    """slds_svae.py:203-223: ONE sample path (B,T,n) of a 0.9-random-walk LDS given the node potentials."""
     h = node_potentials[1]
     N, dev = h.shape[-1], h.device
     eye = torch.eye(N, dtype=torch.float64, device=dev)
@@ -154,9 +170,14 @@ def initialize_local_meanfield(node_potentials, eps=None, generator=None, pit=Fa
     pair_params = (-0.5 * A.T @ A, A.T, -0.5 * eye, 0.)
     if pit:
         from ..lds.lds_pit import natural_lds_inference_parallel
-        x = natural_lds_inference_parallel((init_params, pair_params), node_potentials, 1, eps=eps, generator=generator)[0][:, :, 0]
-    else:
-        x = natural_lds_sample((init_params, pair_params), node_potentials, num_samples=1, eps=eps, generator=generator)[:, :, 0]
+        return natural_lds_inference_parallel((init_params, pair_params), node_potentials, 1, eps=eps, generator=generator)[0][:, :, 0]
+    return natural_lds_sample((init_params, pair_params), node_potentials, num_samples=1, eps=eps, generator=generator)[:, :, 0]
+
+
+def initialize_local_meanfield(node_potentials, eps=None, generator=None, pit=False, path=None):
+    """slds_svae.py:203-226: the statistics of that sample path (compute_stats, :206-215)."""
+    x = path if path is not None else initialize_sample_path(node_potentials, eps, generator, pit)
+    dev = x.device
     out = lambda u, v: u[..., :, None] * v[..., None, :]
     ones = torch.ones(x.shape[0], dtype=torch.float64, device=dev)
     init_stats = (out(x[:, 0], x[:, 0]), x[:, 0], ones, ones)
@@ -178,15 +199,91 @@ def optimize_local_meanfield(global_natparam, node_potentials, tol=1e-2, max_ite
                              dense=None, parallel_in_time="auto"):
     """slds_svae.py:159-175, batched: EVERY sequence follows the reference's rule on its own bound -- it stops (its
     factors are frozen) after the first sweep that moved its bound by less than `tol`, so B sequences in one call
-    reproduce B reference calls whatever their sweep counts.  The per-mode expected parameters (K small NIW/MNIW
-    maps, loop-invariant) are evaluated once per call instead of once per sweep.
-    parallel_in_time: "auto" | True | False (use_parallel_in_time)."""
+    reproduce B reference calls whatever their sweep counts.  The per-mode expected parameters (loop-invariant) are
+    evaluated once per call, batched over the K modes.
+
+    Default path (`_meanfield_device`): a sweep is four launches on persistent buffers -- svae_slds_node_potentials,
+    the HMM kernel, svae_slds_mix_params, the fused LDS kernel (inhomogeneous, per-sequence) -- all taking the (B,)
+    `active` mask, so converged sequences cost nothing and keep their factors; one small host read per sweep decides
+    whether any sequence is still active.  parallel_in_time ("auto" | True | False, use_parallel_in_time) selects the
+    chunk-parallel drivers for few long sequences (torch glue, `_meanfield_torch`)."""
     hmm_global, lds_global = global_natparam
     dense = dense if dense is not None else get_all_lds_local_natparams(lds_global)
     hmm_local = get_hmm_local_natparam(hmm_global)
     pit = use_parallel_in_time(node_potentials[1].shape[0], node_potentials[1].shape[1], parallel_in_time) \
         and not (torch.is_grad_enabled() and any(p.requires_grad for p in node_potentials[:2]))
-    lds_stats = initialize_local_meanfield(node_potentials, init_eps, generator, pit)
+    path = initialize_sample_path(node_potentials, init_eps, generator, pit)
+    B, T, n = node_potentials[1].shape
+    K = hmm_local[0].shape[0]
+    if not pit and K <= 32 and 8 * (4 * K * n * n + K * n + 2 * K) <= 200 * 1024:
+        return _meanfield_device(hmm_local, dense, node_potentials, path, tol, max_iter)
+    lds_stats = initialize_local_meanfield(node_potentials, path=path)
+    return _meanfield_torch(hmm_global, lds_global, dense, hmm_local, node_potentials, lds_stats, tol, max_iter, pit)
+
+
+def _meanfield_device(hmm_local, dense, node_potentials, path, tol, max_iter):
+    import ctypes
+    from .. import _lib
+    from ..lds.lds_inference import lds_estep_forward
+    from ..hmm.hmm_inference import hmm_estep_forward
+    nJ, nh = node_potentials[0].detach().contiguous(), node_potentials[1].detach().contiguous()
+    dev = nh.device
+    B, T, n = nh.shape
+    log_pi, log_A = (_lib.f64(x, dev).contiguous() for x in hmm_local)
+    K = log_pi.shape[0]
+    (iJ, ih, ia, ib), (J11, J12, J22, lZ) = dense
+    iJ, ih, J11, J12, J22, lZ = (_lib.f64(x, dev).contiguous() for x in (iJ, ih, J11, J12, J22, lZ))
+    ic = (_lib.f64(ia, dev) + _lib.f64(ib, dev)).contiguous()
+    new = lambda *s_: torch.empty(s_, dtype=torch.float64, device=dev)
+    Tm = max(T - 1, 1)
+    # per-time second moments the node-potential kernel reads: first those of the initial sample path (compute_stats,
+    # slds_svae.py:206-215), then the LDS kernel rewrites them in place every sweep
+    Exx_t, Exxn_t = new(B, T, n, n), new(B, Tm, n, n)
+    torch.mul(path[..., :, None], path[..., None, :], out=Exx_t)
+    if T > 1:
+        torch.mul(path[:, :-1, :, None], path[:, 1:, None, :], out=Exxn_t)
+    buf = dict(Exx_t=Exx_t, Exxn_t=Exxn_t if T > 1 else None, E_init_xx=new(B, n, n), E_init_x=path[:, 0].contiguous().clone(),
+               E_node_xx=new(B, T, n), E_node_x=new(B, T, n), lognorm=new(B),
+               E_pair_xx=new(B, n, n), E_pair_xxn=new(B, n, n), E_pair_xnxn=new(B, n, n),
+               status=torch.zeros(1, dtype=torch.int32, device=dev),
+               workspace=torch.empty(max(_lib.lib().svae_lds_estep_workspace_bytes(B, T, n, 0, 0), 16), dtype=torch.uint8, device=dev))
+    node = new(B, T, K)
+    hmm_out = (new(B), new(B, K), new(B, K, K), new(B, T, K))
+    m_iJ, m_ih, m_ic = new(B, n, n), new(B, n), new(B)
+    m11, m12, m22, mlZ = new(B, Tm, n, n), new(B, Tm, n, n), new(B, Tm, n, n), new(B, Tm)
+    active = torch.ones(B, dtype=torch.int32, device=dev)
+    L, P, st = _lib.lib(), _lib.ptr, _lib.stream_ptr(dev)
+    ap = ctypes.c_void_p(active.data_ptr())
+    prev = None
+    for _ in range(max_iter):
+        _lib.check(L.svae_slds_node_potentials(B, T, n, K, P(buf["Exx_t"]), P(Exxn_t), P(buf["E_init_x"]), P(iJ), P(ih), P(ic),
+                                               P(J11), P(J12), P(J22), P(lZ), ap, P(node), st), "svae_slds_node_potentials")
+        hmm_estep_forward(log_pi, log_A, node, active=active, out=hmm_out)
+        _lib.check(L.svae_slds_mix_params(B, T, n, K, P(hmm_out[3]), P(iJ), P(ih), P(ic), P(J11), P(J12), P(J22), P(lZ), ap,
+                                          P(m_iJ), P(m_ih), P(m_ic), P(m11), P(m12), P(m22), P(mlZ), st), "svae_slds_mix_params")
+        pair = (m11, m12, m22, mlZ) if T > 1 else (m11[:, :0], m12[:, :0], m22[:, :0], mlZ[:, :0])
+        o = lds_estep_forward((m_iJ, m_ih, m_ic), pair, (nJ, nh), 0, per_t_pair_stats=True, buffers=buf, active=active)
+        vlb = hmm_out[0] + o["lognorm"]
+        if prev is not None:
+            active.mul_(((vlb - prev).abs() >= tol).to(torch.int32))       # frozen sequences: vlb == prev, stay 0
+            if not bool(active.any()):                                    # the one host read per sweep
+                break
+        prev = vlb.clone()
+    else:
+        print('iteration limit reached', file=sys.stderr)
+    ones = lambda *s_: torch.ones(s_, dtype=torch.float64, device=dev)
+    hmm_vlb, Ez0, Etrans, Ez = hmm_out
+    E_init = (o["E_init_xx"], o["E_init_x"], ones(B), ones(B))
+    E_pair = (o["Exx_t"][:, :-1], o["Exxn_t"], o["Exx_t"][:, 1:], ones(B, T - 1)) if T > 1 else \
+        tuple(new(B, 0, n, n) for _ in range(3)) + (ones(B, 0),)
+    E_node = (o["E_node_xx"], o["E_node_x"], ones(B, T))
+    hmm_natparam = (log_pi, log_A, node)
+    lds_natparam = ((m_iJ, m_ih, m_ic), pair)
+    return ((Ez0, Etrans, Ez), (E_init, E_pair, E_node)), (hmm_natparam, lds_natparam), (hmm_vlb, o["lognorm"])
+
+
+def _meanfield_torch(hmm_global, lds_global, dense, hmm_local, node_potentials, lds_stats, tol, max_iter, pit):
+    """The same loop in torch glue around the E-step launches (parallel-in-time drivers; shapes beyond the glue kernels)."""
     B = node_potentials[1].shape[0]
     active = torch.ones(B, dtype=torch.bool, device=node_potentials[1].device)
     cur, prev_vlb = None, None
@@ -209,43 +306,53 @@ def optimize_local_meanfield(global_natparam, node_potentials, tol=1e-2, max_ite
 
 
 def get_global_stats(hmm_stats, lds_stats):
-    """slds_svae.py:229-243, summed over the batch; same structure as the global natural parameters."""
+    """slds_svae.py:229-243, summed over the batch; same structure as the global natural parameters.
+    One (K, B T) x (B T, n^2) product per statistic instead of a loop over the modes."""
     Ez0, Etrans, Ez = hmm_stats
     init_stats, pair_stats = lds_stats
     hmm_global = (Ez0.sum(0), Etrans.sum(0))
     K = Ez.shape[-1]
-    lds_global = []
-    for k in range(K):
-        w0 = Ez[:, 0, k]
-        gi = tuple((w0.reshape((-1,) + (1,) * (s.dim() - 1)) * s).sum(0) for s in init_stats)
-        wt = Ez[:, 1:, k]
-        gp = tuple((wt.reshape(wt.shape + (1,) * (s.dim() - 2)) * s).sum((0, 1)) for s in pair_stats)
-        lds_global.append((gaussian.pack_dense(gi[0], gi[1], gi[2], gi[3]), gp))
+    w0 = Ez[:, 0]                                                     # (B,K)
+    wt = Ez[:, 1:].reshape(-1, K)                                     # (B(T-1),K)
+    gi = tuple((w0.T @ s_.reshape(s_.shape[0], -1)).reshape((K,) + tuple(s_.shape[1:])) for s_ in init_stats)
+    gp = tuple((wt.T @ s_.reshape(wt.shape[0], -1)).reshape((K,) + tuple(s_.shape[2:])) for s_ in pair_stats)
+    packed = gaussian.pack_dense(gi[0], gi[1], gi[2], gi[3])          # (K,n+2,n+2)
+    lds_global = [(packed[k], tuple(x[k] for x in gp)) for k in range(K)]
     return hmm_global, lds_global
 
 
-def slds_prior_expectedstats(global_natparam):
+def slds_prior_expectedstats(global_natparam, lds_expected=None):
     """slds_svae.py:272-284."""
     hmm_natparam, lds_natparams = global_natparam
-    return hmm_prior_expectedstats(hmm_natparam), [(niw.expectedstats(a), mniw.expectedstats(b)) for a, b in lds_natparams]
+    e_niw, e_mniw = lds_expected if lds_expected is not None else lds_global_expectedstats(lds_natparams)
+    K = e_niw.shape[0]
+    return hmm_prior_expectedstats(hmm_natparam), [(e_niw[k], tuple(x[k] for x in e_mniw)) for k in range(K)]
 
 
 def slds_prior_logZ(natparam):
-    """slds_svae.py:254-269."""
+    """slds_svae.py:254-269 (the per-mode terms batched over K)."""
     (dir_nat, mdir_nat), lds_prior_natparams = natparam
-    hmm_term = dirichlet.logZ(dir_nat) + dirichlet.logZ(mdir_nat)
-    return hmm_term + sum(niw.logZ(a) + mniw.logZ(b) for a, b in lds_prior_natparams)
+    niw_nat, mniw_nat = stack_lds_global(lds_prior_natparams)
+    return dirichlet.logZ(dir_nat) + dirichlet.logZ(mdir_nat) + niw.logZ(niw_nat) + mniw.logZ(mniw_nat)
 
 
 def _tuplify(x):
     return tuple(_tuplify(y) for y in x) if isinstance(x, (list, tuple)) else x
 
 
-def slds_prior_vlb(global_natparam, prior_natparam):
-    """slds_svae.py:248-251."""
-    expected_stats = slds_prior_expectedstats(global_natparam)
-    return contract(sub(_tuplify(prior_natparam), _tuplify(global_natparam)), _tuplify(expected_stats)) \
-        - (slds_prior_logZ(prior_natparam) - slds_prior_logZ(global_natparam))
+def slds_prior_vlb(global_natparam, prior_natparam, lds_expected=None):
+    """slds_svae.py:248-251: <prior - global, E_global[stats]> - (logZ(prior) - logZ(global)), evaluated on the stacked
+    per-mode tensors (the inner product of the nested structures is the sum of the component inner products)."""
+    (g_dir, g_mdir), g_lds = global_natparam
+    (p_dir, p_mdir), p_lds = prior_natparam
+    g_niw, g_mniw = stack_lds_global(g_lds)
+    p_niw, p_mniw = stack_lds_global(p_lds)
+    e_niw, e_mniw = lds_expected if lds_expected is not None else lds_global_expectedstats(g_lds)
+    e_dir, e_mdir = hmm_prior_expectedstats((g_dir, g_mdir))
+    inner = ((p_dir - g_dir) * e_dir).sum() + ((p_mdir - g_mdir) * e_mdir).sum() + ((p_niw - g_niw) * e_niw).sum()
+    for pa, ga, ea in zip(p_mniw, g_mniw, e_mniw):
+        inner = inner + ((pa - ga) * ea).sum()
+    return inner - (slds_prior_logZ(prior_natparam) - slds_prior_logZ(global_natparam))
 
 
 def run_inference(prior_natparam, global_natparam, nn_potentials, num_samples, eps=None, init_eps=None, generator=None):
@@ -253,7 +360,8 @@ def run_inference(prior_natparam, global_natparam, nn_potentials, num_samples, e
     hmm_global_natparam, lds_global_natparam = global_natparam
     batched = nn_potentials[1].dim() == 3
     pots = tuple(nn_potentials[:2]) if batched else tuple(p[None] for p in nn_potentials[:2])
-    dense = get_all_lds_local_natparams(lds_global_natparam)
+    lds_expected = lds_global_expectedstats(lds_global_natparam)         # K modes in one batch; reused by the prior term
+    dense = get_all_lds_local_natparams(lds_global_natparam, lds_expected)
     with torch.no_grad():
         (hmm_stats, _), (hmm_local_natparam, lds_local_natparam), _ = \
             optimize_local_meanfield(global_natparam, unbox(pots), init_eps=init_eps, generator=generator, dense=dense)
@@ -262,7 +370,7 @@ def run_inference(prior_natparam, global_natparam, nn_potentials, num_samples, e
     hmm_vlb = get_hmm_vlb(lds_global_natparam, hmm_local_natparam, lds_stats, dense)
     global_lds_stats, local_lds_stats = lds_stats[:-1], lds_stats[-1]
     expected_stats = get_global_stats(hmm_stats, global_lds_stats)
-    global_vlb = slds_prior_vlb(global_natparam, prior_natparam)
+    global_vlb = slds_prior_vlb(global_natparam, prior_natparam, lds_expected)
     lds_vlb = lds_normalizer.sum() - contract(pots, local_lds_stats[:2])
     local_vlb = hmm_vlb.sum() + lds_vlb
     if not batched:

@@ -116,3 +116,21 @@ def split_into_batches(data, seq_len, generator=None):
     perm = torch.randperm(len(chunks), generator=generator).tolist()
     chunks = [chunks[i] for i in perm]
     return chunks, len(chunks)
+
+
+# ---- small dense linear algebra without a device->host round trip ----------------------------------------------
+# torch.linalg.inv / solve / cholesky read their LAPACK-style info word on the host to raise on singular input: on a
+# CUDA stream that is a synchronisation per call (the ~40 tiny exp-family maps of an SVI step would each stall the
+# launch queue).  The *_ex variants leave the check to the caller; on CUDA a singular / non-PD input then shows up
+# as inf / nan in the result (and in the kernels' `status` word), on the CPU the checked versions are kept.
+
+def inv(X):
+    return torch.linalg.inv_ex(X).inverse if X.is_cuda else torch.linalg.inv(X)
+
+
+def solve(A, B):
+    return torch.linalg.solve_ex(A, B).result if A.is_cuda else torch.linalg.solve(A, B)
+
+
+def cholesky(X):
+    return torch.linalg.cholesky_ex(X).L if X.is_cuda else torch.linalg.cholesky(X)

@@ -114,8 +114,8 @@ def test_slds_gradient_at_the_baseline_shape():
         (hmm_stats, _), (hmm_nat, lds_nat), _ = M.optimize_local_meanfield(glob, (nJ.detach(), nh.detach()), init_eps=g64(d["init_eps"][rows]))
         dense_init, dense_pair = M.get_all_lds_local_natparams(glob[1])
     cpu = lambda x: x.detach().cpu()
-    (iJ, ih, ia, ib), pair = lds_nat
-    init3 = (cpu(iJ), cpu(ih), cpu(ia + ib))
+    init_p, pair = lds_nat
+    init3 = (cpu(init_p[0]), cpu(init_p[1]), cpu(sum(init_p[2:])))
     pairc = tuple(cpu(p) for p in pair)
     Jn, hn = cpu(nJ).clone().requires_grad_(True), cpu(nh).clone().requires_grad_(True)
     smp, (E_init, E_pair, E_node), lognorm = OT.natural_lds_inference_general((init3, pairc), (Jn, hn), cpu(g64(d["eps"][rows])))

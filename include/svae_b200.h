@@ -49,6 +49,8 @@ extern "C" {
 #define SVAE_LDS_PER_T_PAIR_STATS 1 /* also write per-time second moments (inhomogeneous E_pair)   */
 #define SVAE_LDS_SAVE_FOR_BWD 2     /* keep what svae_lds_estep_bwd needs in the workspace         */
 #define SVAE_LDS_INIT_PER_SEQ 4     /* init_J (B,n,n), init_h (B,n), init_logZ (B): one per sequence */
+#define SVAE_LDS_BWD_MESSAGES_OUT 32 /* svae_lds_estep_bwd_ports: adjoint of the smoother/sampler alone   */
+#define SVAE_LDS_BWD_MESSAGES_IN 64  /* svae_lds_estep_bwd_ports: adjoint of the filter alone              */
 
 /* Library version / build info: "svae_b200 <version> sm_100a". */
 const char* svae_b200_version(void);
@@ -209,6 +211,33 @@ int svae_lds_estep_bwd_ex(
     const double* g_Exx_t, const double* g_Exxn_t,
     const double* g_E_node_xx, const double* g_E_node_x, const double* g_lognorm,
     double* g_node_J, double* g_node_h, double* g_node_J_dense,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* The reference differentiates its three primitives ONE BY ONE (primitive_with_aux, svae/lds/lds_inference.py:26-39):
+ * natural_smoother_general_grad and natural_sample_backward_grad return cotangents w.r.t. the forward MESSAGES
+ * (cython_lds_inference.pyx:236-306, 357-409), natural_filter_grad takes cotangents of the messages and of lognorm and
+ * returns those of the node potentials (pyx:92-145).  svae_lds_estep_bwd_ports is svae_lds_estep_bwd_ex with those ports:
+ *   flags | SVAE_LDS_BWD_MESSAGES_OUT : run the adjoint of the smoother + sampler only; g_msg_M (B,T,n,n), g_msg_h (B,T,n)
+ *       receive the cotangents of M_t = (filtered precision + J11, information form: filtered natural J = -1/2 (M_t - J11))
+ *       and of the filtered h_t; the covariance-form smoother never reads the prediction messages, whose cotangent is zero
+ *       (the reference's information-form RTS step splits the same total between the two; the totals pushed through
+ *       natural_filter_grad agree, tests/test_lds_primitives_gpu.py).  g_node_* may be NULL.
+ *   flags | SVAE_LDS_BWD_MESSAGES_IN  : run the adjoint of the filter only; in_g_M_pred / in_g_M_filt (B,T,n,n) and
+ *       in_g_h_pred / in_g_h_filt (B,T,n) are cotangents of the prediction / filtered messages (information form: of
+ *       J_info = -2 J_natural, i.e. -1/2 x the natural-form cotangent, symmetrised by the caller; any may be NULL),
+ *       g_lognorm that of the log-normaliser; outputs g_node_J / g_node_h (/ g_node_J_dense).
+ * The workspace is the one a forward launch with SVAE_LDS_SAVE_FOR_BWD filled (with or without message ports). */
+int svae_lds_estep_bwd_ports(
+    int B, int T, int n, int S, int flags,
+    const double* E_node_x, const double* samples, const double* eps,
+    const double* g_samples,
+    const double* g_E_init_xx, const double* g_E_init_x,
+    const double* g_E_pair_xx, const double* g_E_pair_xxn, const double* g_E_pair_xnxn,
+    const double* g_Exx_t, const double* g_Exxn_t,
+    const double* g_E_node_xx, const double* g_E_node_x, const double* g_lognorm,
+    double* g_node_J, double* g_node_h, double* g_node_J_dense,
+    double* g_msg_M, double* g_msg_h,
+    const double* in_g_M_pred, const double* in_g_h_pred, const double* in_g_M_filt, const double* in_g_h_filt,
     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

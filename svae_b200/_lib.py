@@ -15,6 +15,8 @@ SVAE_LDS_MAX_N = 16
 SVAE_LDS_PER_T_PAIR_STATS = 1
 SVAE_LDS_SAVE_FOR_BWD = 2
 SVAE_LDS_INIT_PER_SEQ = 4
+SVAE_LDS_BWD_MESSAGES_OUT = 32
+SVAE_LDS_BWD_MESSAGES_IN = 64
 SVAE_HMM_MAX_K = 32
 SVAE_GMM_MAX_N = 8
 SVAE_HMM_LOGZ_ONLY = 1
@@ -45,6 +47,7 @@ _SIGNATURES = {
     "svae_hmm_chain_viterbi": (_I, [_I] * 3 + [_P] * 5 + [_P]),
     "svae_lds_compose_chunks": (_I, [_I] * 4 + [_P] * 4 + [_LL, _LL] + [_P] * 9 + [_P, _P]),
     "svae_lds_estep_bwd_ex": (_I, [_I] * 5 + [_P] * 17 + [_P, _SZ, _P]),
+    "svae_lds_estep_bwd_ports": (_I, [_I] * 5 + [_P] * 23 + [_P, _SZ, _P]),
     "svae_lds_estep_bwd": (_I, [_I] * 5 + [_P] * 16 + [_P, _SZ, _P]),
     "svae_lds_reduce_stats_workspace_bytes": (_SZ, [_I]),
     "svae_lds_reduce_stats": (_I, [_I] * 2 + [_P] * 7 + [_P, _SZ, _P]),

@@ -142,7 +142,7 @@ extern "C" int svae_lds_estep_fwd(
                                nullptr, nullptr, nullptr, status, workspace, workspace_bytes, stream);
 }
 
-extern "C" int svae_lds_estep_bwd_ex(
+extern "C" int svae_lds_estep_bwd_ports(
     int B, int T, int n, int S, int flags,
     const double* E_node_x, const double* samples, const double* eps,
     const double* g_samples,
@@ -151,9 +151,15 @@ extern "C" int svae_lds_estep_bwd_ex(
     const double* g_Exx_t, const double* g_Exxn_t,
     const double* g_E_node_xx, const double* g_E_node_x, const double* g_lognorm,
     double* g_node_J, double* g_node_h, double* g_node_J_dense,
+    double* g_msg_M, double* g_msg_h,
+    const double* in_g_M_pred, const double* in_g_h_pred, const double* in_g_M_filt, const double* in_g_h_filt,
     void* workspace, size_t workspace_bytes, void* stream) {
   if (B <= 0 || T <= 0 || n <= 0 || S < 0) return SVAE_ERR_BAD_ARG;
-  if (!E_node_x || !workspace || (!g_node_J && !g_node_J_dense) || !g_node_h) return SVAE_ERR_BAD_ARG;
+  const bool s1 = (flags & SVAE_LDS_BWD_MESSAGES_OUT) != 0, s2 = (flags & SVAE_LDS_BWD_MESSAGES_IN) != 0;
+  if (s1 && s2) return SVAE_ERR_BAD_ARG;
+  if (s1 && (!g_msg_M || !g_msg_h)) return SVAE_ERR_BAD_ARG;
+  if (!E_node_x || !workspace) return SVAE_ERR_BAD_ARG;
+  if (!s1 && ((!g_node_J && !g_node_J_dense) || !g_node_h)) return SVAE_ERR_BAD_ARG;
   if (S > 0 && (!samples || !eps)) return SVAE_ERR_BAD_ARG;
   if (n > SVAE_LDS_MAX_N) return SVAE_ERR_UNSUPPORTED;
   const int lps = pick_lps(n, S);
@@ -168,10 +174,30 @@ extern "C" int svae_lds_estep_bwd_ex(
   p.g_Exx_t = g_Exx_t; p.g_Exxn_t = g_Exxn_t;
   p.g_E_node_xx = g_E_node_xx; p.g_E_node_x = g_E_node_x; p.g_lognorm = g_lognorm;
   p.g_node_J = g_node_J; p.g_node_h = g_node_h; p.g_node_J_dense = g_node_J_dense;
+  p.g_msg_M = g_msg_M; p.g_msg_h = g_msg_M ? g_msg_h : nullptr;
+  p.in_g_M_pred = in_g_M_pred; p.in_g_h_pred = in_g_h_pred; p.in_g_M_filt = in_g_M_filt; p.in_g_h_filt = in_g_h_filt;
+  p.flags = (flags & ~(SVAE_LDS_BWD_MESSAGES_OUT | SVAE_LDS_BWD_MESSAGES_IN)) | (s1 ? SVAE_LDS_BWD_SWEEP1_ONLY : 0) |
+            (s2 ? SVAE_LDS_BWD_SWEEP2_ONLY : 0);
   p.stash = static_cast<double*>(workspace);
   cudaError_t e = kLdsBwd[n](p, lps, static_cast<cudaStream_t>(stream));
   g_svae_launches.fetch_add(1);
   return e == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
+}
+
+extern "C" int svae_lds_estep_bwd_ex(
+    int B, int T, int n, int S, int flags,
+    const double* E_node_x, const double* samples, const double* eps,
+    const double* g_samples,
+    const double* g_E_init_xx, const double* g_E_init_x,
+    const double* g_E_pair_xx, const double* g_E_pair_xxn, const double* g_E_pair_xnxn,
+    const double* g_Exx_t, const double* g_Exxn_t,
+    const double* g_E_node_xx, const double* g_E_node_x, const double* g_lognorm,
+    double* g_node_J, double* g_node_h, double* g_node_J_dense,
+    void* workspace, size_t workspace_bytes, void* stream) {
+  return svae_lds_estep_bwd_ports(B, T, n, S, flags & ~(SVAE_LDS_BWD_MESSAGES_OUT | SVAE_LDS_BWD_MESSAGES_IN), E_node_x, samples,
+                                  eps, g_samples, g_E_init_xx, g_E_init_x, g_E_pair_xx, g_E_pair_xxn, g_E_pair_xnxn, g_Exx_t,
+                                  g_Exxn_t, g_E_node_xx, g_E_node_x, g_lognorm, g_node_J, g_node_h, g_node_J_dense, nullptr,
+                                  nullptr, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" int svae_lds_estep_bwd(

@@ -43,8 +43,15 @@ struct LdsBwdParams {
   // outputs
   double *g_node_J, *g_node_h;                             // (B,T,n)
   double *g_node_J_dense;                                  // optional (B,T,n,n): raw Pbar_t, caller symmetrises
+  // message ports (the reference's three primitives differentiated one by one, lds_inference.py:26-39)
+  double *g_msg_M, *g_msg_h;                               // out (sweep 1): cotangent of M_t = filtered precision + J11
+                                                           //   (information form, raw) (B,T,n,n) and of h_filtered (B,T,n)
+  const double *in_g_M_pred, *in_g_h_pred;                 // in (sweep 2 only): cotangents of the PREDICTION messages,
+  const double *in_g_M_filt, *in_g_h_filt;                 //   of the FILTERED messages (information form) (B,T,n,n), (B,T,n)
   double* stash;                                           // forward workspace (SAVE layout); overwritten
 };
+#define SVAE_LDS_BWD_SWEEP1_ONLY 8     // adjoint of the smoother / sampler alone: message cotangents out, no filter adjoint
+#define SVAE_LDS_BWD_SWEEP2_ONLY 16    // adjoint of the filter alone: message cotangents in
 
 // shared-memory doubles per sequence tile of the VJP kernel
 __host__ __device__ inline int lds_bwd_tile_doubles(int N, int S) {
@@ -99,6 +106,11 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
     mbar_fence_init();
   }
   constexpr bool per_t = PER_T;
+  const bool s2only = (p.flags & SVAE_LDS_BWD_SWEEP2_ONLY) != 0;
+  double* stash = p.stash + (size_t)b * T * RS;
+  const double* Ex = p.E_node_x + (size_t)b * T * N;
+  const double g_ln = p.g_lognorm ? p.g_lognorm[b] : 0.0;
+  if (!s2only) {
   // stage the (symmetrised) cotangents of the global statistics
   if (mat) {
 #pragma unroll
@@ -112,12 +124,20 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
   }
   __syncthreads();
 
-  double* stash = p.stash + (size_t)b * T * RS;
-  const double* Ex = p.E_node_x + (size_t)b * T * N;
-  const double g_ln = p.g_lognorm ? p.g_lognorm[b] : 0.0;
-
   // forward records were written through the generic proxy by another kernel: visible to TMA already.
   auto fetch1 = [&](int t) {   // sweep 1, time t -> slot t&1: record t prefix + Sigma_{t+1}
+#if !SVAE_LDS_TMA   // plain-load variant (sanitizer runs: racecheck cannot order async-proxy writes against generic reads)
+    {
+      double* dst = ring + (t & 1) * SLOT;
+      const double* src = stash + (size_t)t * RS;
+      for (int e = c; e < REC; e += LPS) dst[e] = src[e];
+      if (t + 1 < T) {
+        const double* s2 = stash + (size_t)(t + 1) * RS + (3 * N + 1 + S) * NP;
+        for (int e = c; e < N * NP; e += LPS) dst[REC + e] = s2[e];
+      }
+      return;
+    }
+#endif
     if (c == 0) {
       const uint32_t nb1 = (uint32_t)(REC * sizeof(double)), nb2 = (uint32_t)(N * NP * sizeof(double));
       const bool has_next = t + 1 < T;
@@ -213,7 +233,9 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
 #pragma unroll
       for (int i = 0; i < N; ++i) vbS[v * NP + i] = Sb[i];
     }
+#if SVAE_LDS_TMA
     mbar_wait(&bars[t & 1], (uint32_t)((t >> 1) & 1));
+#endif
     __syncwarp();
 
     // ---- the per-step reduction ----------------------------------------------------------------
@@ -397,6 +419,12 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
 #pragma unroll
       for (int i = 0; i < N; ++i) kt[i * NP + c] = Q[i];
       stash[(size_t)t * RS + N * NP + c] = fma(g_ln, mrow[c], wm[c]);   // f_t over the (dead) first row of W
+      if (p.g_msg_M) {
+        const size_t bt = (size_t)b * T + t;
+#pragma unroll
+        for (int i = 0; i < N; ++i) p.g_msg_M[bt * NN + i * N + c] = Q[i];
+        p.g_msg_h[bt * N + c] = fma(g_ln, mrow[c], wm[c]);
+      }
     }
     // carry to t+1
 #pragma unroll
@@ -406,6 +434,11 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
     if (t + 2 < T) fetch1(t + 2);
     __syncwarp();
   }
+  }   // !s2only
+  else {
+    __syncthreads();
+  }
+  if (p.flags & SVAE_LDS_BWD_SWEEP1_ONLY) return;
 
   // ================================ sweep 2: backward in time =================================
   // Q_t / f_t were written through the generic proxy: order them before the async-proxy reads
@@ -414,6 +447,14 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
   __syncwarp();
   // barrier phases continue from sweep 1: slot 0 completed ceil(T/2) times, slot 1 floor(T/2) times
   auto fetch2 = [&](int t, int j) {   // j-th step of sweep 2 (t = T-1-j) -> slot j&1
+#if !SVAE_LDS_TMA
+    {
+      double* dst = ring + (j & 1) * SLOT;
+      const double* src = stash + (size_t)t * RS;
+      for (int e = c; e < REC; e += LPS) dst[e] = src[e];
+      return;
+    }
+#endif
     if (c == 0) {
       const uint32_t nb = (uint32_t)(REC * sizeof(double));
       mbar_arrive_expect_tx(&bars[j & 1], nb);
@@ -435,13 +476,34 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
     const double* mrow = rec + 2 * N * NP;
     const double* frow = rec + N * NP;
     const double* Qm = rec + (2 * N + 1 + S) * NP;
-    const int used0 = (j & 1) == 0 ? (T + 1) / 2 : T / 2;
+    const int used0 = s2only ? 0 : ((j & 1) == 0 ? (T + 1) / 2 : T / 2);
+#if SVAE_LDS_TMA
     mbar_wait(&bars[j & 1], (uint32_t)((used0 + (j >> 1)) & 1));
+#else
+    (void)used0;
+    __syncwarp();
+#endif
     if (mat) {
       double Pn[N];
+      double hn_c;
+      const size_t btq = (size_t)b * T + t;
+      if (!s2only) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) Pn[i] = Qm[i * NP + c];
-      double hn_c = frow[c];
+        for (int i = 0; i < N; ++i) Pn[i] = Qm[i * NP + c];
+        hn_c = frow[c];
+      } else {
+        // seeds of the filter adjoint alone: message cotangents + the log-normaliser's own terms -g/2 (W + m m'), g m
+        const double* Wm = rec + N * NP;
+        const double m_c0 = mrow[c];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          double v = -0.5 * g_ln * fma(mrow[i], m_c0, Wm[i * NP + c]);
+          if (p.in_g_M_pred) v += p.in_g_M_pred[btq * NN + i * N + c];
+          if (p.in_g_M_filt) v += p.in_g_M_filt[btq * NN + i * N + c];
+          Pn[i] = v;
+        }
+        hn_c = g_ln * m_c0 + (p.in_g_h_pred ? p.in_g_h_pred[btq * N + c] : 0.0) + (p.in_g_h_filt ? p.in_g_h_filt[btq * N + c] : 0.0);
+      }
       if (t < T - 1) {
         // T1[:,c] = (Pb_{t+1} G')[:,c] = sum_k Pb[:,k] G[c][k];   Ghb = G hb_{t+1}
         double T1[N];
@@ -485,17 +547,21 @@ __global__ void __launch_bounds__(32, 8) lds_estep_bwd_kernel(const LdsBwdParams
 #pragma unroll
       for (int i = 0; i < N; ++i) Pb[i] = Pn[i];
       hb_c = hn_c;
+      // the node potential enters the FILTERED message only: the prediction message's own cotangent is carried on
+      // (it reaches the previous step through the recursion) but is not part of d/d node_t
+      const bool sub_pred = s2only && p.in_g_M_pred != nullptr;
       double diag = 0.0;
 #pragma unroll
       for (int i = 0; i < N; ++i)
-        if (i == c) diag = Pb[i];
+        if (i == c) diag = Pb[i] - (sub_pred ? p.in_g_M_pred[btq * NN + i * N + c] : 0.0);
       if (valid) {
         const size_t bt = ((size_t)b * T + t) * N + c;
         if (p.g_node_J) p.g_node_J[bt] = -2.0 * diag;
-        if (p.g_node_h) p.g_node_h[bt] = hb_c;
+        if (p.g_node_h) p.g_node_h[bt] = hb_c - ((s2only && p.in_g_h_pred) ? p.in_g_h_pred[bt] : 0.0);
         if (p.g_node_J_dense) {
 #pragma unroll
-          for (int i = 0; i < N; ++i) p.g_node_J_dense[((size_t)b * T + t) * NN + i * N + c] = Pb[i];
+          for (int i = 0; i < N; ++i)
+            p.g_node_J_dense[((size_t)b * T + t) * NN + i * N + c] = Pb[i] - (sub_pred ? p.in_g_M_pred[btq * NN + i * N + c] : 0.0);
         }
       }
     }

@@ -327,8 +327,13 @@ def lds_estep_host(natparam, node_host, num_samples, out_host, chunks=3, generat
     return _plans[key].run(natparam, node_host, out_host, generator)
 
 
-def lds_estep_backward(o, g):
+def lds_estep_backward(o, g, messages_out=False, message_seeds=None):
     """VJP w.r.t. (node_J, node_h): one launch of the reverse-mode kernel.
+
+    messages_out: adjoint of the smoother / sampler ALONE (natural_smoother_general_grad + natural_sample_backward_grad,
+    pyx:236-306,357-409): returns (g_M (B,T,n,n), g_h (B,T,n)), the raw cotangents of M_t = -2 J_filtered + J11_info and of
+    the filtered h.  message_seeds = (g_M_pred, g_h_pred, g_M_filt, g_h_filt) (information form, any None): adjoint of the
+    filter ALONE (natural_filter_grad, pyx:92-145) from cotangents of its messages (+ g["lognorm"]).
 
     `o` is the dict lds_estep_forward(..., save_for_bwd=True) returned (its workspace is consumed),
     `g` maps output names (samples, E_init_xx, E_init_x, E_pair_xx, E_pair_xxn, E_pair_xnxn, Exx_t, Exxn_t,
@@ -354,17 +359,27 @@ def lds_estep_backward(o, g):
     gJ = None if dense else torch.empty((B, T, n), dtype=torch.float64, device=dev)
     gh = torch.empty((B, T, n), dtype=torch.float64, device=dev)
     P = _lib.ptr
-    code = _lib.lib().svae_lds_estep_bwd_ex(
-        B, T, n, S, 0,
+    flags, gM, gmh = 0, None, None
+    seeds = (None,) * 4
+    if messages_out:
+        flags = _lib.SVAE_LDS_BWD_MESSAGES_OUT
+        gM, gmh = torch.empty((B, T, n, n), dtype=torch.float64, device=dev), torch.empty((B, T, n), dtype=torch.float64, device=dev)
+    elif message_seeds is not None:
+        flags = _lib.SVAE_LDS_BWD_MESSAGES_IN
+        seeds = tuple(None if x is None else _lib.f64(x, dev).contiguous() for x in message_seeds)
+    code = _lib.lib().svae_lds_estep_bwd_ports(
+        B, T, n, S, flags,
         P(o["E_node_x"]), P(o["samples"]), P(o["eps"]),
         P(keep["samples"]), P(keep["E_init_xx"]), P(keep["E_init_x"]),
         P(keep["E_pair_xx"]), P(keep["E_pair_xxn"]), P(keep["E_pair_xnxn"]),
         P(keep["Exx_t"]), P(keep["Exxn_t"]),
         P(keep["E_node_xx"]), P(keep["E_node_x"]), P(keep["lognorm"]),
-        P(gJ), P(gh), P(gJd),
+        P(gJ), P(gh), P(gJd), P(gM), P(gmh), P(seeds[0]), P(seeds[1]), P(seeds[2]), P(seeds[3]),
         ctypes.c_void_p(o["workspace"].data_ptr()), o["workspace_bytes"], _lib.stream_ptr(dev))
-    _lib.check(code, "svae_lds_estep_bwd_ex")
+    _lib.check(code, "svae_lds_estep_bwd_ports")
     o["workspace"] = None   # single use, like the reference's intermediates
+    if messages_out:
+        return gM, gmh
     if dense:               # d/dJ_node of a symmetric port: -2 sym(Pbar_t)
         gJ = -(gJd + gJd.transpose(-1, -2))
     return gJ, gh
@@ -518,30 +533,111 @@ cython_natural_lds_sample = natural_lds_sample
 
 # ------------------------------------------------------------------------------------------------
 # the reference's three primitives (lds_inference.py:18-39, cython_lds_inference.pyx:28,149,310), each one
-# launch of the same fused kernel with the message ports of svae_lds_estep_fwd_ex open.  Forward values
-# only: gradients flow through the fused natural_lds_* entry points above.
+# launch of the same fused kernel with the message ports of svae_lds_estep_fwd_ex open -- and each DIFFERENTIABLE
+# on its own like the reference's primitive_with_aux wiring (lds_inference.py:26-39): the filter w.r.t. its node
+# potentials given cotangents of its messages (natural_filter_grad), the smoother and the sampler w.r.t. the
+# forward messages (natural_smoother_general_grad, natural_sample_backward_grad), through the sweep-2-only /
+# sweep-1-only modes of the reverse-mode kernel (svae_lds_estep_bwd_ports).
 # ------------------------------------------------------------------------------------------------
+
+def _sym_info(gJ_nat):
+    """cotangent of a natural-form precision message J -> cotangent of J_info = -2 J (symmetric part)."""
+    return None if gJ_nat is None else -0.25 * (gJ_nat + gJ_nat.transpose(-1, -2))
+
+
+class _FilterFn(torch.autograd.Function):
+    """natural_filter_forward_general with natural_filter_grad as its VJP (defgrad on argument 2, lds_inference.py:27-29)."""
+
+    @staticmethod
+    def forward(ctx, nJ, nh, nlogZ, init_params, pair_params):
+        node = (nJ, nh) if nlogZ is None else (nJ, nh, nlogZ)
+        o = lds_estep_forward(init_params, pair_params, node, 0, None, want_stats=False, messages_out=True, save_for_bwd=True)
+        J_filt = o["J_pred"] + (torch.diag_embed(nJ) if nJ.dim() == 3 else nJ)
+        h_filt = o["h_pred"] + nh
+        ctx.state = {k: o[k] for k in ("B", "T", "n", "S", "dense", "eps", "workspace", "workspace_bytes")}
+        ctx.has_logZ = nlogZ is not None
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(o["E_node_x"], o["lognorm"])
+        return o["J_pred"], o["h_pred"], J_filt, h_filt, o["lognorm"]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gJp, ghp, gJf, ghf, gln):
+        E_node_x, lognorm = ctx.saved_tensors
+        o = dict(ctx.state, E_node_x=E_node_x, samples=None, lognorm=lognorm)
+        B, T = o["B"], o["T"]
+        try:
+            gJ, gh = lds_estep_backward(o, dict(lognorm=gln), message_seeds=(_sym_info(gJp), ghp, _sym_info(gJf), ghf))
+        finally:
+            ctx.state = None
+        g_logZ = gln[:, None].expand(B, T).contiguous() if (ctx.has_logZ and gln is not None) else None
+        return gJ, gh, g_logZ, None, None
+
 
 def natural_filter_forward_general(init_params, pair_params, node_params):
     """((prediction_messages, filtered_messages), lognorm) -- cython_lds_inference.pyx:28-90.
 
     Messages are natural-parameter pairs (J (B,T,n,n), h (B,T,n)) [no B axis for unbatched node_params];
-    the filtered message is the prediction message conditioned on the node potential (pyx:64-66)."""
-    o = lds_estep_forward(init_params, pair_params, node_params, 0, None, want_stats=False, messages_out=True)
-    device = o["J_pred"].device
-    nJ, nh, _, _ = _canonical_node_params(node_params, device)
-    J_filt = o["J_pred"] + (torch.diag_embed(nJ) if nJ.dim() == 3 else nJ)
-    h_filt = o["h_pred"] + nh
-    msgs = ((o["J_pred"], o["h_pred"]), (J_filt, h_filt))
-    if not o["batched"]:
+    the filtered message is the prediction message conditioned on the node potential (pyx:64-66).
+    Differentiable w.r.t. the node potentials (natural_filter_grad, pyx:92-145)."""
+    h_any = node_params[1]
+    device = h_any.device if torch.is_tensor(h_any) and h_any.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    nJ, nh, nlogZ, batched = _canonical_node_params(node_params, device)
+    if torch.is_grad_enabled() and any(torch.is_tensor(x) and x.requires_grad for x in node_params):
+        J_pred, h_pred, J_filt, h_filt, lognorm = _FilterFn.apply(nJ, nh, nlogZ, init_params, pair_params)
+    else:
+        o = lds_estep_forward(init_params, pair_params, (nJ, nh, nlogZ), 0, None, want_stats=False, messages_out=True)
+        J_pred, h_pred, lognorm = o["J_pred"], o["h_pred"], o["lognorm"]
+        J_filt = J_pred + (torch.diag_embed(nJ) if nJ.dim() == 3 else nJ)
+        h_filt = h_pred + nh
+    msgs = ((J_pred, h_pred), (J_filt, h_filt))
+    if not batched:
         msgs = tuple(tuple(x[0] for x in m) for m in msgs)
-        return msgs, o["lognorm"][0]
-    return msgs, o["lognorm"]
+        return msgs, lognorm[0]
+    return msgs, lognorm
+
+
+class _MessagesFn(torch.autograd.Function):
+    """Smoother and/or sampler from given filtered messages; VJP w.r.t. the messages (defgrad on argument 0,
+    lds_inference.py:31-39)."""
+
+    @staticmethod
+    def forward(ctx, J_filt, h_filt, eps, pair_params, S, per_t, want_stats):
+        B, T, n = h_filt.shape
+        dev = h_filt.device
+        zero = torch.zeros((B, T, n), dtype=torch.float64, device=dev)
+        init = (-0.5 * torch.eye(n, dtype=torch.float64, device=dev), zero[0, 0], 0.)   # overridden by the messages
+        o = lds_estep_forward(init, pair_params, (zero, zero, None), S, eps, per_t_pair_stats=per_t, want_stats=want_stats,
+                              from_messages=(J_filt, h_filt), save_for_bwd=True)
+        names = ["samples"] if S else []
+        if want_stats:
+            names += [k for k in (_OUT_PER_T if per_t else _OUT_HOMOG) if k not in ("samples", "lognorm")]
+        ctx.names = names
+        ctx.state = {k: o[k] for k in ("B", "T", "n", "S", "dense", "eps", "workspace", "workspace_bytes")}
+        ctx.set_materialize_grads(False)
+        smp = o["samples"] if S else torch.empty(0, dtype=torch.float64, device=dev)
+        ctx.has_samples = bool(S)
+        ctx.save_for_backward(o["E_node_x"], smp, o["lognorm"])
+        return tuple(o[k] for k in names)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gs):
+        g = dict(zip(ctx.names, gs))
+        E_node_x, smp, lognorm = ctx.saved_tensors
+        o = dict(ctx.state, E_node_x=E_node_x, samples=smp if ctx.has_samples else None, lognorm=lognorm)
+        try:
+            gM, gmh = lds_estep_backward(o, g, messages_out=True)
+        finally:
+            ctx.state = None
+        # M_t = -2 J_filtered + J11_info: d/dJ_filtered (natural form, symmetric port) = -2 sym(d/dM)
+        return -(gM + gM.transpose(-1, -2)), gmh, None, None, None, None, None
 
 
 def _messages_run(forward_messages, pair_params, num_samples, eps, generator, want_stats):
     _, (J_filt, h_filt) = forward_messages
     device = h_filt.device if torch.is_tensor(h_filt) and h_filt.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    needs_grad = torch.is_grad_enabled() and any(torch.is_tensor(x) and x.requires_grad for x in (J_filt, h_filt))
     J_filt, h_filt = _lib.f64(J_filt, device), _lib.f64(h_filt, device)
     batched = h_filt.dim() == 3
     if not batched:
@@ -549,23 +645,40 @@ def _messages_run(forward_messages, pair_params, num_samples, eps, generator, wa
         if eps is not None and torch.as_tensor(eps).dim() == 3:
             eps = torch.as_tensor(eps)[None]
     B, T, n = h_filt.shape
-    zero = torch.zeros((B, T, n), dtype=torch.float64, device=device)
-    init = (-0.5 * torch.eye(n, dtype=torch.float64, device=device), zero[0, 0], 0.)   # overridden by the messages
     homog = _is_homog(pair_params)
-    o = lds_estep_forward(init, pair_params, (zero, zero, None), num_samples, eps, per_t_pair_stats=not homog,
-                          want_stats=want_stats, generator=generator, from_messages=(J_filt, h_filt))
+    S = int(num_samples) if num_samples else 0
+    if needs_grad:
+        if eps is None and S > 0:
+            eps = torch.randn((B, T, S, n), dtype=torch.float64, device=device, generator=generator)
+        elif eps is not None:
+            eps = _lib.f64(eps, device).contiguous()
+        outs = _MessagesFn.apply(J_filt.contiguous(), h_filt.contiguous(), eps, pair_params, S, not homog, want_stats)
+        names = (["samples"] if S else []) + ([k for k in (_OUT_HOMOG if homog else _OUT_PER_T) if k not in ("samples", "lognorm")]
+                                              if want_stats else [])
+        o = dict(zip(names, outs))
+        o.update(B=B, T=T, n=n, S=S, dense=False, eps=eps, lognorm=torch.zeros(B, dtype=torch.float64, device=device))
+        if S == 0:
+            o["samples"] = None
+    else:
+        zero = torch.zeros((B, T, n), dtype=torch.float64, device=device)
+        init = (-0.5 * torch.eye(n, dtype=torch.float64, device=device), zero[0, 0], 0.)   # overridden by the messages
+        o = lds_estep_forward(init, pair_params, (zero, zero, None), S, eps, per_t_pair_stats=not homog,
+                              want_stats=want_stats, generator=generator, from_messages=(J_filt, h_filt))
     o["batched"] = batched
     return o, homog
 
 
 def natural_smoother_general(forward_messages, pair_params):
-    """(E_init_stats, E_pair_stats, E_node_stats) from given forward messages -- pyx:149-195."""
+    """(E_init_stats, E_pair_stats, E_node_stats) from given forward messages -- pyx:149-195.
+    Differentiable w.r.t. the filtered messages (natural_smoother_general_grad, pyx:236-306); the covariance-form
+    recursion does not read the prediction messages, whose gradient is zero (see include/svae_b200.h)."""
     o, homog = _messages_run(forward_messages, pair_params, 0, None, None, True)
     return _pack_stats(o, homog)[1]
 
 
 def natural_sample_backward(forward_messages, pair_params, num_samples=1, eps=None, generator=None):
-    """samples (B,T,S,n) drawn backwards from given filtered messages -- pyx:310-355."""
+    """samples (B,T,S,n) drawn backwards from given filtered messages -- pyx:310-355.
+    Differentiable w.r.t. the filtered messages (natural_sample_backward_grad, pyx:357-409)."""
     o, _ = _messages_run(forward_messages, pair_params, num_samples, eps, generator, False)
     return o["samples"] if o["batched"] else o["samples"][0]
 

@@ -346,6 +346,18 @@ int svae_gmm_meanfield(int B, int T, int K, int N, const double* node_J, const d
                        const double* label_init, double tol, int max_iter, double* label_stats,
                        int* iters, double* kl, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The recognition network's output head fused with node-potential production (svae/nnet.py:43-47 gaussian_info and the
+ * 'info' branch of the Gaussian resnet, nnet.py:90-104):
+ *   act (rows, 2n) = [J_in | h_in] last-layer activations;  res (rows, n) = inputs W + b1 or NULL;  b2 (n) or NULL
+ *   node_J = -1/2 (log1pexp(J_in) + log1pexp(b2)),  node_h = h_in + res        (rows = B*T of the E-step's (B,T,n))
+ * and its VJP w.r.t. act: g_act (rows, 2n) = [-1/2 sigmoid(J_in) g_node_J | g_node_h]   (d/d res = g_node_h,
+ * d/d b2 = -1/2 sigmoid(b2) sum_rows g_node_J are formed by the caller). */
+int svae_gaussian_info_head_fwd(long long rows, int n, const double* act, const double* res, const double* b2,
+                                double* node_J, double* node_h, void* stream);
+int svae_gaussian_info_head_bwd(long long rows, int n, const double* act, const double* g_node_J, const double* g_node_h,
+                                double* g_act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

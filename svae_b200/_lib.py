@@ -40,6 +40,8 @@ _SIGNATURES = {
     "svae_hmm_estep_masked": (_I, [_I] * 4 + [_P] * 8 + [_P]),
     "svae_slds_mix_params": (_I, [_I] * 4 + [_P] * 16 + [_P]),
     "svae_slds_node_potentials": (_I, [_I] * 4 + [_P] * 12 + [_P]),
+    "svae_gaussian_info_head_fwd": (_I, [_LL, _I] + [_P] * 5 + [_P]),
+    "svae_gaussian_info_head_bwd": (_I, [_LL, _I] + [_P] * 4 + [_P]),
     "svae_lds_compose_num_chunks": (_I, [_I, _I]),
     "svae_hmm_compose_chunks": (_I, [_I] * 4 + [_P] * 4 + [_P]),
     "svae_hmm_chain_messages": (_I, [_I] * 3 + [_P] * 7 + [_P]),

@@ -66,7 +66,8 @@ def label_meanfield(label_global, gaussian_globals, gaussian_stats):
 def initialize_meanfield(label_global, node_potentials, generator=None):
     """gmm.py:126-128."""
     T, K = node_potentials.shape[0], label_global.shape[0]
-    return normalize(torch.rand(T, K, dtype=torch.float64, generator=generator).to(node_potentials.device))
+    gdev = generator.device if generator is not None else node_potentials.device    # draw where the generator lives
+    return normalize(torch.rand(T, K, dtype=torch.float64, generator=generator, device=gdev).to(node_potentials.device))
 
 
 def meanfield_fixed_point_cuda(label_global, gaussian_globals, node_J, node_h, label_init, tol=1e-3, max_iter=100):

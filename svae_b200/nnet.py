@@ -57,7 +57,51 @@ def _mlp(nonlinearities):
         for nonlin, (W, b) in zip(nonlinearities, params):
             out = layer(nonlin, W, b, out)
         return unravel(out) if torch.is_tensor(out) else tuple(unravel(o) for o in out)
+
+    def pre_head(params, inputs):
+        """activations entering the output head: every layer but the last nonlinearity, raveled (rows, d_out)."""
+        out = _ravelers(inputs.shape)[0](inputs)
+        for nonlin, (W, b) in zip(nonlinearities[:-1], params[:-1]):
+            out = layer(nonlin, W, b, out)
+        W, b = params[-1]
+        return out @ W + b
+    mlp.pre_head = pre_head
     return mlp
+
+
+class _InfoHeadFn(torch.autograd.Function):
+    """gaussian_info + the resnet's 'info' residual in ONE kernel (csrc/nnet_heads.cu): the node potentials of the E-step
+    are written directly; backward is one kernel plus the two small reductions for the residual parameters."""
+
+    @staticmethod
+    def forward(ctx, act, res, b2):
+        from . import _lib
+        rows, two_n = act.shape
+        n = two_n // 2
+        act, res, b2 = act.contiguous(), res.contiguous(), b2.contiguous()
+        J = torch.empty((rows, n), dtype=torch.float64, device=act.device)
+        h = torch.empty((rows, n), dtype=torch.float64, device=act.device)
+        P = _lib.ptr
+        _lib.check(_lib.lib().svae_gaussian_info_head_fwd(rows, n, P(act), P(res), P(b2), P(J), P(h), _lib.stream_ptr(act.device)),
+                   "svae_gaussian_info_head_fwd")
+        ctx.save_for_backward(act, b2)
+        return J, h
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gJ, gh):
+        from . import _lib
+        act, b2 = ctx.saved_tensors
+        rows, two_n = act.shape
+        n = two_n // 2
+        gJ = None if gJ is None else gJ.contiguous()
+        gh = None if gh is None else gh.contiguous()
+        g_act = torch.empty_like(act)
+        P = _lib.ptr
+        _lib.check(_lib.lib().svae_gaussian_info_head_bwd(rows, n, P(act), P(gJ), P(gh), P(g_act), _lib.stream_ptr(act.device)),
+                   "svae_gaussian_info_head_bwd")
+        g_b2 = None if gJ is None else -0.5 * torch.sigmoid(b2) * gJ.sum(0)
+        return g_act, gh, g_b2
 
 
 def init_mlp(d_in, layer_specs, generator=None, device=None):
@@ -93,6 +137,10 @@ def _gresnet(mlp_type, mlp):
             mu_mlp, sigmasq_mlp = mlp(mlp_params, inputs)
             mu_res = unravel(ravel(inputs) @ W + b1)
             return (mu_mlp + mu_res, sigmasq_mlp + log1pexp(b2))
+        if inputs.is_cuda and inputs.dtype == torch.float64 and hasattr(mlp, "pre_head"):
+            # fused output head: one kernel from the last layer's activations to (J_node, h_node)
+            J, h = _InfoHeadFn.apply(mlp.pre_head(mlp_params, inputs), ravel(inputs) @ W + b1, b2)
+            return (unravel(J), unravel(h))
         J_mlp, h_mlp = mlp(mlp_params, inputs)
         h_res = unravel(ravel(inputs) @ W + b1)
         return (J_mlp + (-0.5 * log1pexp(b2)), h_mlp + h_res)

@@ -154,22 +154,9 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_BWD_MINB(N)) lds_estep_bwd_pac
     mbar_wait(&bars[t & 1], (uint32_t)((t >> 1) & 1));
     __syncwarp(MASK);
 
-    double wrow[N];                           // W[c][:] (= W[:, c])
-#pragma unroll
-    for (int q2 = 0; q2 < NP / 2; ++q2) {
-      const double2 w = ld2(&W[c * NP + 2 * q2]);
-      wrow[2 * q2] = w.x;
-      if (2 * q2 + 1 < N) wrow[2 * q2 + 1] = w.y;
-    }
-    double inner[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) inner[i] = 0.0;
-    double Sbn[N], vbn[1 + SA];
-#pragma unroll
-    for (int i = 0; i < N; ++i) Sbn[i] = 0.0;
-#pragma unroll
-    for (int v = 0; v < 1 + SA; ++v) vbn[v] = 0.0;
-
+    // Register discipline (168 registers at 9..12 resident warps per SM): once published to shared memory, Sb and vb are
+    // dead, so the carries G' Cb and G' vb are written straight into them; Cb lives only from its product to the carry;
+    // (Sb W) joins `inner` late, from the same broadcast as (Gb G').
     if (!last) {
       double grow[N];                         // G_t[k][c] over k: row c of the transposed storage
 #pragma unroll
@@ -178,25 +165,47 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_BWD_MINB(N)) lds_estep_bwd_pac
         grow[2 * q2] = w.x;
         if (2 * q2 + 1 < N) grow[2 * q2 + 1] = w.y;
       }
-      // Cb[:,c] = Sb G[:,c]  and  inner[:,c] = (Sb W)[:,c]  share the broadcast of Sb's columns
-      double Cb[N];
+      // vb_{t+1}[c] = (G' vb)[c]
 #pragma unroll
-      for (int i = 0; i < N; ++i) Cb[i] = 0.0;
-#pragma unroll
-      for (int k = 0; k < N; ++k) {
+      for (int v = 0; v < 1 + S; ++v) {
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int q2 = 0; q2 < NP / 2; ++q2) {
-          const double2 v = ld2(&SbS[k * NP + 2 * q2]);
-          Cb[2 * q2] = fma(v.x, grow[k], Cb[2 * q2]);
-          inner[2 * q2] = fma(v.x, wrow[k], inner[2 * q2]);
-          if (2 * q2 + 1 < N) {
-            Cb[2 * q2 + 1] = fma(v.y, grow[k], Cb[2 * q2 + 1]);
-            inner[2 * q2 + 1] = fma(v.y, wrow[k], inner[2 * q2 + 1]);
+          const double2 w = ld2(&vbS[v * NP + 2 * q2]);
+          s0 = fma(grow[2 * q2], w.x, s0);
+          if (2 * q2 + 1 < N) s1 = fma(grow[2 * q2 + 1], w.y, s1);
+        }
+        vb[v] = s0 + s1;
+      }
+      {
+        // Cb[:,c] = Sb G[:,c]
+        double Cb[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) Cb[i] = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+          for (int q2 = 0; q2 < NP / 2; ++q2) {
+            const double2 v = ld2(&SbS[k * NP + 2 * q2]);
+            Cb[2 * q2] = fma(v.x, grow[k], Cb[2 * q2]);
+            if (2 * q2 + 1 < N) Cb[2 * q2 + 1] = fma(v.y, grow[k], Cb[2 * q2 + 1]);
           }
         }
-      }
 #pragma unroll
-      for (int q2 = 0; q2 < NP / 2; ++q2) st2(&CbS[c * NP + 2 * q2], Cb[2 * q2], (2 * q2 + 1 < N) ? Cb[2 * q2 + 1] : 0.0);
+        for (int q2 = 0; q2 < NP / 2; ++q2) st2(&CbS[c * NP + 2 * q2], Cb[2 * q2], (2 * q2 + 1 < N) ? Cb[2 * q2 + 1] : 0.0);
+        // Sb_{t+1}[:,c] = (G' Cb)[:,c]
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int q2 = 0; q2 < NP / 2; ++q2) {
+            const double2 g = ld2(&G[i * NP + 2 * q2]);          // G_t[k][i], k = 2q2, 2q2+1
+            s0 = fma(g.x, Cb[2 * q2], s0);
+            if (2 * q2 + 1 < N) s1 = fma(g.y, Cb[2 * q2 + 1], s1);
+          }
+          Sb[i] = s0 + s1;
+        }
+      }
       double Gb[N];
       {
         // C[:,c] = G Sigma_{t+1}[:,c]
@@ -240,29 +249,6 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_BWD_MINB(N)) lds_estep_bwd_pac
           if (2 * q2 + 1 < N) Gb[2 * q2 + 1] = fma(v.y, xn_c[s], Gb[2 * q2 + 1]);
         }
       }
-      // carries: Sb_{t+1}[:,c] = (G' Cb)[:,c],  vb_{t+1}[c] = (G' vb)[c]
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int q2 = 0; q2 < NP / 2; ++q2) {
-          const double2 g = ld2(&G[i * NP + 2 * q2]);          // G_t[k][i], k = 2q2, 2q2+1
-          s0 = fma(g.x, Cb[2 * q2], s0);
-          if (2 * q2 + 1 < N) s1 = fma(g.y, Cb[2 * q2 + 1], s1);
-        }
-        Sbn[i] = s0 + s1;
-      }
-#pragma unroll
-      for (int v = 0; v < 1 + S; ++v) {
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int q2 = 0; q2 < NP / 2; ++q2) {
-          const double2 w = ld2(&vbS[v * NP + 2 * q2]);
-          s0 = fma(grow[2 * q2], w.x, s0);
-          if (2 * q2 + 1 < N) s1 = fma(grow[2 * q2 + 1], w.y, s1);
-        }
-        vbn[v] = s0 + s1;
-      }
       __syncwarp(MASK);                       // CbS visible
 #pragma unroll
       for (int k = 0; k < N; ++k) {
@@ -277,8 +263,30 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_BWD_MINB(N)) lds_estep_bwd_pac
       __syncwarp(MASK);                       // every lane is done with Cb: the tile now holds Gb
 #pragma unroll
       for (int q2 = 0; q2 < NP / 2; ++q2) st2(&CbS[c * NP + 2 * q2], Gb[2 * q2], (2 * q2 + 1 < N) ? Gb[2 * q2 + 1] : 0.0);
-      __syncwarp(MASK);
-      // inner[:,c] += (Gb G')[:,c] = sum_k Gb[:,k] G_t[c][k]
+    }
+    load_in(t + 1 < T ? t + 1 : t);           // next step's per-lane cotangent elements (issued before the barrier below)
+    __syncwarp(MASK);                         // Gb visible
+    double wrow[N];                           // W[c][:] (= W[:, c])
+#pragma unroll
+    for (int q2 = 0; q2 < NP / 2; ++q2) {
+      const double2 w = ld2(&W[c * NP + 2 * q2]);
+      wrow[2 * q2] = w.x;
+      if (2 * q2 + 1 < N) wrow[2 * q2 + 1] = w.y;
+    }
+    // inner[:,c] = (Sb W)[:,c] + (Gb G')[:,c] = sum_k Sb[:,k] W[k][c] + Gb[:,k] G_t[c][k]
+    double inner[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) inner[i] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+      for (int q2 = 0; q2 < NP / 2; ++q2) {
+        const double2 v = ld2(&SbS[k * NP + 2 * q2]);
+        inner[2 * q2] = fma(v.x, wrow[k], inner[2 * q2]);
+        if (2 * q2 + 1 < N) inner[2 * q2 + 1] = fma(v.y, wrow[k], inner[2 * q2 + 1]);
+      }
+    }
+    if (!last) {
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const double gck = G[k * NP + c];
@@ -289,19 +297,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_BWD_MINB(N)) lds_estep_bwd_pac
           if (2 * q2 + 1 < N) inner[2 * q2 + 1] = fma(v.y, gck, inner[2 * q2 + 1]);
         }
       }
-    } else {
-      // last step: only (Sb W)[:,c]
-#pragma unroll
-      for (int k = 0; k < N; ++k) {
-#pragma unroll
-        for (int q2 = 0; q2 < NP / 2; ++q2) {
-          const double2 v = ld2(&SbS[k * NP + 2 * q2]);
-          inner[2 * q2] = fma(v.x, wrow[k], inner[2 * q2]);
-          if (2 * q2 + 1 < N) inner[2 * q2 + 1] = fma(v.y, wrow[k], inner[2 * q2 + 1]);
-        }
-      }
     }
-    load_in(t + 1 < T ? t + 1 : t);           // next step's per-lane cotangent elements
 
     // (W mb)_c,  mb = mub + sum_s xb_s
     {
@@ -386,10 +382,6 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_BWD_MINB(N)) lds_estep_bwd_pac
       for (int i = 0; i < N; ++i) kt[i * NP + c] = Q[i];
       stash[(size_t)t * RS + N * NP + c] = f_c;
     }
-#pragma unroll
-    for (int i = 0; i < N; ++i) Sb[i] = Sbn[i];
-#pragma unroll
-    for (int v = 0; v < 1 + S; ++v) vb[v] = vbn[v];
     __syncwarp(MASK);                         // every lane is done with the ring slot, SbS, vbS, epS, wm, us
     if (t + 2 < T) fetch(t + 2, t & 1);
   }

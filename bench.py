@@ -352,7 +352,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a mismatched collective must fail within minutes, not hold the box for NCCL's default 10
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     n, T, B, S = D, T_LEN, BATCH, NUM_SAMPLES
 
     rng = np.random.default_rng(0)
@@ -385,13 +387,22 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     with ClockSampler(local) as clk:
-        # warm-up: at least W (>= 3) steps and at least ~1 s so the clock sampler sees the GPU under load
+        # warm-up: at least W (>= 3) steps and at least ~1 s so the clock sampler sees the GPU under load.  Every rank must
+        # issue the SAME number of steps (each carries a collective): blocks of 32 steps, and the decision to go on is itself
+        # all-reduced (a rank-local clock check would let ranks disagree by a step and dead-lock the all-reduce sequence).
         t0 = time.perf_counter()
         i = 0
-        while i < max(args.warmup, 3) or time.perf_counter() - t0 < 1.0:
+        for _ in range(max(args.warmup, 3)):
             step(i); i += 1
-            if i % 16 == 0:
-                torch.cuda.synchronize()
+        while True:
+            torch.cuda.synchronize()
+            more = torch.tensor([1.0 if time.perf_counter() - t0 < 1.0 else 0.0], device=dev)
+            if world > 1:
+                dist.all_reduce(more, op=dist.ReduceOp.MAX)
+            if float(more.item()) == 0.0:
+                break
+            for _ in range(32):
+                step(i); i += 1
         barrier()
         # ---- device-timed region: exactly K steps -------------------------------------------------
         l0 = _lib.launch_count()

@@ -87,8 +87,10 @@ def hmm_logZ_parallel(natparam, chunk_len=None):
 def hmm_viterbi_parallel(natparam, chunk_len=None):
     """hmm_viterbi (svae/hmm/hmm_inference.py:54-63) for few long sequences: max-plus chunk matrices, back-tracked
     boundary states, then the ordinary Viterbi kernel on every chunk with both end states pinned.  The optimal path is
-    unique for tie-free potentials, so the result equals the sequential one.
-    NOTE: stages 1-2 are validated on CPU through the host build of their phase code; first GPU run pending."""
+    unique for tie-free potentials, so the result equals the sequential one (tests/test_hmm_pit_gpu.py, exact).  With TIES
+    the sequential kernel and this driver both return a maximum-score path but may break the tie differently (first
+    argmax per step there; per chunk boundary, then per step here): equal scores, possibly different paths.  The -1e300
+    pins rely on the Viterbi kernel adding node potentials without exponentiating or rescaling them (csrc/hmm_estep.cu)."""
     lp, lA, node, batched, dev = H._canon(natparam)
     B, T, K = node.shape
     Lc = int(chunk_len) if chunk_len else default_chunk_len(T)

@@ -96,9 +96,15 @@ def meanfield_fixed_point_cuda(label_global, gaussian_globals, node_J, node_h, l
     return out, iters, kl
 
 
+WARN_ITERATION_LIMIT = False   # the reference prints 'iteration limit reached' (gmm.py:107-108); on the CUDA path that needs
+                               # the kernel's iteration count on the host, i.e. one synchronisation per E-step: opt-in
+
+
 def meanfield_fixed_point(label_global, gaussian_globals, node_potentials, tol=1e-3, max_iter=100,
-                          label_init=None, generator=None):
-    """gmm.py:90-110.  On a CUDA device with diagonal node precisions the loop runs inside one kernel launch."""
+                          label_init=None, generator=None, diagonal=None):
+    """gmm.py:90-110.  On a CUDA device with diagonal node precisions the loop runs inside one kernel launch.
+    diagonal: True when the caller knows the node precisions are diagonal (local_meanfield does: it packed them from
+    (J (T,N), h)); None = find out (costs a device->host synchronisation on CUDA)."""
     kl = float('inf')
     label_stats = initialize_meanfield(label_global, node_potentials, generator) if label_init is None else label_init
     if node_potentials.is_cuda:
@@ -106,9 +112,14 @@ def meanfield_fixed_point(label_global, gaussian_globals, node_potentials, tol=1
         A = node_potentials[..., :N, :N]
         diag = torch.diagonal(A, dim1=-1, dim2=-2)
         from .. import _lib
-        if N <= _lib.SVAE_GMM_MAX_N and bool((A - torch.diag_embed(diag)).abs().max() == 0):
-            return meanfield_fixed_point_cuda(label_global, gaussian_globals, diag, node_potentials[..., :N, N],
-                                              label_stats, tol, max_iter)[0]
+        if diagonal is None:
+            diagonal = bool((A - torch.diag_embed(diag)).abs().max() == 0)
+        if N <= _lib.SVAE_GMM_MAX_N and diagonal:
+            labels, iters, _ = meanfield_fixed_point_cuda(label_global, gaussian_globals, diag, node_potentials[..., :N, N],
+                                                          label_stats, tol, max_iter)
+            if WARN_ITERATION_LIMIT and int(iters.max()) >= max_iter:
+                print('iteration limit reached', file=sys.stderr)
+            return labels
     for _ in range(max_iter):
         gaussian_natparam, gaussian_stats, gaussian_kl = gaussian_meanfield(gaussian_globals, node_potentials, label_stats)
         label_natparam, label_stats, label_kl = label_meanfield(label_global, gaussian_globals, gaussian_stats)
@@ -127,12 +138,13 @@ def meanfield_fixed_point(label_global, gaussian_globals, node_potentials, tol=1
 def local_meanfield(global_natparam, node_potentials, label_init=None, generator=None):
     """gmm.py:62-88."""
     dirichlet_natparam, niw_natparams = global_natparam
+    diagonal = node_potentials[0].dim() == node_potentials[1].dim()      # (J (T,N), h (T,N)): the recognition head's output
     node_potentials = gaussian.pack_dense(*node_potentials)
     label_global = dirichlet.expectedstats(dirichlet_natparam)
     gaussian_globals = niw.expectedstats(niw_natparams)
     with torch.no_grad():
         label_stats = meanfield_fixed_point(label_global, gaussian_globals, node_potentials.detach(),
-                                            label_init=label_init, generator=generator)
+                                            label_init=label_init, generator=generator, diagonal=diagonal or None)
     gaussian_natparam, gaussian_stats, gaussian_kl = gaussian_meanfield(gaussian_globals, node_potentials, label_stats)
     label_natparam, label_stats, label_kl = label_meanfield(label_global, gaussian_globals, gaussian_stats)
     dirichlet_stats = label_stats.sum(0)

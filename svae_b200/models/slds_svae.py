@@ -360,7 +360,11 @@ def run_inference(prior_natparam, global_natparam, nn_potentials, num_samples, e
     hmm_global_natparam, lds_global_natparam = global_natparam
     batched = nn_potentials[1].dim() == 3
     pots = tuple(nn_potentials[:2]) if batched else tuple(p[None] for p in nn_potentials[:2])
-    lds_expected = lds_global_expectedstats(lds_global_natparam)         # K modes in one batch; reused by the prior term
+    # the K modes stacked ONCE (global and prior), every per-mode map batched over them and reused by the prior term
+    lds_global_natparam = stack_lds_global(lds_global_natparam)
+    global_natparam = (hmm_global_natparam, lds_global_natparam)
+    prior_natparam = (prior_natparam[0], stack_lds_global(prior_natparam[1]))
+    lds_expected = lds_global_expectedstats(lds_global_natparam)
     dense = get_all_lds_local_natparams(lds_global_natparam, lds_expected)
     with torch.no_grad():
         (hmm_stats, _), (hmm_local_natparam, lds_local_natparam), _ = \

@@ -427,6 +427,7 @@ def run_ours(args):
     # piece sizes of the host pipeline: small first piece so the device-to-host stream (the bound) starts early;
     # swept on a B200 in scripts/e2e_probe.py (profiles/r01_e2e_chunk_sweep.txt)
     E2E_CHUNKS = K.ramp_schedule(B, 256, 1.5, 1024)
+    RI_CHUNKS = K.trapezoid_schedule(B)      # host-to-device bound: scripts/e2e_probe_ri.py
     h_nJ = sets[0][0].cpu().pin_memory(); h_nh = sets[0][1].cpu().pin_memory()
     out_host = dict(
         samples=torch.empty((B, T, S, n), dtype=torch.float64).pin_memory(),
@@ -437,32 +438,57 @@ def run_ours(args):
     for v in out_host.values():
         v.zero_()                                # first touch on this rank's NUMA node
 
-    def e2e_step(i):
+    from svae_b200.models import lds as LDSM
+
+    def e2e_step_all(i):
+        """primitive level: every per-sequence output of natural_lds_inference_general goes back to the host"""
         acc = K.lds_estep_host((gi, gp), (h_nJ, h_nh), S, out_host, chunks=E2E_CHUNKS, generator=gen, device=dev)
         if world > 1:
             dist.all_reduce(acc)
         acc_host.copy_(acc, non_blocking=True)
 
-    for i in range(3):
-        e2e_step(i)
-    barrier()
+    ri_host = torch.empty(((n + 2) * (n + 2) + 3 * n * n + 2,), dtype=torch.float64).pin_memory()   # packed NIW stats | MNIW stats | local_kl
+
+    def e2e_step_ri(i):
+        """model level (what make_gradfun calls, svae.py:21-22): lds.run_inference for a host-resident minibatch -- samples,
+        the summed global statistics and local_kl come back; the node statistics feed local_kl on the device"""
+        _, stats, _, local_kl = LDSM.run_inference_host(None, None, (h_nJ, h_nh), S, out_host["samples"], chunks=RI_CHUNKS,
+                                                        generator=gen, device=dev, local_natparam=(gi, gp))
+        acc = torch.cat([stats[0].reshape(-1)] + [x.reshape(-1) for x in stats[1]] + [local_kl.reshape(1)])
+        if world > 1:
+            dist.all_reduce(acc)            # the one collective of an SVI step: global statistics + local KL
+        ri_host.copy_(acc, non_blocking=True)
+
+    def time_e2e(fn):
+        for i in range(3):
+            fn(i)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(e2e_steps):
+            fn(i)
+        f1.record()
+        barrier()
+        tt = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) / e2e_steps
+
     e2e_steps = max(3, min(args.steps, 20))
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    f1.record()
-    barrier()
-    t = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / e2e_steps
+    e2e_all_ms = time_e2e(e2e_step_all)
+    e2e_ms = time_e2e(e2e_step_ri)
     h2d = h_nJ.numel() * 8 + h_nh.numel() * 8
-    d2h = sum(v.numel() * 8 for v in out_host.values()) + acc_host.numel() * 8
+    d2h_all = sum(v.numel() * 8 for v in out_host.values()) + acc_host.numel() * 8
+    d2h = out_host["samples"].numel() * 8 + ri_host.numel() * 8
     del h_nJ, h_nh, out_host
 
     peak, peak_src = measured_peak_hbm()
-    extra = {"numa": numa}
+    extra = {"numa": numa,
+             "e2e_all_outputs": dict(value=world * B / (e2e_all_ms * 1e-3), unit=UNIT, ms_per_step=e2e_all_ms, h2d_bytes_per_step=h2d,
+                                     d2h_bytes_per_step=d2h_all,
+                                     note="primitive level (natural_lds_inference_general): samples AND the per-sequence node "
+                                          "statistics E_node_xx, E_node_x, lognorm copied back; floor = that %.0f MB device-to-host "
+                                          "copy (~4.0 ms at the ~50 GB/s PCIe 5 x16 delivers)" % (d2h_all / 1e6))}
 
     # ---- strong scaling (BASELINE.json configs[3]): a GLOBAL batch of 4096 sequences sharded over the ranks, same
     #      step (kernel + minibatch reduction + the one all-reduce); measured at every N, max over ranks ----------
@@ -619,11 +645,15 @@ def run_ours(args):
                         step="fused filter+smoother+sampler kernel, 2-stage minibatch reduction of the global statistics"
                              + (", NCCL all-reduce of the %d-double accumulator" % (4 * n * n + n + 1) if world > 1 else "")),
             e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                     ms_per_step=e2e_ms,
-                     note="pinned host buffers (allocated on the GPU's NUMA node); pieces of %s sequences pipelined (one copy "
-                          "stream per direction, kernels on 3 streams), persistent device buffers; noise drawn on device; "
-                          "floor = the %.0f MB device-to-host copy of a step (~4.0 ms at the ~50 GB/s PCIe 5 x16 delivers)"
-                          % (E2E_CHUNKS, d2h / 1e6)),
+                     ms_per_step=e2e_ms, api="svae_b200.models.lds.run_inference_host",
+                     note="the model-level call make_gradfun makes (svae.py:21-22, models/lds.py:35-41) for a host-resident "
+                          "minibatch: pinned node potentials in (%.0f MB), pinned samples + summed global statistics + local_kl out "
+                          "(%.0f MB); the per-sequence node statistics are consumed by the local_kl contraction on the device (their "
+                          "only consumer in run_inference) -- extra.e2e_all_outputs is the same pipeline with them copied back too; "
+                          "pieces of %s sequences pipelined (one copy stream per direction, kernels on 3 streams), pinned buffers on "
+                          "the GPU's NUMA node, persistent device buffers, noise drawn on device; floor = the host-to-device copy "
+                          "(2.4 ms at the 55 GB/s measured) + the last piece's kernel (0.6 ms: 200 sequential steps) and copy"
+                          % (h2d / 1e6, d2h / 1e6, RI_CHUNKS)),
             gpu_launches=int(launches),
             clocks=clk.summary(),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,

@@ -260,11 +260,17 @@ class LdsHostPipeline:
             self.bufs.append(d)
         self.acc = new(4 * n * n + n + 1)
 
-    def run(self, natparam, node_host, out_host, generator=None):
-        """node_host = (J_node, h_node) pinned CPU tensors (B,T,n); out_host = dict of pinned CPU tensors
-        {"samples", "E_node_xx", "E_node_x", "lognorm"} filled in place.  Returns the device tensor
-        sum_b [E_init | E_pair | lognorm] (see lds_reduce_global_stats)."""
+    def run(self, natparam, node_host, out_host, generator=None, outputs="all"):
+        """node_host = (J_node, h_node) pinned CPU tensors (B,T,n); out_host = dict of pinned CPU tensors filled in place.
+        outputs="all": {"samples", "E_node_xx", "E_node_x", "lognorm"} -- every per-sequence output of
+            natural_lds_inference_general (lds_inference.py:196-202) goes back to the host;
+        outputs="run_inference": {"samples"} only -- what models/lds.py:35-41 run_inference hands its caller: the samples, the
+            summed global statistics and local_kl = <node potentials, E_node> - lognorm; the node statistics are consumed on
+            the device by that contraction (their only consumer) and never cross PCIe.
+        Returns the device tensor sum_b [E_init | E_pair | lognorm] (see lds_reduce_global_stats); in "run_inference" mode
+        (acc, local_kl) with local_kl a device scalar."""
         init_params, pair_params = natparam
+        ri = outputs == "run_inference"
         J_h, h_h = node_host
         cur = torch.cuda.current_stream(self.device)
         S = self.S
@@ -286,20 +292,28 @@ class LdsHostPipeline:
                     d["eps"].normal_(generator=generator)
                 o = lds_estep_forward(init_params, pair_params, (d["J"], d["h"]), S, d["eps"], buffers=d)
                 lds_reduce_global_stats(o, out=d["acc"], work=d["rwork"])
+                if ri:      # <node potentials, E_node> of this piece (models/lds.py:40); lognorm's sum is the last entry of acc
+                    d["kl"] = torch.dot(d["J"].reshape(-1), o["E_node_xx"].reshape(-1)) + torch.dot(d["h"].reshape(-1), o["E_node_x"].reshape(-1))
                 self.ev_done[k].record(st)
             self.s_out.wait_event(self.ev_done[k])
             with torch.cuda.stream(self.s_out):
                 if S:
                     out_host["samples"][lo:hi].copy_(o["samples"], non_blocking=True)
-                out_host["E_node_xx"][lo:hi].copy_(o["E_node_xx"], non_blocking=True)
-                out_host["E_node_x"][lo:hi].copy_(o["E_node_x"], non_blocking=True)
-                out_host["lognorm"][lo:hi].copy_(o["lognorm"], non_blocking=True)
+                if not ri:
+                    out_host["E_node_xx"][lo:hi].copy_(o["E_node_xx"], non_blocking=True)
+                    out_host["E_node_x"][lo:hi].copy_(o["E_node_x"], non_blocking=True)
+                    out_host["lognorm"][lo:hi].copy_(o["lognorm"], non_blocking=True)
         self.acc.zero_()
         cur.wait_stream(self.s_out)
         for st in self.streams:
             cur.wait_stream(st)
         for k in live:
             self.acc += self.bufs[k]["acc"]
+        if ri:
+            kl = self.bufs[live[0]]["kl"]
+            for k in live[1:]:
+                kl = kl + self.bufs[k]["kl"]
+            return self.acc, kl - self.acc[-1]
         return self.acc
 
 
@@ -316,7 +330,20 @@ def ramp_schedule(B, first=256, growth=1.5, largest=1024):
     return sizes
 
 
-def lds_estep_host(natparam, node_host, num_samples, out_host, chunks=3, generator=None, device=None, _plans={}):
+def trapezoid_schedule(B):
+    """Piece sizes for the host pipeline when the host-to-device copy is the bound (run_inference mode): small first piece
+    (the first kernel starts early), plateau, small last pieces (after the last input byte has arrived only a short kernel and
+    a short copy remain).  Swept on a B200 (scripts/e2e_probe_ri.py, profiles/r02_e2e_chunk_sweep.txt): 3.47 ms against
+    3.84 ms for the ramp at B = 4096."""
+    if B < 1024:
+        return [B]
+    fr = (0.09375, 0.1875, 0.25, 0.25, 0.15625)
+    sizes = [max(1, int(round(f * B))) for f in fr]
+    sizes.append(B - sum(sizes))
+    return [x for x in sizes if x > 0]
+
+
+def lds_estep_host(natparam, node_host, num_samples, out_host, chunks=3, generator=None, device=None, _plans={}, outputs="all"):
     """Functional wrapper around LdsHostPipeline (plans are cached per shape)."""
     B, T, n = node_host[1].shape
     S = int(num_samples) if num_samples else 0
@@ -324,7 +351,7 @@ def lds_estep_host(natparam, node_host, num_samples, out_host, chunks=3, generat
     key = (B, T, n, S, chunks if isinstance(chunks, int) else tuple(chunks), str(device))
     if key not in _plans:
         _plans[key] = LdsHostPipeline(B, T, n, S, chunks, device)
-    return _plans[key].run(natparam, node_host, out_host, generator)
+    return _plans[key].run(natparam, node_host, out_host, generator, outputs)
 
 
 def lds_estep_backward(o, g, messages_out=False, message_seeds=None):

@@ -60,6 +60,33 @@ def run_inference(prior_natparam, global_natparam, nn_potentials, num_samples, e
 cython_run_inference = run_inference
 
 
+def run_inference_host(prior_natparam, global_natparam, nn_potentials_host, num_samples, samples_host, chunks=None,
+                       generator=None, device=None, local_natparam=None):
+    """run_inference (lds.py:35-41) for HOST-resident minibatches: pinned node potentials (J, h) (B,T,n) in, pinned
+    samples (B,T,S,n) out, through lds_inference.LdsHostPipeline (pieces of the batch flow H2D copy -> fused kernel ->
+    statistics reduction + <node, E_node> contraction -> D2H copy on rotating streams).  Returns the same 4-tuple as
+    run_inference with `samples` = samples_host (filled when the current stream has been synchronised), the summed
+    global statistics and the KL scalars on the device.  local_natparam = (init_params, pair_params) skips the per-call
+    NIW/MNIW maps when the caller already holds them (they are constant across the minibatches of an SVI step)."""
+    from ..lds.lds_inference import lds_estep_host, trapezoid_schedule
+    B, T, n = nn_potentials_host[1].shape
+    expected_global = None
+    if local_natparam is None:
+        expected_global = lds_prior_expectedstats(global_natparam)
+        local_natparam = (gaussian.unpack_dense(expected_global[0]), expected_global[1])
+    chunks = chunks if chunks is not None else trapezoid_schedule(B)
+    acc, local_kl = lds_estep_host(local_natparam, nn_potentials_host[:2], num_samples, dict(samples=samples_host), chunks=chunks,
+                                   generator=generator, device=device, outputs="run_inference")
+    nn = n * n
+    ExxT0, Ex0 = acc[:nn].reshape(n, n), acc[nn:nn + n]
+    o = nn + n
+    Exx, Exxn, Exnxn = (acc[o + k * nn:o + (k + 1) * nn].reshape(n, n) for k in range(3))
+    Bt = torch.tensor(float(B), dtype=torch.float64, device=acc.device)
+    global_expected_stats = (gaussian.pack_dense(ExxT0, Ex0, Bt, Bt), (Exx, Exxn, Exnxn, Bt * (T - 1)))
+    global_kl = lds_prior_kl(global_natparam, prior_natparam, expected_global) if prior_natparam is not None else None
+    return samples_host, global_expected_stats, global_kl, local_kl
+
+
 def make_prior_natparam(n, scaling=1., device=None):
     """lds.py:57-67 on the in-tree NIW/MNIW parameterisations."""
     eye = torch.eye(n, dtype=torch.float64, device=device)

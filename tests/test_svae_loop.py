@@ -185,3 +185,25 @@ def test_optimizers_on_nested_tuples():
     pa = adam(gradfun, p0, num_iters=2000, step_size=0.01)
     for q in (ps, pa):
         assert torch.allclose(q[0], target[0], atol=1e-3) and torch.allclose(q[1][0], target[1][0], atol=1e-3)
+
+
+@pytest.mark.gpu
+def test_lds_run_inference_host_equals_run_inference():
+    """models/lds.py run_inference for a host-resident minibatch (pinned buffers through LdsHostPipeline): the summed global
+    statistics and local_kl equal the device-resident call's; the samples are valid draws (same statistics, own noise)."""
+    from svae_b200.models import lds
+    n, T, B = 5, 12, 300
+    g = torch.Generator().manual_seed(3)
+    prior = lds.make_prior_natparam(n, device="cuda")
+    glob = lds.make_prior_natparam(n, scaling=1.7, device="cuda")
+    J = (-0.5 * torch.nn.functional.softplus(torch.randn(B, T, n, dtype=torch.float64, generator=g))).pin_memory()
+    h = torch.randn(B, T, n, dtype=torch.float64, generator=g).pin_memory()
+    for S in (0, 1):
+        smp_host = torch.zeros((B, T, max(S, 1), n), dtype=torch.float64).pin_memory()
+        smp, stats, gkl, lkl = lds.run_inference_host(prior, glob, (J, h), S, smp_host, chunks=[64, 100, 136])
+        torch.cuda.synchronize()
+        _, wstats, wgkl, wlkl = lds.run_inference(prior, glob, (J.cuda(), h.cuda()), S)
+        assert torch.allclose(flat(stats), flat(wstats), rtol=1e-10, atol=1e-10)
+        assert abs(float(lkl) - float(wlkl)) < 1e-9 * abs(float(wlkl)) and abs(float(gkl) - float(wgkl)) < 1e-12 * max(1., abs(float(wgkl)))
+        if S:
+            assert torch.isfinite(smp).all() and float(smp.abs().max()) > 0

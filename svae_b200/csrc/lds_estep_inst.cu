@@ -95,17 +95,17 @@ static cudaError_t launch_one(const LdsFwdParams& p, cudaStream_t stream) {
 }
 
 // the packed mapping (lds_estep_packed.cuh): N lanes per sequence, 32/N sequences per warp
-template <int N, int S, bool SAVE>
+template <int N, int S, bool SAVE, bool INHOMOG>
 static cudaError_t launch_packed(const LdsFwdParams& p, cudaStream_t stream) {
   constexpr int SPW = lds_packed_spw(N);
   const long long grid = ((long long)p.B + SPW - 1) / SPW;
-  const size_t smem = sizeof(double) * (3 * N * lds_np(N) + 2 + (size_t)SPW * lds_packed_tile_doubles(N, S));
-  auto kern = lds_estep_packed_kernel<N, S, SAVE>;
+  const size_t smem = sizeof(double) * (3 * N * lds_np(N) + 2 + (size_t)SPW * lds_packed_tile_doubles(N, S, INHOMOG));
+  auto kern = lds_estep_packed_kernel<N, S, SAVE, INHOMOG>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  if (p.T > 1) {
+  if (p.T > 1 && !INHOMOG) {
     std::lock_guard<std::mutex> lock(g_const_mu);
     LdsFwdParams q = p;
     int slot = 0;
@@ -127,10 +127,11 @@ static cudaError_t launch_packed(const LdsFwdParams& p, cudaStream_t stream) {
 // the packed kernel covers the hot configuration only; everything else runs the general kernel
 static bool packed_eligible(const LdsFwdParams& p, bool inhomog) {
   static const bool enabled = [] { const char* e = getenv("SVAE_LDS_PACKED"); return !(e && atoi(e) == 0); }();
-  return enabled && !inhomog && p.S <= 2 && !(p.flags & SVAE_LDS_FLAG_INIT_PER_SEQ) && !p.Exx_t && !p.Exxn_t &&
-         !p.msg_J_pred && !p.msg_h_pred && !p.in_J_filt && !p.in_h_filt && !p.node_J_dense && !p.term_J &&
-         p.E_init_xx && p.E_init_x && p.E_pair_xx && p.E_pair_xxn && p.E_pair_xnxn && p.E_node_xx && p.E_node_x &&
-         p.lognorm && (p.S == 0 || p.samples);
+  if (!enabled || p.S > 2 || p.msg_J_pred || p.msg_h_pred || p.in_J_filt || p.in_h_filt || p.node_J_dense || p.term_J ||
+      !p.E_init_xx || !p.E_init_x || !p.E_node_xx || !p.E_node_x || !p.lognorm || (p.S > 0 && !p.samples))
+    return false;
+  if (inhomog) return true;       // per-sequence / per-time parameters, optional per-time outputs
+  return !(p.flags & SVAE_LDS_FLAG_INIT_PER_SEQ) && !p.Exx_t && !p.Exxn_t && p.E_pair_xx && p.E_pair_xxn && p.E_pair_xnxn;
 }
 
 #define SVAE_CAT_(a, b) a##b
@@ -150,11 +151,15 @@ cudaError_t SVAE_CAT(lds_fwd_launch_n, SVAE_N)(const LdsFwdParams& p, int cpl, i
   constexpr int N = SVAE_N;
   if (packed_eligible(p, inhomog)) {
     const bool save = (p.flags & SVAE_LDS_FLAG_SAVE) != 0;
+#define SVAE_PACKED_CASE(SS) \
+    return inhomog ? (save ? launch_packed<N, SS, true, true>(p, stream) : launch_packed<N, SS, false, true>(p, stream)) \
+                   : (save ? launch_packed<N, SS, true, false>(p, stream) : launch_packed<N, SS, false, false>(p, stream))
     switch (p.S) {
-      case 0: return save ? launch_packed<N, 0, true>(p, stream) : launch_packed<N, 0, false>(p, stream);
-      case 1: return save ? launch_packed<N, 1, true>(p, stream) : launch_packed<N, 1, false>(p, stream);
-      default: return save ? launch_packed<N, 2, true>(p, stream) : launch_packed<N, 2, false>(p, stream);
+      case 0: SVAE_PACKED_CASE(0);
+      case 1: SVAE_PACKED_CASE(1);
+      default: SVAE_PACKED_CASE(2);
     }
+#undef SVAE_PACKED_CASE
   }
 #ifdef SVAE_LDS_ENABLE_CPL2   // two column slots per lane: measured slower than CPL = 1 on B200
   if (cpl == 2) {

@@ -38,9 +38,9 @@ __host__ __device__ constexpr int lds_packed_spw(int N) { return 32 / N; }
 // shared-memory doubles per sequence tile; padded so that consecutive tiles start one ROW (NP doubles) apart modulo
 // 128 bytes: the rows the 32/N sequences of a warp touch with one instruction then sit side by side in bank space
 // (2 wavefronts for 3 x 80 bytes at n = 10 instead of the 4 that ncu counted with a 48-byte skew)
-__host__ __device__ constexpr int lds_packed_tile_doubles(int N, int S) {
+__host__ __device__ constexpr int lds_packed_tile_doubles(int N, int S, bool inhomog = false) {
   const int NP = lds_np(N);
-  const int fa = 2 * N * NP + 2 * (2 + S) * NP;                 // Lr, Lt, node ring
+  const int fa = 2 * N * NP + 2 * (2 + S) * NP + (inhomog ? 6 * N * NP : 0);   // Lr, Lt, node ring, 2 x {J11|J12|J22} of a step
   const int fb = 2 * (2 * N + 1 + S) * NP + N * NP;             // stash ring, Cs
   const int raw = (3 + 2 * S) * NP /*hf, mu, sd, w, x*/ + (fa > fb ? fa : fb);
   return raw + ((NP % 16 - raw % 16) + 16) % 16;
@@ -71,7 +71,11 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   return y;
 }
 
-template <int N, int S, bool SAVE>
+// INHOMOG: pair parameters per (sequence, time) (the SLDS mixture of K modes, svae/models/slds_svae.py:92-103): a step's three
+// n x n blocks are staged by cp.async one step ahead (every lane copies its own column; the J12 rows the prediction
+// broadcasts become visible at the end-of-step barrier), the initial state may be per sequence, the per-time second moments
+// E[x_t x_t'], E[x_t x_{t+1}'] can be written out (the HMM node potentials are contracted from them).
+template <int N, int S, bool SAVE, bool INHOMOG>
 __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kernel(const LdsFwdParams p) {
   constexpr int NP = lds_np(N);
   constexpr int NN = N * N;
@@ -80,8 +84,9 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
   constexpr unsigned MASK = ACT == 32 ? 0xffffffffu : ((1u << ACT) - 1u);
   constexpr int SS = (2 * N + 1 + S) * NP;                       // fetched prefix of a stash record
   constexpr int NODE = (2 + S) * NP;
-  constexpr int TILE = lds_packed_tile_doubles(N, S);
+  constexpr int TILE = lds_packed_tile_doubles(N, S, INHOMOG);
   constexpr int SA = S > 0 ? S : 1;                              // array extent (no zero-length arrays)
+  constexpr int PB = 3 * N * NP;                                 // one staged step of pair parameters: J11 | J12 | J22
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x;
   const int T = p.T;
@@ -93,7 +98,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
   double* shJ11 = smem;            // J22 + J11: what every non-terminal prediction lands in
   double* shJ12 = shJ11 + N * NP;
   double* shJ22 = shJ12 + N * NP;
-  if (T > 1) {
+  if (T > 1 && !INHOMOG) {
     for (int e = lane; e < NN; e += 32) {
       const int i = e / N, j = e % N;
       shJ11[i * NP + j] = -2.0 * p.J22[e] - 2.0 * p.J11[e];
@@ -123,6 +128,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
   double* Lr = uni;                // Lr[k*NP+j]: pivot row k of the LDL' elimination (j >= k), Lr[k*NP+k] = d_k
   double* Lt = Lr + N * NP;        // Lt[i*NP+k] = L~[i][k], unit lower factor, row-major
   double* nring = Lt + N * NP;     // 2 x { J_node | h_node | eps rows }
+  double* pst = nring + 2 * NODE;  // INHOMOG: 2 x { J11 | J12 | J22 } natural form, row-major [i][j]
   double* ring = uni;              // backward sweep: 2 stash records
   double* Cs = ring + 2 * SS;      // Cs[k*NP+i] = C[i][k]
 
@@ -152,26 +158,43 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
     cp_async_commit();
   };
 
+  const bool init_per_seq = INHOMOG && (p.flags & SVAE_LDS_FLAG_INIT_PER_SEQ) != 0;
+  auto stage_pair = [&](int t) {              // pair parameters of step t -> pst slot t&1 (own column of each block)
+    if (INHOMOG) {
+      const size_t off = (size_t)t * p.pair_stride_t + (size_t)b * p.pair_stride_b + c;
+      double* dst = pst + (t & 1) * PB + c;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        cp_async8(dst + i * NP, p.J11 + off + i * N);
+        cp_async8(dst + N * NP + i * NP, p.J12 + off + i * N);
+        cp_async8(dst + 2 * N * NP + i * NP, p.J22 + off + i * N);
+      }
+      cp_async_commit();
+    }
+  };
+
   double lacc = 0.0;     // - 1/2 sum log d (this lane's pivots)
   double lq = 0.0;       // sum_t h_f[c] m_t[c]
   double dprod = 1.0;
   int badbits = 0;
 
+  if (INHOMOG && T > 1) stage_pair(0);
   stage_node(0);
   if (T > 1) stage_node(1); else cp_async_commit();
+  cp_async_wait<1>();                          // everything but node 1 has landed (own elements only are read here)
 
   // a: column c of M_t = J_pred + J11 (the node precision joins at the pivot), information form
   double a[N];
-  double hpred = p.init_h[c];
+  const double* iJ = p.init_J + (init_per_seq ? (size_t)b * NN : 0);
+  double hpred = p.init_h[(init_per_seq ? (size_t)b * N : 0) + c];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    a[i] = -2.0 * p.init_J[i * N + c];
-    if (T > 1) a[i] -= 2.0 * p.J11[i * N + c];
+    a[i] = -2.0 * iJ[i * N + c];
+    if (T > 1) a[i] -= 2.0 * (INHOMOG ? pst[i * NP + c] : p.J11[i * N + c]);
   }
   double mu = 0.0, x[SA];
 #pragma unroll
   for (int s = 0; s < SA; ++s) x[s] = 0.0;
-  cp_async_wait<1>();
 
   // =========================== forward in time: information filter ===========================
   for (int t = 0; t < T; ++t) {
@@ -186,10 +209,12 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
     hfv[c] = hf;                    // visible to the other lanes after the elimination's barriers
 
     // right-hand sides: r = column c of J12 (-> Y = M^-1 J12), q = e_c (-> column c of M^-1)
+    const double* pb = pst + (t & 1) * PB;      // INHOMOG: this step's J11 | J12 | J22
+    if (INHOMOG && t + 1 < T - 1) stage_pair(t + 1);   // the other slot is free since the end of the previous step
     double r[N], q[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      r[i] = last ? 0.0 : shJ12[i * NP + c];
+      r[i] = last ? 0.0 : (INHOMOG ? -pb[N * NP + i * NP + c] : shJ12[i * NP + c]);
       q[i] = (i == c) ? 1.0 : 0.0;
     }
 
@@ -316,21 +341,32 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
     }
     SVAE_CLK(4)
     if (!last) {
-      cp_async_wait<0>();            // own elements of step t+1 have landed (no cross-lane reads of the ring)
+      cp_async_wait<0>();            // own elements of step t+1 (node potentials, pair parameters) have landed
       if (t + 2 < T) stage_node(t + 2);
       // predict straight into next step's M:  J22 + J11 - J12' Y   (information-form J12 = -natural J12)
-      const double* pm = (t + 1 == T - 1) ? shJ22 : shJ11;
+      if (INHOMOG) {
+        const double* pn = pst + ((t + 1) & 1) * PB;              // next step's J11 (own column: no barrier needed)
 #pragma unroll
-      for (int i = 0; i < N; ++i) a[i] = pm[i * NP + c];
-#ifdef SVAE_PACKED_SLOT0     // experiment: compile-time constant bank address (immediate operands instead of LDCU)
-      const double* cj12 = c_J12[0];
-#else
-      const double* cj12 = c_J12[p.const_slot];
-#endif
+        for (int i = 0; i < N; ++i) a[i] = -2.0 * pb[2 * N * NP + i * NP + c] - ((t + 1 < T - 1) ? 2.0 * pn[i * NP + c] : 0.0);
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
+        for (int k = 0; k < N; ++k) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) a[i] = fma(cj12[k * N + i], r[k], a[i]);
+          for (int q2 = 0; q2 < NP / 2; ++q2) {
+            const double2 w = ld2(&pb[N * NP + k * NP + 2 * q2]);   // natural J12[k][:]: visible since the last barrier
+            a[2 * q2] = fma(w.x, r[k], a[2 * q2]);
+            if (2 * q2 + 1 < N) a[2 * q2 + 1] = fma(w.y, r[k], a[2 * q2 + 1]);
+          }
+        }
+      } else {
+        const double* pm = (t + 1 == T - 1) ? shJ22 : shJ11;
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = pm[i * NP + c];
+        const double* cj12 = c_J12[p.const_slot];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) a[i] = fma(cj12[k * N + i], r[k], a[i]);
+        }
       }
       hpred = -hq;
     } else {
@@ -355,8 +391,15 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
       double tot = 0.0;
 #pragma unroll
       for (int i = 0; i < N; ++i) tot += hfv[i];
-      double konst = p.init_logZ ? p.init_logZ[0] : 0.0;
-      if (p.pair_logZ) konst += (double)(T - 1) * p.pair_logZ[0];
+      double konst = p.init_logZ ? p.init_logZ[init_per_seq ? b : 0] : 0.0;
+      if (p.pair_logZ) {
+        if (!INHOMOG) {
+          konst += (double)(T - 1) * p.pair_logZ[0];
+        } else {
+          const size_t lz0 = (size_t)b * p.pair_stride_b / NN, lzs = (size_t)p.pair_stride_t / NN;   // strides are multiples of n^2
+          for (int t = 0; t < T - 1; ++t) konst += p.pair_logZ[lz0 + (size_t)t * lzs];
+        }
+      }
       if (p.node_logZ)
         for (int t = 0; t < T; ++t) konst += p.node_logZ[(size_t)b * T + t];
       p.lognorm[b] = tot + konst;
@@ -519,16 +562,32 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
         if (!lastt) acc_xxn[i] = fma(mi, mun, acc_xxn[i]);
         if (valid) {
           const size_t o = (size_t)b * NN + i * N + c;
-          if (lastt) p.E_pair_xnxn[o] = (T > 1) ? exx : 0.0;
+          if (lastt && p.E_pair_xnxn) p.E_pair_xnxn[o] = (T > 1) ? exx : 0.0;
           if (first) {
             p.E_init_xx[o] = exx;
-            p.E_pair_xx[o] = (T > 1) ? acc_mid[i] + exx : 0.0;
-            p.E_pair_xxn[o] = acc_xxn[i];
-            if (T > 1) p.E_pair_xnxn[o] = (lastt ? 0.0 : p.E_pair_xnxn[o]) + acc_mid[i];
+            if (p.E_pair_xx) p.E_pair_xx[o] = (T > 1) ? acc_mid[i] + exx : 0.0;
+            if (p.E_pair_xxn) p.E_pair_xxn[o] = acc_xxn[i];
+            if (p.E_pair_xnxn && T > 1) p.E_pair_xnxn[o] = (lastt ? 0.0 : p.E_pair_xnxn[o]) + acc_mid[i];
           }
         }
       }
       if (first && valid) p.E_init_x[(size_t)b * N + c] = mu;
+    }
+    if (INHOMOG && p.Exx_t && valid) {
+      // per-time second moments: E[x_t x_t'][:,c] = Sigma_t[:,c] + mu_t mu_t[c],  E[x_t x_{t+1}'][:,c] = C[:,c] + mu_t mu_{t+1}[c]
+      double* ox = p.Exx_t + ((size_t)b * T + t) * NN + c;
+      double* oxn = (p.Exxn_t && !lastt) ? p.Exxn_t + ((size_t)b * (T - 1) + t) * NN + c : nullptr;
+#pragma unroll
+      for (int q2 = 0; q2 < NP / 2; ++q2) {
+        const double2 w = ld2(&mu_s[2 * q2]);
+        const double2 cv = ld2(&Cs[c * NP + 2 * q2]);               // C[:,c]: this lane's own row of the tile
+        ox[(2 * q2) * N] = fma(w.x, mu, z[2 * q2]);
+        if (oxn) oxn[(2 * q2) * N] = fma(w.x, mun, cv.x);
+        if (2 * q2 + 1 < N) {
+          ox[(2 * q2 + 1) * N] = fma(w.y, mu, z[2 * q2 + 1]);
+          if (oxn) oxn[(2 * q2 + 1) * N] = fma(w.y, mun, cv.y);
+        }
+      }
     }
     if (valid) {
       oEx[t * N] = mu;

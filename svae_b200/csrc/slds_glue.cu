@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <cstdlib>
+#include <initializer_list>
 #include "svae_b200.h"
 
 extern std::atomic<uint64_t> g_svae_launches;
@@ -188,6 +190,215 @@ static cudaError_t glue_launch(Kern kern, int B, int T, int n, int K, cudaStream
   return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// K <= 8: both contractions are (B T) x {3 n^2} x 8 products in fp64 -- the shape of the fp64 tensor-core instruction
+// mma.m8n8k4 (one warp: 8 rows x 8 modes, 4 elements of the inner dimension per issue).  A warp owns 8 consecutive
+// (sequence, time) rows; the K mode blocks sit in shared memory in the fragment order, so a step is one global (or one
+// shared) load + one mma per lane instead of 24 shared loads + 24 fma of the row-per-warp kernels below, which stay as
+// the general path (K <= 32).  Fragment layout (PTX ISA, mma.m8n8k4 .f64): g = lane >> 2, q = lane & 3;
+// A[g][q], B[q][g], C[g][2q], C[g][2q+1].
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__host__ __device__ inline int mma_nn4(int n) { return (n * n + 3) & ~3; }     // inner dimension padded to the k-step
+__host__ __device__ inline int mma_n4(int n) { return (n + 3) & ~3; }
+// mix kernel: row stride of the [k][e] blocks, == 8 (mod 16) doubles so that the 4 k-rows of a B fragment tile the banks
+__host__ __device__ inline int mma_ld8(int cols) { const int c = (cols + 7) & ~7; return (c & 15) == 8 ? c : c + 8; }
+
+size_t glue_mma_node_smem(int n) { return sizeof(double) * 8 * ((size_t)4 * mma_nn4(n) + mma_n4(n)); }
+size_t glue_mma_mix_smem(int n) { return sizeof(double) * 8 * ((size_t)4 * mma_ld8(n * n) + mma_ld8(n + 2)); }
+
+// node (B,T,8-or-fewer): see slds_node_potentials_kernel for the contraction
+__global__ void __launch_bounds__(256) slds_node_potentials_mma_kernel(
+    int B, int T, int n, int K, const double* __restrict__ Exx_t, const double* __restrict__ Exxn_t,
+    const double* __restrict__ Ex0, const double* __restrict__ iJ, const double* __restrict__ ih,
+    const double* __restrict__ ic, const double* __restrict__ J11, const double* __restrict__ J12,
+    const double* __restrict__ J22, const double* __restrict__ lZ, const int* __restrict__ active,
+    double* __restrict__ node) {
+  extern __shared__ double sm[];
+  const int nn = n * n, nn4 = mma_nn4(n), n4 = mma_n4(n);
+  double* s11 = sm;                   // [e][k], k fastest (8 wide, zero beyond K and beyond n^2)
+  double* s12 = s11 + 8 * nn4;
+  double* s22 = s12 + 8 * nn4;
+  double* sJ = s22 + 8 * nn4;
+  double* sh = sJ + 8 * nn4;          // [i][k]
+  for (int x = threadIdx.x; x < 8 * nn4; x += blockDim.x) {
+    const int e = x >> 3, k = x & 7;
+    const bool in = e < nn && k < K;
+    s11[x] = in ? J11[k * nn + e] : 0.0;
+    s12[x] = in ? J12[k * nn + e] : 0.0;
+    s22[x] = in ? J22[k * nn + e] : 0.0;
+    sJ[x] = in ? iJ[k * nn + e] : 0.0;
+  }
+  for (int x = threadIdx.x; x < 8 * n4; x += blockDim.x) {
+    const int e = x >> 3, k = x & 7;
+    sh[x] = (e < n && k < K) ? ih[k * n + e] : 0.0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, wpb = blockDim.x >> 5;
+  const long long rows = (long long)B * T, groups = (rows + 7) >> 3;
+  for (long long grp = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); grp < groups; grp += (long long)gridDim.x * wpb) {
+    const long long row = grp * 8 + g;
+    const bool inr = row < rows;
+    const long long rc = inr ? row : rows - 1;
+    const long long b = rc / T;
+    const int t = (int)(rc - b * T);
+    const bool act = inr && (!active || active[b] != 0);
+    const bool trans = act && t > 0, first = act && t == 0;
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0, f0 = 0.0, f1 = 0.0;       // three independent accumulation chains
+    const double* pa = Exx_t + (size_t)(rc - (t > 0)) * nn + q;            // E[x_{t-1} x_{t-1}']
+    const double* pc = Exx_t + (size_t)rc * nn + q;                        // E[x_t x_t']
+    const double* px = Exxn_t + ((size_t)b * (T - 1) + (t > 0 ? t - 1 : 0)) * nn + q;   // E[x_{t-1} x_t']
+    const double* b11 = s11 + q * 8 + g;
+    const double* b12 = s12 + q * 8 + g;
+    const double* b22 = s22 + q * 8 + g;
+#pragma unroll 5
+    for (int e0 = 0; e0 < nn4; e0 += 4) {
+      const bool ld = trans && e0 + q < nn;
+      const double va = ld ? pa[e0] : 0.0, vx = ld ? px[e0] : 0.0, vc = ld ? pc[e0] : 0.0;
+      dmma884(c0, c1, va, b11[e0 * 8]);
+      dmma884(d0, d1, vx, b12[e0 * 8]);
+      dmma884(f0, f1, vc, b22[e0 * 8]);
+    }
+    if (__any_sync(0xffffffffu, first)) {                                   // a row group holding the start of a sequence
+      const double* bJ = sJ + q * 8 + g;
+      const double* bh = sh + q * 8 + g;
+      for (int e0 = 0; e0 < nn4; e0 += 4) dmma884(c0, c1, (first && e0 + q < nn) ? pc[e0] : 0.0, bJ[e0 * 8]);
+      const double* p0 = Ex0 + (size_t)b * n + q;
+      for (int e0 = 0; e0 < n4; e0 += 4) dmma884(d0, d1, (first && e0 + q < n) ? p0[e0] : 0.0, bh[e0 * 8]);
+    }
+    if (act) {
+      const int k0 = 2 * q;
+      const double* cst = (t == 0) ? ic : lZ;
+      double* o = node + (size_t)row * K + k0;
+      const double v0 = c0 + d0 + f0, v1 = c1 + d1 + f1;
+      if (K == 8) {
+        *reinterpret_cast<double2*>(o) = make_double2(v0 + cst[k0], v1 + cst[k0 + 1]);
+      } else {
+        if (k0 < K) o[0] = v0 + cst[k0];
+        if (k0 + 1 < K) o[1] = v1 + cst[k0 + 1];
+      }
+    }
+  }
+}
+
+// init / pair parameters mixed with E[z] (B,T,K <= 8): see slds_mix_kernel
+__global__ void __launch_bounds__(256) slds_mix_mma_kernel(
+    int B, int T, int n, int K, const double* __restrict__ Ez, const double* __restrict__ iJ,
+    const double* __restrict__ ih, const double* __restrict__ ic, const double* __restrict__ J11,
+    const double* __restrict__ J12, const double* __restrict__ J22, const double* __restrict__ lZ,
+    const int* __restrict__ active, double* __restrict__ oJ, double* __restrict__ oh, double* __restrict__ oc,
+    double* __restrict__ o11, double* __restrict__ o12, double* __restrict__ o22, double* __restrict__ olZ) {
+  extern __shared__ double sm[];
+  const int nn = n * n, ld = mma_ld8(nn), ldv = mma_ld8(n + 2);
+  double* s11 = sm;                  // [k][e], e fastest, row stride ld (zero beyond K and beyond n^2)
+  double* s12 = s11 + 8 * ld;
+  double* s22 = s12 + 8 * ld;
+  double* sJ = s22 + 8 * ld;
+  double* sv = sJ + 8 * ld;          // [k][ ih (n) | ic | lZ ]
+  for (int x = threadIdx.x; x < 8 * ld; x += blockDim.x) {
+    const int k = x / ld, e = x - k * ld;
+    const bool in = e < nn && k < K;
+    s11[x] = in ? J11[k * nn + e] : 0.0;
+    s12[x] = in ? J12[k * nn + e] : 0.0;
+    s22[x] = in ? J22[k * nn + e] : 0.0;
+    sJ[x] = in ? iJ[k * nn + e] : 0.0;
+  }
+  for (int x = threadIdx.x; x < 8 * ldv; x += blockDim.x) {
+    const int k = x / ldv, e = x - k * ldv;
+    sv[x] = (k >= K) ? 0.0 : (e < n ? ih[k * n + e] : (e == n ? ic[k] : (e == n + 1 ? lZ[k] : 0.0)));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, wpb = blockDim.x >> 5;
+  const long long rows = (long long)B * T, groups = (rows + 7) >> 3;
+  const bool vec2 = (nn & 1) == 0;                                          // 16-byte stores stay aligned
+  for (long long grp = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); grp < groups; grp += (long long)gridDim.x * wpb) {
+    const long long rowA = grp * 8 + g;                                     // A fragment: this lane's row of E[z]
+    const long long rcA = rowA < rows ? rowA : rows - 1;
+    const double w_lo = (rowA < rows && q < K) ? Ez[(size_t)rcA * K + q] : 0.0;
+    const double w_hi = (rowA < rows && 4 + q < K) ? Ez[(size_t)rcA * K + 4 + q] : 0.0;
+    // C fragment: row g again, columns e0 + 2q, e0 + 2q + 1
+    const long long b = rcA / T;
+    const int t = (int)(rcA - b * T);
+    const bool act = rowA < rows && (!active || active[b] != 0);
+    const bool trans = act && t > 0, first = act && t == 0;
+    const size_t o = ((size_t)b * (T - 1) + (t > 0 ? t - 1 : 0)) * nn;
+    auto tile = [&](const double* sB, int stride, int e0, double& v0, double& v1) {
+      v0 = 0.0; v1 = 0.0;
+      dmma884(v0, v1, w_lo, sB[q * stride + e0 + g]);
+      dmma884(v0, v1, w_hi, sB[(4 + q) * stride + e0 + g]);
+    };
+    auto put = [&](double* dst, int e, int lim, double v0, double v1) {       // dst already offset to the row
+      if (vec2 && e + 1 < lim) *reinterpret_cast<double2*>(dst + e) = make_double2(v0, v1);
+      else { if (e < lim) dst[e] = v0; if (e + 1 < lim) dst[e + 1] = v1; }
+    };
+    if (__any_sync(0xffffffffu, trans)) {
+#pragma unroll 2
+      for (int e0 = 0; e0 < nn; e0 += 8) {
+        double a0, a1, x0, x1, c0, c1;
+        tile(s11, ld, e0, a0, a1);
+        tile(s12, ld, e0, x0, x1);
+        tile(s22, ld, e0, c0, c1);
+        if (trans) {
+          const int e = e0 + 2 * q;
+          put(o11 + o, e, nn, a0, a1);
+          put(o12 + o, e, nn, x0, x1);
+          put(o22 + o, e, nn, c0, c1);
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, first)) {
+      for (int e0 = 0; e0 < nn; e0 += 8) {
+        double v0, v1;
+        tile(sJ, ld, e0, v0, v1);
+        if (first) put(oJ + (size_t)b * nn, e0 + 2 * q, nn, v0, v1);
+      }
+    }
+    for (int e0 = 0; e0 < n + 2; e0 += 8) {                                   // h (t = 0), init constant (t = 0), pair logZ (t > 0)
+      double v[2];
+      tile(sv, ldv, e0, v[0], v[1]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int e = e0 + 2 * q + j;
+        if (first && e < n) oh[(size_t)b * n + e] = v[j];
+        if (first && e == n) oc[b] = v[j];
+        if (trans && e == n + 1) olZ[(size_t)b * (T - 1) + (t - 1)] = v[j];
+      }
+    }
+  }
+}
+
+template <typename Kern, typename... Args>
+static cudaError_t glue_mma_launch(Kern kern, size_t smem, int B, int T, int n, int K, cudaStream_t stream, Args... args) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long groups = ((long long)B * T + 7) / 8;
+  long long grid = (groups + 7) / 8;                 // 8 warps per CTA, one 8-row group per warp and pass
+  const long long cap = (long long)sms * 8;
+  if (grid > cap) grid = cap;
+  kern<<<(unsigned)grid, 256, smem, stream>>>(B, T, n, K, args...);
+  return cudaGetLastError();
+}
+
+static bool aligned16(std::initializer_list<const void*> ps) {
+  for (const void* q : ps) if (reinterpret_cast<uintptr_t>(q) & 15) return false;
+  return true;
+}
+
+static bool glue_use_mma(int n, int K) {
+  static const bool enabled = [] { const char* e = getenv("SVAE_SLDS_MMA"); return !(e && atoi(e) == 0); }();
+  return enabled && K <= 8 && glue_mma_node_smem(n) <= 200 * 1024 && glue_mma_mix_smem(n) <= 200 * 1024;
+}
+
 }  // namespace svae
 
 extern "C" int svae_slds_node_potentials(int B, int T, int n, int K, const double* Exx_t, const double* Exxn_t,
@@ -201,7 +412,8 @@ extern "C" int svae_slds_node_potentials(int B, int T, int n, int K, const doubl
   if (T == 1) { J11 = J12 = J22 = init_J; pair_logZ = init_c; Exxn_t = Exx_t; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if (K <= 8) e = svae::glue_launch(svae::slds_node_potentials_kernel<8>, B, T, n, K, st, Exx_t, Exxn_t, Ex0, init_J, init_h, init_c, J11, J12, J22, pair_logZ, active, node);
+  if (svae::glue_use_mma(n, K) && svae::aligned16({node})) e = svae::glue_mma_launch(svae::slds_node_potentials_mma_kernel, svae::glue_mma_node_smem(n), B, T, n, K, st, Exx_t, Exxn_t, Ex0, init_J, init_h, init_c, J11, J12, J22, pair_logZ, active, node);
+  else if (K <= 8) e = svae::glue_launch(svae::slds_node_potentials_kernel<8>, B, T, n, K, st, Exx_t, Exxn_t, Ex0, init_J, init_h, init_c, J11, J12, J22, pair_logZ, active, node);
   else if (K <= 16) e = svae::glue_launch(svae::slds_node_potentials_kernel<16>, B, T, n, K, st, Exx_t, Exxn_t, Ex0, init_J, init_h, init_c, J11, J12, J22, pair_logZ, active, node);
   else e = svae::glue_launch(svae::slds_node_potentials_kernel<32>, B, T, n, K, st, Exx_t, Exxn_t, Ex0, init_J, init_h, init_c, J11, J12, J22, pair_logZ, active, node);
   g_svae_launches.fetch_add(1);
@@ -220,7 +432,8 @@ extern "C" int svae_slds_mix_params(int B, int T, int n, int K, const double* Ez
   if (T == 1) { J11 = J12 = J22 = init_J; pair_logZ = init_c; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if (K <= 8) e = svae::glue_launch(svae::slds_mix_kernel<8>, B, T, n, K, st, Ez, init_J, init_h, init_c, J11, J12, J22, pair_logZ, active, out_init_J, out_init_h, out_init_c, out_J11, out_J12, out_J22, out_pair_logZ);
+  if (svae::glue_use_mma(n, K) && svae::aligned16({out_init_J, out_J11, out_J12, out_J22})) e = svae::glue_mma_launch(svae::slds_mix_mma_kernel, svae::glue_mma_mix_smem(n), B, T, n, K, st, Ez, init_J, init_h, init_c, J11, J12, J22, pair_logZ, active, out_init_J, out_init_h, out_init_c, out_J11, out_J12, out_J22, out_pair_logZ);
+  else if (K <= 8) e = svae::glue_launch(svae::slds_mix_kernel<8>, B, T, n, K, st, Ez, init_J, init_h, init_c, J11, J12, J22, pair_logZ, active, out_init_J, out_init_h, out_init_c, out_J11, out_J12, out_J22, out_pair_logZ);
   else if (K <= 16) e = svae::glue_launch(svae::slds_mix_kernel<16>, B, T, n, K, st, Ez, init_J, init_h, init_c, J11, J12, J22, pair_logZ, active, out_init_J, out_init_h, out_init_c, out_J11, out_J12, out_J22, out_pair_logZ);
   else e = svae::glue_launch(svae::slds_mix_kernel<32>, B, T, n, K, st, Ez, init_J, init_h, init_c, J11, J12, J22, pair_logZ, active, out_init_J, out_init_h, out_init_c, out_J11, out_J12, out_J22, out_pair_logZ);
   g_svae_launches.fetch_add(1);

@@ -128,10 +128,12 @@ static cudaError_t launch_packed(const LdsFwdParams& p, cudaStream_t stream) {
 static bool packed_eligible(const LdsFwdParams& p, bool inhomog) {
   static const bool enabled = [] { const char* e = getenv("SVAE_LDS_PACKED"); return !(e && atoi(e) == 0); }();
   if (!enabled || p.S > 2 || p.msg_J_pred || p.msg_h_pred || p.in_J_filt || p.in_h_filt || p.node_J_dense || p.term_J ||
-      !p.E_init_xx || !p.E_init_x || !p.E_node_xx || !p.E_node_x || !p.lognorm || (p.S > 0 && !p.samples))
+      (p.S > 0 && !p.samples))
     return false;
+  // statistic buffers are optional, in pairs (natural_lds_sample passes no E_init_* / E_pair_*)
+  if ((p.E_node_xx != nullptr) != (p.E_node_x != nullptr)) return false;
   if (inhomog) return true;       // per-sequence / per-time parameters, optional per-time outputs
-  return !(p.flags & SVAE_LDS_FLAG_INIT_PER_SEQ) && !p.Exx_t && !p.Exxn_t && p.E_pair_xx && p.E_pair_xxn && p.E_pair_xnxn;
+  return !(p.flags & SVAE_LDS_FLAG_INIT_PER_SEQ) && !p.Exx_t && !p.Exxn_t;
 }
 
 #define SVAE_CAT_(a, b) a##b

@@ -144,8 +144,9 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
   const double* nh = p.node_h + (size_t)b * T * N + c;
   const double* eps = S > 0 ? p.eps + (size_t)b * T * S * N + c : nullptr;
   // per-time outputs, element c of this sequence (the packed launcher requires every output buffer)
-  double* oEx = p.E_node_x + (size_t)b * T * N + c;
-  double* oExx = p.E_node_xx + (size_t)b * T * N + c;
+  const bool stats = p.E_node_x != nullptr;          // statistic buffers are optional (natural_lds_sample: samples only)
+  double* oEx = stats ? p.E_node_x + (size_t)b * T * N + c : nullptr;
+  double* oExx = stats ? p.E_node_xx + (size_t)b * T * N + c : nullptr;
   double* oSmp = S > 0 ? p.samples + (size_t)b * T * S * N + c : nullptr;
 
   // node potentials (+ noise) of time t -> ring slot t&1; every lane copies and later reads its own element only
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
       }
       if (p.node_logZ)
         for (int t = 0; t < T; ++t) konst += p.node_logZ[(size_t)b * T + t];
-      p.lognorm[b] = tot + konst;
+      if (p.lognorm) p.lognorm[b] = tot + konst;
     }
     // negative pivot (sign bit) or a NaN that reached the normaliser
     if ((badbits < 0 || !(part == part)) && p.status) atomicMax(p.status, (int)b + 1);
@@ -564,14 +565,14 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
           const size_t o = (size_t)b * NN + i * N + c;
           if (lastt && p.E_pair_xnxn) p.E_pair_xnxn[o] = (T > 1) ? exx : 0.0;
           if (first) {
-            p.E_init_xx[o] = exx;
+            if (p.E_init_xx) p.E_init_xx[o] = exx;
             if (p.E_pair_xx) p.E_pair_xx[o] = (T > 1) ? acc_mid[i] + exx : 0.0;
             if (p.E_pair_xxn) p.E_pair_xxn[o] = acc_xxn[i];
             if (p.E_pair_xnxn && T > 1) p.E_pair_xnxn[o] = (lastt ? 0.0 : p.E_pair_xnxn[o]) + acc_mid[i];
           }
         }
       }
-      if (first && valid) p.E_init_x[(size_t)b * N + c] = mu;
+      if (first && valid && p.E_init_x) p.E_init_x[(size_t)b * N + c] = mu;
     }
     if (INHOMOG && p.Exx_t && valid) {
       // per-time second moments: E[x_t x_t'][:,c] = Sigma_t[:,c] + mu_t mu_t[c],  E[x_t x_{t+1}'][:,c] = C[:,c] + mu_t mu_{t+1}[c]
@@ -590,8 +591,10 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
       }
     }
     if (valid) {
-      oEx[t * N] = mu;
-      oExx[t * N] = diag;
+      if (stats) {
+        oEx[t * N] = mu;
+        oExx[t * N] = diag;
+      }
 #pragma unroll
       for (int s = 0; s < S; ++s) oSmp[(t * S + s) * N] = x[s];
     }

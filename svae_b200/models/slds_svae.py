@@ -196,7 +196,7 @@ def _tree_where(mask, new, old):
 
 
 def optimize_local_meanfield(global_natparam, node_potentials, tol=1e-2, max_iter=100, init_eps=None, generator=None,
-                             dense=None, parallel_in_time="auto"):
+                             dense=None, parallel_in_time="auto", hmm_local=None):
     """slds_svae.py:159-175, batched: EVERY sequence follows the reference's rule on its own bound -- it stops (its
     factors are frozen) after the first sweep that moved its bound by less than `tol`, so B sequences in one call
     reproduce B reference calls whatever their sweep counts.  The per-mode expected parameters (loop-invariant) are
@@ -209,7 +209,7 @@ def optimize_local_meanfield(global_natparam, node_potentials, tol=1e-2, max_ite
     chunk-parallel drivers for few long sequences (torch glue, `_meanfield_torch`)."""
     hmm_global, lds_global = global_natparam
     dense = dense if dense is not None else get_all_lds_local_natparams(lds_global)
-    hmm_local = get_hmm_local_natparam(hmm_global)
+    hmm_local = hmm_local if hmm_local is not None else get_hmm_local_natparam(hmm_global)
     pit = use_parallel_in_time(node_potentials[1].shape[0], node_potentials[1].shape[1], parallel_in_time) \
         and not (torch.is_grad_enabled() and any(p.requires_grad for p in node_potentials[:2]))
     path = initialize_sample_path(node_potentials, init_eps, generator, pit)
@@ -355,6 +355,91 @@ def slds_prior_vlb(global_natparam, prior_natparam, lds_expected=None):
     return inner - (slds_prior_logZ(prior_natparam) - slds_prior_logZ(global_natparam))
 
 
+
+# ---- the global side of a step, replayed as ONE CUDA graph ------------------------------------------------
+# lds_global_expectedstats + get_all_lds_local_natparams + slds_prior_vlb are ~300 launches on (K, n+2, n+2)-sized
+# tensors: host-bound (about 4 ms of an SVI step whose kernels take 6).  They are a pure function of the stacked global
+# and prior natural parameters with static shapes, so the sequence is captured once per (shapes, device) and replayed:
+# inputs are copied into the graph's static buffers, outputs are read from them (the caller gets clones of what it
+# returns to its own caller).  Only taken when nothing on the global side needs a gradient -- the SVI step takes the
+# natural gradient in closed form (svae.py:33-34) and never differentiates the global KL -- and SVAE_SLDS_GRAPH != 0.
+
+def _global_side(hmm_global, g_niw, g_mniw, hmm_prior, p_niw, p_mniw):
+    lds_global = StackedLdsGlobal((g_niw, tuple(g_mniw)))
+    lds_expected = lds_global_expectedstats(lds_global)
+    dense = get_all_lds_local_natparams(lds_global, lds_expected)
+    global_vlb = slds_prior_vlb((tuple(hmm_global), lds_global), (tuple(hmm_prior), StackedLdsGlobal((p_niw, tuple(p_mniw)))),
+                                lds_expected)
+    hmm_local = get_hmm_local_natparam(tuple(hmm_global))
+    return lds_expected, dense, global_vlb, hmm_local
+
+
+_GLOBAL_GRAPHS = {}
+
+
+def _flatten(x, out):
+    if isinstance(x, (tuple, list)):
+        for y in x:
+            _flatten(y, out)
+    else:
+        out.append(x)
+    return out
+
+
+def _unflatten_like(x, it):
+    if isinstance(x, (tuple, list)):
+        return tuple(_unflatten_like(y, it) for y in x)
+    return next(it)
+
+
+def global_side(hmm_global, lds_global, hmm_prior, lds_prior):
+    """(lds_expected, dense, global_vlb, hmm_local) for stacked global / prior natural parameters; graph replay on CUDA."""
+    import os
+    args = (tuple(hmm_global), lds_global[0], tuple(lds_global[1]), tuple(hmm_prior), lds_prior[0], tuple(lds_prior[1]))
+    flat_in = _flatten(args, [])
+    eligible = (os.environ.get("SVAE_SLDS_GRAPH", "1") != "0" and all(torch.is_tensor(t) and t.is_cuda for t in flat_in)
+                and not (torch.is_grad_enabled() and any(t.requires_grad for t in flat_in))
+                and not torch.cuda.is_current_stream_capturing())
+    if not eligible:
+        return _global_side(*args)
+    key = (flat_in[0].device,) + tuple((tuple(t.shape), t.dtype) for t in flat_in)
+    entry = _GLOBAL_GRAPHS.get(key)
+    if entry is None:
+        entry = _GLOBAL_GRAPHS[key] = _capture_global_side(args, flat_in)
+    if entry is False:                                   # capture was refused once (an op that synchronises): stay eager
+        return _global_side(*args)
+    graph, static_in, static_out = entry
+    with torch.no_grad():
+        torch._foreach_copy_(static_in, [t.detach() for t in flat_in])
+        graph.replay()
+    lds_expected, dense, global_vlb, hmm_local = static_out
+    # static buffers are overwritten by the next call (silently: a replay does not bump version counters), so whatever
+    # can outlive this step -- returned values, tensors the autograd graph of the differentiable pass saves -- is cloned
+    dense = tuple(tuple(x.clone() for x in grp) for grp in dense)
+    return lds_expected, dense, global_vlb.clone(), tuple(x.clone() for x in hmm_local)
+
+
+def _capture_global_side(args, flat_in):
+    try:
+        with torch.no_grad():
+            static_in = [t.detach().clone() for t in flat_in]
+            static_args = _unflatten_like(args, iter(static_in))
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                        # warm-up off the capture (lazy handles, workspaces)
+                    _global_side(*static_args)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = _global_side(*static_args)
+        return graph, static_in, static_out
+    except Exception as e:                                # noqa: BLE001 -- any capture failure means "run eagerly"
+        print("svae_b200: SLDS global-side graph capture refused (%s: %s); running it eagerly" % (type(e).__name__, e), file=sys.stderr)
+        torch.cuda.synchronize()
+        return False
+
+
 def run_inference(prior_natparam, global_natparam, nn_potentials, num_samples, eps=None, init_eps=None, generator=None):
     """slds_svae.py:289-310: returns (samples, expected_stats, global_vlb, local_vlb)."""
     hmm_global_natparam, lds_global_natparam = global_natparam
@@ -364,17 +449,16 @@ def run_inference(prior_natparam, global_natparam, nn_potentials, num_samples, e
     lds_global_natparam = stack_lds_global(lds_global_natparam)
     global_natparam = (hmm_global_natparam, lds_global_natparam)
     prior_natparam = (prior_natparam[0], stack_lds_global(prior_natparam[1]))
-    lds_expected = lds_global_expectedstats(lds_global_natparam)
-    dense = get_all_lds_local_natparams(lds_global_natparam, lds_expected)
+    lds_expected, dense, global_vlb, hmm_local = global_side(hmm_global_natparam, lds_global_natparam, *prior_natparam)
     with torch.no_grad():
         (hmm_stats, _), (hmm_local_natparam, lds_local_natparam), _ = \
-            optimize_local_meanfield(global_natparam, unbox(pots), init_eps=init_eps, generator=generator, dense=dense)
+            optimize_local_meanfield(global_natparam, unbox(pots), init_eps=init_eps, generator=generator, dense=dense,
+                                     hmm_local=hmm_local)
     samples, lds_stats, lds_normalizer = natural_lds_inference_general(lds_local_natparam, pots, num_samples, eps=eps,
                                                                        generator=generator)
     hmm_vlb = get_hmm_vlb(lds_global_natparam, hmm_local_natparam, lds_stats, dense)
     global_lds_stats, local_lds_stats = lds_stats[:-1], lds_stats[-1]
     expected_stats = get_global_stats(hmm_stats, global_lds_stats)
-    global_vlb = slds_prior_vlb(global_natparam, prior_natparam, lds_expected)
     lds_vlb = lds_normalizer.sum() - contract(pots, local_lds_stats[:2])
     local_vlb = hmm_vlb.sum() + lds_vlb
     if not batched:

@@ -42,7 +42,8 @@ extern "C" {
 #define SVAE_ERR_CUDA (-4)          /* launch failed (cudaGetLastError != cudaSuccess)            */
 
 #define SVAE_LDS_MAX_N 16           /* latent dimension range compiled into the library: 1..16    */
-#define SVAE_HMM_MAX_K 32           /* discrete states: 1..32 (lane = state)                       */
+#define SVAE_HMM_MAX_K 32           /* discrete states of the register-resident kernels: 1..32 (lane = state) */
+#define SVAE_HMM_WIDE_MAX_K 1024    /* svae_hmm_estep_wide / svae_hmm_viterbi: 1..1024 (thread = state)       */
 #define SVAE_GMM_MAX_N 8            /* GMM latent dimension: 1..8                                  */
 
 /* flags for svae_lds_estep_fwd */
@@ -273,6 +274,16 @@ int svae_hmm_estep_masked(int B, int T, int K, int flags, const double* log_pi, 
                           const double* node, const int* active, double* logZ, double* Ez0, double* Etrans,
                           double* Ez, void* stream);
 
+/* The same E-step for ANY number of states up to SVAE_HMM_WIDE_MAX_K (the reference's hmm_logZ / hmm_logZ_grad take any
+ * K, svae/hmm/cython_hmm_inference.pyx:93-166).  K <= SVAE_HMM_MAX_K runs the register-resident kernel of
+ * svae_hmm_estep_masked and ignores the workspace; larger K runs one CTA per sequence (thread = state) and needs
+ * svae_hmm_wide_workspace_bytes(K) bytes of device scratch (exp(log_A - max), its transpose, the shift), written by a
+ * one-CTA preparation launch on the same stream.  Same arguments, outputs and mask otherwise. */
+size_t svae_hmm_wide_workspace_bytes(int K);
+int svae_hmm_estep_wide(int B, int T, int K, int flags, const double* log_pi, const double* log_A,
+                        const double* node, const int* active, double* logZ, double* Ez0, double* Etrans,
+                        double* Ez, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * SLDS local mean field: the two contractions that couple the HMM factor and the LDS factor, batched over
  * (sequence, time).  K discrete modes with per-mode parameters stacked on a leading K axis:
@@ -324,7 +335,8 @@ int svae_hmm_chain_viterbi(int B, int C, int K, const double* log_pi, const doub
                            const double* node_last, double* delta_scratch, int* boundary_states, void* stream);
 
 /* Viterbi path (svae/hmm/hmm_inference.py:54-63, pyhsmm `viterbi`): path (B,T) int32, first maximal
- * index on ties.  workspace: svae_hmm_viterbi_workspace_bytes() bytes of device scratch (back-pointers). */
+ * index on ties.  workspace: svae_hmm_viterbi_workspace_bytes() bytes of device scratch (back-pointers: one byte per
+ * (b,t,k) for K <= SVAE_HMM_MAX_K, two for K up to SVAE_HMM_WIDE_MAX_K, which runs one CTA per sequence). */
 size_t svae_hmm_viterbi_workspace_bytes(int B, int T, int K);
 int svae_hmm_viterbi(int B, int T, int K, const double* log_pi, const double* log_A, const double* node,
                      int32_t* path, void* workspace, size_t workspace_bytes, void* stream);

@@ -17,7 +17,8 @@ SVAE_LDS_SAVE_FOR_BWD = 2
 SVAE_LDS_INIT_PER_SEQ = 4
 SVAE_LDS_BWD_MESSAGES_OUT = 32
 SVAE_LDS_BWD_MESSAGES_IN = 64
-SVAE_HMM_MAX_K = 32
+SVAE_HMM_MAX_K = 32          # register-resident kernels (lane = state)
+SVAE_HMM_WIDE_MAX_K = 1024   # svae_hmm_estep_wide / svae_hmm_viterbi (thread = state)
 SVAE_GMM_MAX_N = 8
 SVAE_HMM_LOGZ_ONLY = 1
 
@@ -38,6 +39,8 @@ _SIGNATURES = {
     "svae_lds_estep_fwd_ex": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 21 + [_P, _P, _SZ, _P]),
     "svae_lds_estep_fwd_masked": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 22 + [_P, _P, _SZ, _P]),
     "svae_hmm_estep_masked": (_I, [_I] * 4 + [_P] * 8 + [_P]),
+    "svae_hmm_wide_workspace_bytes": (_SZ, [_I]),
+    "svae_hmm_estep_wide": (_I, [_I] * 4 + [_P] * 8 + [_P, _SZ, _P]),
     "svae_slds_mix_params": (_I, [_I] * 4 + [_P] * 16 + [_P]),
     "svae_slds_node_potentials": (_I, [_I] * 4 + [_P] * 12 + [_P]),
     "svae_gaussian_info_head_fwd": (_I, [_LL, _I] + [_P] * 5 + [_P]),

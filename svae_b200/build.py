@@ -18,6 +18,11 @@ OBJ = os.path.join(CSRC, "build" + ("_" + TAG if TAG else ""))
 INC = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libsvae_b200%s.so" % ("_" + TAG if TAG else ""))
 MAX_N = 16
+# experiment hook: SVAE_BUILD_NS="10,16" compiles the LDS kernels for those latent dimensions only (stubs for the rest);
+# refused for the untagged product library
+NS = [int(x) for x in os.environ.get("SVAE_BUILD_NS", "").split(",") if x]
+if NS and not TAG:
+    raise RuntimeError("SVAE_BUILD_NS needs SVAE_BUILD_TAG: the product library carries every latent dimension")
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -29,7 +34,8 @@ def _units():
     for f in sorted(os.listdir(CSRC)):
         if f.endswith("_inst.cu"):
             for n in range(1, MAX_N + 1):
-                units.append((f, ["-DSVAE_N=%d" % n], "%s_n%d.o" % (f[:-8], n)))
+                stub = ["-DSVAE_STUB"] if NS and n not in NS else []
+                units.append((f, ["-DSVAE_N=%d" % n] + stub, "%s_n%d.o" % (f[:-8], n)))
         elif f.endswith(".cu"):
             units.append((f, [], f[:-3] + ".o"))
     return units

@@ -61,8 +61,14 @@ __device__ __forceinline__ double hmm_rcp(double x) {
 // rescaling is legal, the logs are accounted exactly), and exp(node - max) of the NEXT step is computed while
 // the current dot product is in flight.  In the backward sweep E[z_t], the transition-count outer product and
 // the normaliser 1/s_t of step t are finished during step t-1.
+// -DSVAE_HMM_OSMEM=Q (K in 17..32 only): the transition-count accumulator (one 32-double column per lane, 64 registers)
+// lives in shared memory and is updated every Q steps from a ring of the last Q alpha vectors, so the kernel fits 128
+// registers and a K = 32 batch of 2048 sequences is resident in ONE wave (16 warps per SM) instead of two.
+#ifndef SVAE_HMM_OSMEM
+#define SVAE_HMM_OSMEM 0
+#endif
 #ifndef SVAE_HMM_MINB32
-#define SVAE_HMM_MINB32 8
+#define SVAE_HMM_MINB32 (SVAE_HMM_OSMEM ? 16 : 8)
 #endif
 template <int LPS>
 __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_estep_kernel(const HmmParams p) {
@@ -70,6 +76,9 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
   constexpr int LP = (LPS + 1) & ~1;
   constexpr int LQ = LP < 2 ? 2 : LP;
   __shared__ __align__(16) double sbuf[SPW][8][LQ];
+  constexpr int OQ = (LPS == 32) ? SVAE_HMM_OSMEM : 0;       // pending outer products per flush (0: registers)
+  __shared__ __align__(16) double Osm[OQ ? 32 * 32 : 2];      // Osm[i*32 + j]: column j belongs to lane j
+  __shared__ __align__(16) double aring[OQ ? OQ : 1][LQ];     // alpha vectors of the pending outer products
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPS, j = lane % LPS;
   const int K = p.K, T = p.T;
@@ -154,9 +163,35 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
   double Pr[LPS];   // row j of P:  Pr[i] = P[j][i]
 #pragma unroll
   for (int i = 0; i < LPS; ++i) Pr[i] = (act && i < K) ? exp(p.log_A[j * K + i] - gmax) : 0.0;
-  double O[LPS];    // column j of sum_t alpha_t (x) w_{t+1} / s_t
+  double O[OQ ? 1 : LPS];    // column j of sum_t alpha_t (x) w_{t+1} / s_t
+  double wq[OQ ? OQ : 1];    // OQ: the scaled w_{t+1}[j] of the pending outer products
+  int npend = 0;
+  if (OQ) {
 #pragma unroll
-  for (int i = 0; i < LPS; ++i) O[i] = 0.0;
+    for (int i = 0; i < 32; ++i) Osm[i * 32 + j] = 0.0;
+#pragma unroll
+    for (int q = 0; q < (OQ ? OQ : 1); ++q) { wq[q] = 0.0; aring[q][j] = 0.0; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < (OQ ? 1 : LPS); ++i) O[i] = 0.0;
+  }
+  // OQ: Osm[:, j] += sum_q aring[q][:] * wq[q]   (own column: no other lane touches it)
+  auto flush = [&]() {
+#pragma unroll
+    for (int i2 = 0; i2 < 16; ++i2) {
+      double o0 = Osm[(2 * i2) * 32 + j], o1 = Osm[(2 * i2 + 1) * 32 + j];
+#pragma unroll
+      for (int q = 0; q < (OQ ? OQ : 1); ++q) {
+        const double2 a2 = *reinterpret_cast<const double2*>(&aring[q][2 * i2]);
+        o0 = fma(a2.x, wq[q], o0);
+        o1 = fma(a2.y, wq[q], o1);
+      }
+      Osm[(2 * i2) * 32 + j] = o0;
+      Osm[(2 * i2 + 1) * 32 + j] = o1;
+    }
+#pragma unroll
+    for (int q = 0; q < (OQ ? OQ : 1); ++q) wq[q] = 0.0;
+  };
   __syncwarp();
   double bet = act ? 1.0 : 0.0;     // beta_{t+1}, arbitrary positive scale
   double kb = 1.0;                  // lagged rescaling of beta
@@ -175,7 +210,7 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
     const int sl = 2 + 3 * (t & 1);
     double* wb = sbuf[sub][sl];
     double* pbf = sbuf[sub][sl + 1];
-    double* ab = sbuf[sub][sl + 2];
+    double* ab = OQ ? aring[npend] : sbuf[sub][sl + 2];
     const double w = exl * bet * kb;          // w_{t+1}[j]
     wb[j] = w;
     pbf[j] = prd_prev;                        // alpha_{t+1} .* (P w_{t+2})
@@ -202,11 +237,22 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
       const double invs = hmm_rcp((ss[0] + ss[1]) + (ss[2] + ss[3]));
       if (act && valid) Ez[(size_t)(t + 1) * K + j] = prd_prev * invs;
       const double wsc = w_prev * invs;
+      if (OQ) {
 #pragma unroll
-      for (int i2 = 0; i2 < LPS / 2; ++i2) {
-        const double2 a2 = *reinterpret_cast<const double2*>(&ab[2 * i2]);
-        O[2 * i2] = fma(a2.x, wsc, O[2 * i2]);
-        O[2 * i2 + 1] = fma(a2.y, wsc, O[2 * i2 + 1]);
+        for (int q = 0; q < (OQ ? OQ : 1); ++q)
+          if (q == npend) wq[q] = wsc;
+        if (++npend == OQ) {          // warp-uniform
+          flush();
+          npend = 0;
+          __syncwarp();               // the ring is rewritten from the next iteration on
+        }
+      } else {
+#pragma unroll
+        for (int i2 = 0; i2 < LPS / 2; ++i2) {
+          const double2 a2 = *reinterpret_cast<const double2*>(&ab[2 * i2]);
+          O[2 * i2] = fma(a2.x, wsc, O[2 * i2]);
+          O[2 * i2 + 1] = fma(a2.y, wsc, O[2 * i2 + 1]);
+        }
       }
       kb = invs;
     }
@@ -230,15 +276,25 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
     const double invs = 1.0 / s0;
     ez0 = prd_prev * invs;
     if (act && valid) Ez[j] = ez0;
-    double* ab = sbuf[sub][0];
-    ab[j] = at_prev;
-    __syncwarp();
     const double wsc = w_prev * invs;
+    if (OQ) {
+      __syncwarp();
+      aring[npend][j] = at_prev;
 #pragma unroll
-    for (int i2 = 0; i2 < LPS / 2; ++i2) {
-      const double2 a2 = *reinterpret_cast<const double2*>(&ab[2 * i2]);
-      O[2 * i2] = fma(a2.x, wsc, O[2 * i2]);
-      O[2 * i2 + 1] = fma(a2.y, wsc, O[2 * i2 + 1]);
+      for (int q = 0; q < (OQ ? OQ : 1); ++q)
+        if (q == npend) wq[q] = wsc;
+      __syncwarp();
+      flush();                        // the slots past npend carry wq = 0 and finite (stale or zero) alpha values
+    } else {
+      double* ab = sbuf[sub][0];
+      ab[j] = at_prev;
+      __syncwarp();
+#pragma unroll
+      for (int i2 = 0; i2 < LPS / 2; ++i2) {
+        const double2 a2 = *reinterpret_cast<const double2*>(&ab[2 * i2]);
+        O[2 * i2] = fma(a2.x, wsc, O[2 * i2]);
+        O[2 * i2 + 1] = fma(a2.y, wsc, O[2 * i2 + 1]);
+      }
     }
   }
   __syncwarp();
@@ -247,7 +303,7 @@ __global__ void __launch_bounds__(32, (LPS == 32) ? SVAE_HMM_MINB32 : 16) hmm_es
     if (p.Etrans) {
 #pragma unroll
       for (int i = 0; i < LPS; ++i)
-        if (i < K) p.Etrans[(size_t)b * K * K + i * K + j] = exp(p.log_A[i * K + j] - gmax) * O[i];
+        if (i < K) p.Etrans[(size_t)b * K * K + i * K + j] = exp(p.log_A[i * K + j] - gmax) * (OQ ? Osm[i * 32 + j] : O[OQ ? 0 : i]);
     }
   }
 }
@@ -319,6 +375,10 @@ __global__ void __launch_bounds__(32) hmm_viterbi_kernel(const ViterbiParams p) 
 template <int LPS>
 static cudaError_t launch_hmm(const HmmParams& p, cudaStream_t s) {
   constexpr int SPW = 32 / LPS;
+  if (LPS == 32 && SVAE_HMM_OSMEM) {
+    // 16 one-warp CTAs of 11 KB each per SM: ask for the large shared-memory carve-out (a hint; per device, cheap)
+    cudaFuncSetAttribute(hmm_estep_kernel<LPS>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  }
   hmm_estep_kernel<LPS><<<(unsigned)((p.B + SPW - 1) / SPW), 32, 0, s>>>(p);
   return cudaGetLastError();
 }
@@ -372,17 +432,22 @@ extern "C" int svae_hmm_estep(int B, int T, int K, int flags, const double* log_
   return svae_hmm_estep_masked(B, T, K, flags, log_pi, log_A, node, nullptr, logZ, Ez0, Etrans, Ez, stream);
 }
 
+int svae_hmm_viterbi_wide_launch(int B, int T, int K, const double* log_pi, const double* log_A, const double* node,
+                                 int32_t* path, void* workspace, cudaStream_t s);   // hmm_wide.cu
+
 extern "C" size_t svae_hmm_viterbi_workspace_bytes(int B, int T, int K) {
   if (B <= 0 || T <= 0 || K <= 0) return 0;
-  return (size_t)B * (size_t)T * (size_t)K;
+  return (size_t)B * (size_t)T * (size_t)K * (K > SVAE_HMM_MAX_K ? 2 : 1);    // 8- or 16-bit back-pointers
 }
 
 extern "C" int svae_hmm_viterbi(int B, int T, int K, const double* log_pi, const double* log_A, const double* node,
                                 int32_t* path, void* workspace, size_t workspace_bytes, void* stream) {
   if (B <= 0 || T <= 0 || K <= 0) return SVAE_ERR_BAD_ARG;
   if (!log_pi || !log_A || !node || !path || !workspace) return SVAE_ERR_BAD_ARG;
-  if (K > SVAE_HMM_MAX_K) return SVAE_ERR_UNSUPPORTED;
+  if (K > SVAE_HMM_WIDE_MAX_K) return SVAE_ERR_UNSUPPORTED;
   if (workspace_bytes < svae_hmm_viterbi_workspace_bytes(B, T, K)) return SVAE_ERR_WORKSPACE;
+  if (K > SVAE_HMM_MAX_K)
+    return svae_hmm_viterbi_wide_launch(B, T, K, log_pi, log_A, node, path, workspace, static_cast<cudaStream_t>(stream));
   svae::ViterbiParams p;
   p.B = B; p.T = T; p.K = K; p.log_pi = log_pi; p.log_A = log_A; p.node = node;
   p.path = path; p.back = static_cast<uint8_t*>(workspace);

@@ -8,6 +8,20 @@
 #error "compile with -DSVAE_N=<latent dim>"
 #endif
 
+#define SVAE_CAT_(a, b) a##b
+#define SVAE_CAT(a, b) SVAE_CAT_(a, b)
+
+#ifdef SVAE_STUB
+// experiment builds (SVAE_BUILD_NS=...): latent dimensions left out of a variant library
+namespace svae {
+cudaError_t SVAE_CAT(lds_bwd_launch_n, SVAE_N)(const LdsBwdParams&, int, cudaStream_t) { return cudaErrorNotSupported; }
+}
+#else
+
+#ifndef SVAE_LDS_BWD_PACKED_MAXN
+#define SVAE_LDS_BWD_PACKED_MAXN 16
+#endif
+
 namespace svae {
 
 template <int N, int LPS, bool PER_T>
@@ -47,13 +61,13 @@ static cudaError_t launch_bwd_packed(const LdsBwdParams& p, cudaStream_t stream)
 
 static bool bwd_packed_eligible(const LdsBwdParams& p) {
   static const bool enabled = [] { const char* e = getenv("SVAE_LDS_PACKED"); return !(e && atoi(e) == 0); }();
+  // largest latent dimension the packed VJP takes (it spills beyond n = 12: DESIGN.md 3.2); dev override by environment
+  static const int max_n = [] { const char* e = getenv("SVAE_LDS_BWD_PACKED_MAXN"); return e ? atoi(e) : SVAE_LDS_BWD_PACKED_MAXN; }();
+  if (SVAE_N > max_n) return false;
   return enabled && p.S <= 2 && (p.flags & (SVAE_LDS_BWD_SWEEP1_ONLY | SVAE_LDS_BWD_SWEEP2_ONLY)) == 0 && !p.g_E_init_xx &&
          !p.g_E_init_x && !p.g_E_pair_xx && !p.g_E_pair_xxn && !p.g_E_pair_xnxn && !p.g_Exx_t && !p.g_Exxn_t &&
          !p.g_node_J_dense && !p.g_msg_M && p.g_node_J && p.g_node_h;
 }
-
-#define SVAE_CAT_(a, b) a##b
-#define SVAE_CAT(a, b) SVAE_CAT_(a, b)
 
 cudaError_t SVAE_CAT(lds_bwd_launch_n, SVAE_N)(const LdsBwdParams& p, int lps, cudaStream_t stream) {
   constexpr int N = SVAE_N;
@@ -75,3 +89,4 @@ cudaError_t SVAE_CAT(lds_bwd_launch_n, SVAE_N)(const LdsBwdParams& p, int lps, c
 }
 
 }  // namespace svae
+#endif  // SVAE_STUB

@@ -8,6 +8,16 @@
 #error "compile with -DSVAE_N=<latent dim>"
 #endif
 
+#define SVAE_CAT_(a, b) a##b
+#define SVAE_CAT(a, b) SVAE_CAT_(a, b)
+
+#ifdef SVAE_STUB
+// experiment builds (SVAE_BUILD_NS=... python -m svae_b200.build): latent dimensions left out of a variant library
+namespace svae {
+cudaError_t SVAE_CAT(lds_fwd_launch_n, SVAE_N)(const LdsFwdParams&, int, int, bool, cudaStream_t) { return cudaErrorNotSupported; }
+}
+#else
+
 #include <mutex>
 #include <cstdlib>
 
@@ -99,7 +109,7 @@ template <int N, int S, bool SAVE, bool INHOMOG>
 static cudaError_t launch_packed(const LdsFwdParams& p, cudaStream_t stream) {
   constexpr int SPW = lds_packed_spw(N);
   const long long grid = ((long long)p.B + SPW - 1) / SPW;
-  const size_t smem = sizeof(double) * (3 * N * lds_np(N) + 2 + (size_t)SPW * lds_packed_tile_doubles(N, S, INHOMOG));
+  const size_t smem = sizeof(double) * (3 * N * lds_np(N) + 2 + (size_t)SPW * lds_packed_tile_doubles(N, S, INHOMOG, lds_packed_nog(SAVE, INHOMOG)));
   auto kern = lds_estep_packed_kernel<N, S, SAVE, INHOMOG>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -135,9 +145,6 @@ static bool packed_eligible(const LdsFwdParams& p, bool inhomog) {
   if (inhomog) return true;       // per-sequence / per-time parameters, optional per-time outputs
   return !(p.flags & SVAE_LDS_FLAG_INIT_PER_SEQ) && !p.Exx_t && !p.Exxn_t;
 }
-
-#define SVAE_CAT_(a, b) a##b
-#define SVAE_CAT(a, b) SVAE_CAT_(a, b)
 
 template <int N, int CPL, int LPS>
 static cudaError_t launch_if_fits(const LdsFwdParams& p, bool inhomog, cudaStream_t stream) {
@@ -180,3 +187,4 @@ cudaError_t SVAE_CAT(lds_fwd_launch_n, SVAE_N)(const LdsFwdParams& p, int cpl, i
 }
 
 }  // namespace svae
+#endif  // SVAE_STUB

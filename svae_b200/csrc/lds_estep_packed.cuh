@@ -35,13 +35,24 @@ namespace svae {
 
 __host__ __device__ constexpr int lds_packed_spw(int N) { return 32 / N; }
 
+// -DSVAE_PACKED_NOG=1: the smoother gain G_t = M_t^-1 J12 is NOT written to the stash record; the backward sweep rebuilds
+// what it needs of it from M_t^-1 (which it fetches anyway) and the constant-bank J12:  C = M^-1 (J12 Sigma_{t+1}),
+// row c of G = J12' M^-1[:,c].  +2 n^2 multiply-adds per lane-step on constant operands, no extra shared-memory traffic,
+// the record's fetched part shrinks from (2n+1+S) to (n+1+S) rows (homogeneous, non-saving launches only: the VJP kernel
+// reads G from the saved record).
+#ifndef SVAE_PACKED_NOG
+#define SVAE_PACKED_NOG 0
+#endif
+
+__host__ __device__ constexpr bool lds_packed_nog(bool save, bool inhomog) { return (SVAE_PACKED_NOG != 0) && !save && !inhomog; }
+
 // shared-memory doubles per sequence tile; padded so that consecutive tiles start one ROW (NP doubles) apart modulo
 // 128 bytes: the rows the 32/N sequences of a warp touch with one instruction then sit side by side in bank space
 // (2 wavefronts for 3 x 80 bytes at n = 10 instead of the 4 that ncu counted with a 48-byte skew)
-__host__ __device__ constexpr int lds_packed_tile_doubles(int N, int S, bool inhomog = false) {
+__host__ __device__ constexpr int lds_packed_tile_doubles(int N, int S, bool inhomog = false, bool nog = false) {
   const int NP = lds_np(N);
   const int fa = 2 * N * NP + 2 * (2 + S) * NP + (inhomog ? 6 * N * NP : 0);   // Lr, Lt, node ring, 2 x {J11|J12|J22} of a step
-  const int fb = 2 * (2 * N + 1 + S) * NP + N * NP;             // stash ring, Cs
+  const int fb = 2 * ((nog ? N : 2 * N) + 1 + S) * NP + N * NP;   // stash ring (fetched part of two records), Cs
   const int raw = (3 + 2 * S) * NP /*hf, mu, sd, w, x*/ + (fa > fb ? fa : fb);
   return raw + ((NP % 16 - raw % 16) + 16) % 16;
 }
@@ -84,7 +95,10 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
   constexpr unsigned MASK = ACT == 32 ? 0xffffffffu : ((1u << ACT) - 1u);
   constexpr int SS = (2 * N + 1 + S) * NP;                       // fetched prefix of a stash record
   constexpr int NODE = (2 + S) * NP;
-  constexpr int TILE = lds_packed_tile_doubles(N, S, INHOMOG);
+  constexpr bool NOG = lds_packed_nog(SAVE, INHOMOG);
+  constexpr int FOFF = NOG ? N * NP : 0;                         // fetched part of a record: doubles [FOFF, SS)
+  constexpr int SLOT = SS - FOFF;                                // ring slot
+  constexpr int TILE = lds_packed_tile_doubles(N, S, INHOMOG, NOG);
   constexpr int SA = S > 0 ? S : 1;                              // array extent (no zero-length arrays)
   constexpr int PB = 3 * N * NP;                                 // one staged step of pair parameters: J11 | J12 | J22
   extern __shared__ __align__(16) double smem[];
@@ -130,7 +144,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
   double* nring = Lt + N * NP;     // 2 x { J_node | h_node | eps rows }
   double* pst = nring + 2 * NODE;  // INHOMOG: 2 x { J11 | J12 | J22 } natural form, row-major [i][j]
   double* ring = uni;              // backward sweep: 2 stash records
-  double* Cs = ring + 2 * SS;      // Cs[k*NP+i] = C[i][k]
+  double* Cs = ring + 2 * SLOT;    // Cs[k*NP+i] = C[i][k]
 
   if (lane == 0) {
     mbar_init(&bars[0], 1);
@@ -333,7 +347,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
       double* st = stash + (size_t)t * RS;
 #pragma unroll
       for (int q2 = 0; q2 < NP / 2; ++q2) {
-        st2(&st[c * NP + 2 * q2], -r[2 * q2], (2 * q2 + 1 < N) ? -r[2 * q2 + 1] : 0.0);
+        if (!NOG) st2(&st[c * NP + 2 * q2], -r[2 * q2], (2 * q2 + 1 < N) ? -r[2 * q2 + 1] : 0.0);
         st2(&st[N * NP + c * NP + 2 * q2], q[2 * q2], (2 * q2 + 1 < N) ? q[2 * q2 + 1] : 0.0);
       }
       st[2 * N * NP + c] = m;
@@ -420,19 +434,19 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
   auto fetch = [&](int t, int j) {   // j-th backward step (t = T-2-j) -> ring slot j&1
 #if SVAE_LDS_TMA
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bars[j & 1], (uint32_t)(SPW * SS * sizeof(double)));
+      mbar_arrive_expect_tx(&bars[j & 1], (uint32_t)(SPW * SLOT * sizeof(double)));
 #pragma unroll
       for (int s2 = 0; s2 < SPW; ++s2) {
         long long bs = (long long)blockIdx.x * SPW + s2;
         if (bs >= p.B) bs = (long long)p.B - 1;
-        tma_load_1d(tile0 + s2 * TILE + ring_off + (j & 1) * SS, p.stash + ((size_t)bs * T + t) * RS,
-                    (uint32_t)(SS * sizeof(double)), &bars[j & 1]);
+        tma_load_1d(tile0 + s2 * TILE + ring_off + (j & 1) * SLOT, p.stash + ((size_t)bs * T + t) * RS + FOFF,
+                    (uint32_t)(SLOT * sizeof(double)), &bars[j & 1]);
       }
     }
 #else
-    double* dst = ring + (j & 1) * SS;
-    const double* src = stash + (size_t)t * RS;
-    for (int e = c; e < SS; e += N) dst[e] = src[e];
+    double* dst = ring + (j & 1) * SLOT;
+    const double* src = stash + (size_t)t * RS + FOFF;
+    for (int e = c; e < SLOT; e += N) dst[e] = src[e];
 #endif
   };
   if (T >= 2) fetch(T - 2, 0);
@@ -447,7 +461,7 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
     SVAE_CLK(6)
     if (t < T - 1) {
       const int j = T - 2 - t;
-      const double* rec = ring + (j & 1) * SS;
+      const double* rec = ring + (j & 1) * SLOT - FOFF;     // record-relative offsets below; [0, FOFF) is not fetched
 #if SVAE_LDS_TMA
       mbar_wait(&bars[j & 1], (uint32_t)((j >> 1) & 1));
 #else
@@ -457,17 +471,42 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
       const double* G = rec;                    // G[k*NP+i] = G_t[i][k]
       const double* Minv = rec + N * NP;
       // C[:,c] = G Sigma_{t+1}[:,c]
-      double cc[N];
+      double cc[N], gk[N];
 #pragma unroll
       for (int i = 0; i < N; ++i) cc[i] = 0.0;
+      if constexpr (NOG) {
+        // G = M^-1 J12 (natural-form J12 in the constant bank):  C[:,c] = M^-1 (J12 Sigma_{t+1}[:,c])
+        const double* cj12 = c_J12[p.const_slot];
+        double w[N];
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
+        for (int j = 0; j < N; ++j) w[j] = 0.0;
 #pragma unroll
-        for (int q2 = 0; q2 < NP / 2; ++q2) {
-          const double2 g = ld2(&G[k * NP + 2 * q2]);
-          cc[2 * q2] = fma(g.x, z[k], cc[2 * q2]);
-          if (2 * q2 + 1 < N) cc[2 * q2 + 1] = fma(g.y, z[k], cc[2 * q2 + 1]);
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+          for (int j = 0; j < N; ++j) w[j] = fma(cj12[j * N + k], z[k], w[j]);
         }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+#pragma unroll
+          for (int q2 = 0; q2 < NP / 2; ++q2) {
+            const double2 g = ld2(&Minv[j * NP + 2 * q2]);          // row j of the symmetric M^-1
+            cc[2 * q2] = fma(g.x, w[j], cc[2 * q2]);
+            if (2 * q2 + 1 < N) cc[2 * q2 + 1] = fma(g.y, w[j], cc[2 * q2 + 1]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+          for (int q2 = 0; q2 < NP / 2; ++q2) {
+            const double2 g = ld2(&G[k * NP + 2 * q2]);
+            cc[2 * q2] = fma(g.x, z[k], cc[2 * q2]);
+            if (2 * q2 + 1 < N) cc[2 * q2 + 1] = fma(g.y, z[k], cc[2 * q2 + 1]);
+          }
+        }
+        // row c of G
+#pragma unroll
+        for (int k = 0; k < N; ++k) gk[k] = G[k * NP + c];
       }
 #pragma unroll
       for (int q2 = 0; q2 < NP / 2; ++q2) {
@@ -475,10 +514,19 @@ __global__ void __launch_bounds__(32, SVAE_PACKED_MINB(N)) lds_estep_packed_kern
         acc_xxn[2 * q2] += cc[2 * q2];            // Cov(x_t, x_{t+1})[i][c]; the mean outer product joins below
         if (2 * q2 + 1 < N) acc_xxn[2 * q2 + 1] += cc[2 * q2 + 1];
       }
-      // row c of G; element c of  mu_t = m_t + G mu_{t+1},  x_t = b_t + G x_{t+1}
-      double gk[N];
+      if constexpr (NOG) {
+        const double* cj12 = c_J12[p.const_slot];
+        // row c of G:  G[c][k] = sum_j M^-1[j][c] J12[j][k]
 #pragma unroll
-      for (int k = 0; k < N; ++k) gk[k] = G[k * NP + c];
+        for (int k = 0; k < N; ++k) gk[k] = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const double zj = Minv[j * NP + c];
+#pragma unroll
+          for (int k = 0; k < N; ++k) gk[k] = fma(cj12[j * N + k], zj, gk[k]);
+        }
+      }
+      // element c of  mu_t = m_t + G mu_{t+1},  x_t = b_t + G x_{t+1}  (row c of G: the operands the Sigma update uses anyway)
       double mnew = rec[2 * N * NP + c], xnew[SA];
 #pragma unroll
       for (int s = 0; s < S; ++s) xnew[s] = rec[(2 * N + 1 + s) * NP + c];

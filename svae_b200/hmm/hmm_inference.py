@@ -6,7 +6,9 @@ Same names and return structure as the reference:
   hmm_viterbi(natparam)   -> int32 state path                                      (hmm_inference.py:54-63)
   hmm_estep_slow          == hmm_estep       (hmm_inference.py:65, vgrad(hmm_logZ))
 natparam = (init_params (K,), pair_params (K,K) row = from-state, node_params (T,K) or (B,T,K)), all log
-values.  Everything runs in the sm_100a kernels of libsvae_b200.so (csrc/hmm_estep.cu); no CPU path.
+values.  Everything runs in the sm_100a kernels of libsvae_b200.so; no CPU path.  Up to 32 states: the register-resident
+kernels of csrc/hmm_estep.cu (lane = state); 33..1024 states: one CTA per sequence, thread = state (csrc/hmm_wide.cu) --
+the reference takes any K.
 """
 from __future__ import annotations
 import ctypes
@@ -27,8 +29,8 @@ def _canon(natparam):
     lp, lA = _lib.f64(init_params, dev), _lib.f64(pair_params, dev)
     if lp.shape != (K,) or lA.shape != (K, K):
         raise ValueError("init/pair params shapes %s %s for K=%d" % (tuple(lp.shape), tuple(lA.shape), K))
-    if K > _lib.SVAE_HMM_MAX_K:
-        raise ValueError("K=%d > %d" % (K, _lib.SVAE_HMM_MAX_K))
+    if K > _lib.SVAE_HMM_WIDE_MAX_K:
+        raise ValueError("K=%d > %d" % (K, _lib.SVAE_HMM_WIDE_MAX_K))
     return lp, lA, node.contiguous(), batched, dev
 
 
@@ -46,9 +48,18 @@ def hmm_estep_forward(lp, lA, node, logz_only=False, active=None, out=None):
         if not logz_only:
             Ez0, Etrans, Ez = new(B, K), new(B, K, K), new(B, T, K)
     P = _lib.ptr
-    code = _lib.lib().svae_hmm_estep_masked(B, T, K, _lib.SVAE_HMM_LOGZ_ONLY if logz_only else 0, P(lp), P(lA), P(node),
-                                            None if active is None else ctypes.c_void_p(active.data_ptr()),
-                                            P(logZ), P(Ez0), P(Etrans), P(Ez), _lib.stream_ptr(dev))
+    L = _lib.lib()
+    flags = _lib.SVAE_HMM_LOGZ_ONLY if logz_only else 0
+    act = None if active is None else ctypes.c_void_p(active.data_ptr())
+    if K > _lib.SVAE_HMM_MAX_K:      # one CTA per sequence, thread = state; scratch for exp(log A - max) and its transpose
+        wbytes = L.svae_hmm_wide_workspace_bytes(K)
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        code = L.svae_hmm_estep_wide(B, T, K, flags, P(lp), P(lA), P(node), act, P(logZ), P(Ez0), P(Etrans), P(Ez),
+                                     ctypes.c_void_p(work.data_ptr()), wbytes, _lib.stream_ptr(dev))
+        _lib.check(code, "svae_hmm_estep_wide")
+        return logZ, Ez0, Etrans, Ez
+    code = L.svae_hmm_estep_masked(B, T, K, flags, P(lp), P(lA), P(node), act,
+                                   P(logZ), P(Ez0), P(Etrans), P(Ez), _lib.stream_ptr(dev))
     _lib.check(code, "svae_hmm_estep_masked")
     return logZ, Ez0, Etrans, Ez
 

@@ -7,6 +7,8 @@
 #include <cmath>
 #include "lds_compose_core.h"
 #include "hmm_compose_core.h"
+#include "hmm_wide_core.h"
+#include <cstdint>
 
 static double rnd() { return (double)rand() / RAND_MAX - 0.5; }
 
@@ -66,6 +68,30 @@ int main() {
     if (!(logZ == logZ)) { std::printf("HMM K=%d failed\n", K); return 1; }
     for (int z : zb)
       if (z < 0 || z >= K) { std::printf("HMM K=%d boundary state out of range\n", K); return 1; }
+  }
+  // ---- wide HMM (K > 32): E-step and Viterbi, exact tile / workspace / output extents -------------------------------
+  for (int K : {33, 40, 64, 97}) {
+    for (int T : {1, 2, 19}) {
+      std::vector<double> lA(K * K), lp(K), node((size_t)T * K);
+      for (auto& x : lA) x = rnd();
+      for (auto& x : lp) x = rnd();
+      for (auto& x : node) x = 3 * rnd();
+      std::vector<double> ws(svae::hmm_wide_workspace_doubles(K)), pm(svae::hmm_wide_prep_tile_doubles(K));
+      svae::hmm_wide_prep(pm.data(), K, lA.data(), ws.data(), ws.data() + (size_t)K * K, ws.data() + 2 * (size_t)K * K);
+      std::vector<double> mem(svae::hmm_wide_tile_doubles(K)), E0(K), Et((size_t)K * K), Ez((size_t)T * K);
+      double logZ;
+      svae::hmm_wide_sequence(mem.data(), K, T, lp.data(), ws.data(), ws.data() + (size_t)K * K, ws[2 * (size_t)K * K],
+                              node.data(), &logZ, E0.data(), Et.data(), Ez.data(), false);
+      double tot = 0.0;
+      for (double v : Et) tot += v;
+      if (!(logZ == logZ) || std::fabs(tot - (T - 1)) > 1e-9 * (T + 1)) { std::printf("wide HMM K=%d T=%d failed\n", K, T); return 1; }
+      std::vector<double> vm(svae::hmm_wide_viterbi_tile_doubles(K));
+      std::vector<uint16_t> back((size_t)T * K);
+      std::vector<int32_t> path(T);
+      svae::hmm_wide_viterbi(vm.data(), K, T, lp.data(), lA.data(), node.data(), path.data(), back.data());
+      for (int z : path)
+        if (z < 0 || z >= K) { std::printf("wide HMM K=%d path out of range\n", K); return 1; }
+    }
   }
   std::printf("asan run ok\n");
   return 0;

@@ -41,6 +41,52 @@ def test_hmm_vs_oracle(K_, T, B):
     assert np.array_equal(K.hmm_viterbi(nat).cpu().numpy(), H.hmm_viterbi((lp, lA, node)))
 
 
+@pytest.mark.parametrize("K_,T,B", [(33, 40, 5), (48, 1, 3), (64, 2, 2), (64, 300, 16), (100, 57, 4), (257, 21, 2)])
+def test_hmm_wide_vs_oracle(K_, T, B):
+    """More than 32 states: one CTA per sequence, thread = state (csrc/hmm_wide.cu; phase code pinned on CPU by
+    tests/test_hmm_wide_cpu.py) -- E-step, log-normaliser alone, Viterbi, and the VJP of hmm_logZ."""
+    from svae_b200.hmm import hmm_inference as K
+    rng = np.random.default_rng(K_ * 1000 + T)
+    lp, lA = H.rand_hmm_natparam(K_, rng)
+    lA = lA + rng.standard_normal((K_, 1))
+    node = 3.0 * rng.standard_normal((B, T, K_))
+    w_logZ, (wE0, wEt, wEz) = H.hmm_estep((lp, lA, node))
+    nat = (_g(lp), _g(lA), _g(node))
+    logZ, (Ez0, Etrans, Ez) = K.hmm_estep(nat)
+    assert rel_err(logZ.cpu().numpy(), w_logZ) < RTOL
+    assert rel_err(Ez.cpu().numpy(), wEz) < RTOL and rel_err(Ez0.cpu().numpy(), wE0) < RTOL
+    if T > 1:
+        assert rel_err(Etrans.cpu().numpy(), wEt) < RTOL
+    else:
+        assert float(Etrans.abs().max()) == 0.0
+    assert np.array_equal(K.hmm_viterbi(nat).cpu().numpy(), H.hmm_viterbi((lp, lA, node)))
+    a, b_, c = _g(lp, True), _g(lA, True), _g(node, True)
+    out = K.hmm_logZ((a, b_, c))
+    assert rel_err(out.detach().cpu().numpy(), w_logZ) < RTOL
+    out.sum().backward()
+    assert rel_err(c.grad.cpu().numpy(), wEz) < RTOL and rel_err(a.grad.cpu().numpy(), wE0.sum(0)) < RTOL
+    if T > 1:
+        assert rel_err(b_.grad.cpu().numpy(), wEt.sum(0)) < RTOL
+
+
+def test_hmm_wide_mask_and_limits():
+    from svae_b200.hmm import hmm_inference as K
+    rng = np.random.default_rng(11)
+    K_, T, B = 40, 9, 4
+    lp, lA = H.rand_hmm_natparam(K_, rng)
+    node = rng.standard_normal((B, T, K_))
+    lpg, lAg, ng = _g(lp), _g(lA), _g(node)
+    full = K.hmm_estep_forward(lpg, lAg, ng)
+    sentinel = [torch.full_like(x, -7.0) for x in full]
+    active = torch.tensor([1, 0, 1, 0], dtype=torch.int32, device="cuda")
+    got = K.hmm_estep_forward(lpg, lAg, ng, active=active, out=tuple(sentinel))
+    for g_, f_ in zip(got, full):
+        assert torch.equal(g_[0], f_[0]) and torch.equal(g_[2], f_[2])
+        assert float((g_[1] + 7.0).abs().max()) == 0.0 and float((g_[3] + 7.0).abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        K.hmm_estep((torch.zeros(1025, device="cuda"), torch.zeros(1025, 1025, device="cuda"), torch.zeros(1, 2, 1025, device="cuda")))
+
+
 def test_hmm_logZ_vjp_is_the_estep():
     from svae_b200.hmm import hmm_inference as K
     rng = np.random.default_rng(3)

@@ -104,7 +104,9 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
     if dense:                      # dense precisions ride the cold port; the diagonal port gets zeros
         nJd, nJ = nJ, torch.zeros_like(nh)
     if n > _lib.SVAE_LDS_MAX_N:
-        raise ValueError("latent dimension %d > %d" % (n, _lib.SVAE_LDS_MAX_N))
+        raise ValueError("latent dimension %d > %d: the fused kernel is compiled for n <= %d; the reference-named drivers "
+                         "(natural_lds_inference_general, natural_lds_estep_general, natural_lds_sample) take larger n "
+                         "through lds_large.py" % (n, _lib.SVAE_LDS_MAX_N, _lib.SVAE_LDS_MAX_N))
     iJ, ih, ilogZ = _canonical_init_params(init_params, device)
     init_per_seq = iJ.dim() == 3
     if init_per_seq:
@@ -458,8 +460,17 @@ class _LDSEStepFn(torch.autograd.Function):
         return gJ, gh, g_logZ, None, None, None, None, None
 
 
+def _latent_dim(node_params):
+    h = node_params[1]
+    return int(h.shape[-1]) if hasattr(h, "shape") else int(torch.as_tensor(h).shape[-1])
+
+
 def _estep(init_params, pair_params, node_params, S, eps, per_t, generator=None):
-    """Dispatch: plain launch when nothing requires grad, autograd Function otherwise."""
+    """Dispatch: plain launch when nothing requires grad, autograd Function otherwise; latent dimensions above the
+    compiled kernels' range run the same recursions as batched device linear algebra (lds_large.py)."""
+    if _latent_dim(node_params) > _lib.SVAE_LDS_MAX_N:
+        from . import lds_large
+        return lds_large.estep(init_params, pair_params, node_params, S, eps, per_t, generator)
     needs_grad = torch.is_grad_enabled() and any(torch.is_tensor(x) and x.requires_grad for x in node_params)
     if not needs_grad:
         return lds_estep_forward(init_params, pair_params, node_params, S, eps, per_t_pair_stats=per_t,
@@ -550,8 +561,12 @@ cython_natural_lds_estep_general = natural_lds_estep_general
 def natural_lds_sample(natparam, node_params, num_samples=1, eps=None, generator=None):
     """samples only -- lds_inference.py:253-264."""
     init_params, pair_params = natparam
-    o = lds_estep_forward(init_params, pair_params, node_params, num_samples, eps,
-                          want_stats=False, generator=generator)
+    if _latent_dim(node_params) > _lib.SVAE_LDS_MAX_N:
+        from . import lds_large
+        o = lds_large.estep(init_params, pair_params, node_params, num_samples, eps, False, generator, want_stats=False)
+    else:
+        o = lds_estep_forward(init_params, pair_params, node_params, num_samples, eps,
+                              want_stats=False, generator=generator)
     return o["samples"] if o["batched"] else o["samples"][0]
 
 

@@ -200,3 +200,29 @@ def test_minibatch_reduction_and_host_pipeline():
     assert rel_err(out_host["E_node_x"].numpy(), o["E_node_x"].cpu().numpy()) < 1e-12
     assert rel_err(out_host["lognorm"].numpy(), o["lognorm"].cpu().numpy()) < 1e-12
     assert torch.isfinite(out_host["samples"]).all()
+
+
+@pytest.mark.parametrize("n,T,B,S", [(20, 12, 3, 1), (33, 5, 2, 2)])
+def test_latent_dimension_above_the_compiled_range(n, T, B, S):
+    """n > 16 runs the same recursions as batched device linear algebra (svae_b200/lds/lds_large.py): same API, same
+    outputs as the oracle, gradients w.r.t. the node potentials from autograd (checked against the oracle's)."""
+    from oracle import lds_torch as OT
+    from svae_b200.lds import lds_inference as K
+    rng = np.random.default_rng(n)
+    init, pair = O.rand_lds_natparam(n, rng)
+    node = O.rand_node_potentials(B, T, n, rng)
+    eps = rng.standard_normal((B, T, S, n))
+    want = O.natural_lds_inference_general((init, pair), node, eps)
+    _compare(_run(init, pair, node, eps, S), want)
+    natparam = (tuple(_gpu(x) for x in init), tuple(_gpu(x) for x in pair))
+    nJ, nh = _gpu(node[0]).requires_grad_(True), _gpu(node[1]).requires_grad_(True)
+    samples, (_, _, E_node), lognorm = K.natural_lds_inference_general(natparam, (nJ, nh), S, _gpu(eps))
+    w = rng.standard_normal((B, T, S, n))
+    gx = rng.standard_normal((B, T, n))
+    ((samples * _gpu(w)).sum() + (E_node[1] * _gpu(gx)).sum() - lognorm.sum()).backward()
+    z = lambda *sh: np.zeros(sh)
+    wJ, wh = OT.vjp_node_params((init, pair), node[:2], eps, w, ((z(B, n, n), z(B, n)), (z(B, n, n),) * 3, (z(B, T, n), gx)),
+                                -np.ones(B))
+    assert rel_err(nJ.grad.cpu().numpy(), wJ) < 1e-8 and rel_err(nh.grad.cpu().numpy(), wh) < 1e-8
+    smp = K.natural_lds_sample(natparam, tuple(_gpu(x) for x in node), S, _gpu(eps))
+    assert rel_err(smp.cpu().numpy(), want[0]) < RTOL

@@ -44,6 +44,7 @@ extern "C" {
 #define SVAE_LDS_MAX_N 16           /* latent dimension range compiled into the library: 1..16    */
 #define SVAE_HMM_MAX_K 32           /* discrete states of the register-resident kernels: 1..32 (lane = state) */
 #define SVAE_HMM_WIDE_MAX_K 1024    /* svae_hmm_estep_wide / svae_hmm_viterbi: 1..1024 (thread = state)       */
+#define SVAE_HMM_TC_MIN_K 17        /* svae_hmm_estep_wide: 17..32 states run on the fp64 tensor-core instruction */
 #define SVAE_GMM_MAX_N 8            /* GMM latent dimension: 1..8                                  */
 
 /* flags for svae_lds_estep_fwd */
@@ -275,11 +276,15 @@ int svae_hmm_estep_masked(int B, int T, int K, int flags, const double* log_pi, 
                           double* Ez, void* stream);
 
 /* The same E-step for ANY number of states up to SVAE_HMM_WIDE_MAX_K (the reference's hmm_logZ / hmm_logZ_grad take any
- * K, svae/hmm/cython_hmm_inference.pyx:93-166).  K <= SVAE_HMM_MAX_K runs the register-resident kernel of
- * svae_hmm_estep_masked and ignores the workspace; larger K runs one CTA per sequence (thread = state) and needs
- * svae_hmm_wide_workspace_bytes(K) bytes of device scratch (exp(log_A - max), its transpose, the shift), written by a
- * one-CTA preparation launch on the same stream.  Same arguments, outputs and mask otherwise. */
-size_t svae_hmm_wide_workspace_bytes(int K);
+ * K, svae/hmm/cython_hmm_inference.pyx:93-166) -- the entry point a caller with a scratch buffer should use:
+ *   K <  SVAE_HMM_TC_MIN_K        the register-resident kernel of svae_hmm_estep_masked (workspace ignored);
+ *   SVAE_HMM_TC_MIN_K..32 states  with a workspace: 8 sequences per warp, the K x K products and the transition counts on
+ *                                 the fp64 tensor-core instruction (csrc/hmm_tc.cu; the workspace holds the scaled forward
+ *                                 messages and w_{t+1}/s_t, 2 B T K doubles); workspace NULL: as above;
+ *   33..SVAE_HMM_WIDE_MAX_K       one CTA per sequence, thread = state (csrc/hmm_wide.cu); the workspace (required) holds
+ *                                 exp(log_A - max), its transpose and the shift, written by a one-CTA preparation launch.
+ * Same arguments, outputs and mask otherwise; everything is enqueued on `stream`. */
+size_t svae_hmm_wide_workspace_bytes(int B, int T, int K);
 int svae_hmm_estep_wide(int B, int T, int K, int flags, const double* log_pi, const double* log_A,
                         const double* node, const int* active, double* logZ, double* Ez0, double* Etrans,
                         double* Ez, void* workspace, size_t workspace_bytes, void* stream);

@@ -125,6 +125,8 @@ def worker(tag):
     if "vjp12" in cases: vjp_case(12, 200, 4096, 1)
     if "vjp14" in cases: vjp_case(14, 200, 4096, 1)
     if "hmm32" in cases: hmm_case(32, 500, 2048)
+    if "hmmbig" in cases: hmm_case(32, 500, 16384)
+    if "hmm24" in cases: hmm_case(24, 500, 2048)
     if "hmm20" in cases: hmm_case(20, 500, 2048)
     if "hmmT" in cases:
         for T in (1, 2, 3, 6, 7, 11):

@@ -19,6 +19,7 @@ SVAE_LDS_BWD_MESSAGES_OUT = 32
 SVAE_LDS_BWD_MESSAGES_IN = 64
 SVAE_HMM_MAX_K = 32          # register-resident kernels (lane = state)
 SVAE_HMM_WIDE_MAX_K = 1024   # svae_hmm_estep_wide / svae_hmm_viterbi (thread = state)
+SVAE_HMM_TC_MIN_K = 17       # svae_hmm_estep_wide: 17..32 states on the fp64 tensor-core instruction
 SVAE_GMM_MAX_N = 8
 SVAE_HMM_LOGZ_ONLY = 1
 
@@ -39,7 +40,7 @@ _SIGNATURES = {
     "svae_lds_estep_fwd_ex": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 21 + [_P, _P, _SZ, _P]),
     "svae_lds_estep_fwd_masked": (_I, [_I] * 5 + [_P] * 7 + [_LL, _LL] + [_P] * 22 + [_P, _P, _SZ, _P]),
     "svae_hmm_estep_masked": (_I, [_I] * 4 + [_P] * 8 + [_P]),
-    "svae_hmm_wide_workspace_bytes": (_SZ, [_I]),
+    "svae_hmm_wide_workspace_bytes": (_SZ, [_I] * 3),
     "svae_hmm_estep_wide": (_I, [_I] * 4 + [_P] * 8 + [_P, _SZ, _P]),
     "svae_slds_mix_params": (_I, [_I] * 4 + [_P] * 16 + [_P]),
     "svae_slds_node_potentials": (_I, [_I] * 4 + [_P] * 12 + [_P]),

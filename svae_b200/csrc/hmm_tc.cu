@@ -1,0 +1,364 @@
+// hmm_tc.cu -- HMM local E-step for 17..32 states on the fp64 tensor-core instruction (mma.m8n8k4), sm_100a.
+//
+// What it replaces in the reference is what hmm_estep.cu replaces: svae/hmm/cython_hmm_inference.pyx:93-166 (hmm_logZ /
+// hmm_logZ_grad: with cotangent 1 the E-step) and svae/hmm/hmm_inference.py:21-41.
+//
+// Why.  ncu on hmm_estep_kernel<32> (profiles/r02_hmm_*_summary.txt): one warp per sequence, the K x K matrix-vector products
+// as 32 DFMA per lane against a message broadcast through shared memory -- 146 shared-memory wavefronts and ~500
+// warp-instructions per sequence-step; short-scoreboard (shared-memory) stalls dominate, and neither more resident warps
+// (the -DSVAE_HMM_OSMEM build: 16 instead of 8 per SM, same 1.13 ms) nor fewer registers move it.  The dense contraction
+// belongs on the tensor cores, with the BATCH as the M dimension:
+//   * a warp owns 8 sequences (row g = lane >> 2 of every fragment); a step's 8 x 32 by 32 x 32 product is 32 mma.m8n8k4
+//     whose B operands -- P = exp(log A - max) forward, P' backward -- stay in registers for the whole sweep;
+//   * state vectors live in the ACCUMULATOR layout (lane (g,q): states 8 nt + 2 q + e, nt < 4, e < 2), and the A operand of
+//     slab s is defined as element [s >> 1][s & 1] of it, i.e. the contraction runs over the states in the order
+//     8 (s >> 1) + 2 q + (s & 1): the output of one step is the input of the next with NO shuffle or shared memory (the P
+//     fragment tables absorb the relabelling; scripts/dev_hmm_tc_numpy.py pins the index maps);
+//   * row sums / maxima are 8 local operations + 2 quad shuffles; node potentials are read as 64-byte quad segments.
+//   * the per-sequence transition counts  E[#i->j] = P[i][j] sum_t ahat_t[i] w_{t+1}[j] / s_t  do not fit next to 8 sequences
+//     per warp (8 x 32 x 32 accumulators), so the sweep leaves ahat_t and w_{t+1}/s_t in a workspace and a second kernel
+//     forms the 32 x 32 x T product of each sequence with the contraction over TIME on the tensor cores (16 mma per 4 steps).
+// Same scaled recursions and outputs as hmm_estep.cu (the tests hold both to the same golden vectors).
+#include <atomic>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <cstdlib>
+#include "svae_b200.h"
+
+extern std::atomic<uint64_t> g_svae_launches;
+
+namespace svae {
+
+__device__ __forceinline__ void hmm_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double quad_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ float quad_maxf(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+__device__ __forceinline__ double tc_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+struct HmmTcParams {
+  int B, T, K, fwd_only;
+  const double *log_pi, *log_A, *node;   // (K), (K,K) row = from, (B,T,K)
+  const int* active;
+  double *logZ, *Ez0, *Ez;               // (B), (B,K), (B,T,K)
+  double *wsA, *wsW;                     // workspace (B,T,K) each: ahat_t; w_{t+1} / s_t (rows 0 .. T-2)
+};
+
+// max of log_A over the K x K entries, the same value in every lane
+__device__ __forceinline__ double tc_gmax(const double* log_A, int K, int lane) {
+  float m = -INFINITY;
+  for (int e = lane; e < K * K; e += 32) m = fmaxf(m, (float)log_A[e]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  return (double)m;
+}
+
+// ---- forward-backward sweep: one warp per 8 sequences ------------------------------------------------------------
+__global__ void __launch_bounds__(32) hmm_tc_sweep_kernel(const HmmTcParams p) {
+  const int lane = threadIdx.x, g = lane >> 2, q = lane & 3;
+  const int K = p.K, T = p.T;
+  const long long seq = (long long)blockIdx.x * 8 + g;
+  const long long b = seq < p.B ? seq : (long long)p.B - 1;
+  const bool valid = seq < p.B && (!p.active || p.active[b] != 0);
+  const double NEG = -INFINITY;
+  const double gmax = tc_gmax(p.log_A, K, lane);
+
+  // this lane's 8 states: st(nt, e) = 8 nt + 2 q + e
+  bool in[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) in[nt][e] = (8 * nt + 2 * q + e) < K;
+
+  const double* node = p.node + (size_t)b * T * K + 2 * q;
+  double* Ez = p.Ez ? p.Ez + (size_t)b * T * K + 2 * q : nullptr;
+  double* wsA = p.wsA ? p.wsA + (size_t)b * T * K + 2 * q : nullptr;
+  double* wsW = p.wsW ? p.wsW + (size_t)b * T * K + 2 * q : nullptr;
+
+  auto load_row = [&](const double* base, int t, double (&x)[4][2], double fill) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) x[nt][e] = in[nt][e] ? __ldg(base + (size_t)t * K + 8 * nt + e) : fill;
+  };
+  auto store_row = [&](double* base, int t, const double (&x)[4][2]) {
+    if (!valid) return;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if (in[nt][e]) base[(size_t)t * K + 8 * nt + e] = x[nt][e];
+  };
+  auto row_maxf = [&](const double (&x)[4][2]) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) m = fmaxf(m, fmaxf((float)x[nt][0], (float)x[nt][1]));
+    return quad_maxf(m);
+  };
+  auto row_sum = [&](const double (&x)[4][2]) {
+    const double s = ((x[0][0] + x[0][1]) + (x[1][0] + x[1][1])) + ((x[2][0] + x[2][1]) + (x[3][0] + x[3][1]));
+    return quad_sum(s);
+  };
+  // out = v (8 x 32, this warp's 8 sequences) times the 32 x 32 matrix whose fragments are F[s][nt]
+  auto matvec = [&](const double (&v)[4][2], const double (&F)[8][4], double (&out)[4][2]) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) out[nt][0] = out[nt][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) hmm_dmma(out[nt][0], out[nt][1], v[s >> 1][s & 1], F[s][nt]);
+  };
+
+  // ------------------------------------------------ forward ------------------------------------------------
+  double e_[4][2];          // message (unnormalised)
+  double logZ;
+  {
+    double F[8][4];         // F[s][nt] = P[8 (s>>1) + 2 q + (s&1)][8 nt + g]
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int i = 8 * (s >> 1) + 2 * q + (s & 1), j = 8 * nt + g;
+        F[s][nt] = (i < K && j < K) ? exp(p.log_A[i * K + j] - gmax) : 0.0;
+      }
+    double x[4][2], xn1[4][2], xn2[4][2];
+    load_row(node, 0, x, NEG);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) x[nt][e] = in[nt][e] ? p.log_pi[8 * nt + 2 * q + e] + x[nt][e] : NEG;
+    {
+      const double m = (double)row_maxf(x);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) e_[nt][e] = in[nt][e] ? exp(x[nt][e] - m) : 0.0;
+      logZ = m;
+    }
+    if (T > 1) load_row(node, 1, xn1, NEG);
+    if (T > 2) load_row(node, 2, xn2, NEG);
+    double cprod = 1.0;
+    for (int t = 1; t < T; ++t) {
+      // node potentials of step t are in xn1; fetch t + 2 while this step computes
+      double xq[4][2];
+      if (t + 2 < T) load_row(node, t + 2, xq, NEG);
+      double d[4][2];
+      matvec(e_, F, d);
+      const double c = row_sum(e_);
+      const double invc = tc_rcp(c);
+      const double m = (double)row_maxf(xn1);
+      double ah[4][2];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          ah[nt][e] = e_[nt][e] * invc;                                   // ahat_{t-1}
+          e_[nt][e] = in[nt][e] ? d[nt][e] * invc * exp(xn1[nt][e] - m) : 0.0;
+        }
+      if (!p.fwd_only) store_row(wsA, t - 1, ah);
+      logZ += m;
+      cprod *= c;
+      if ((t & 7) == 7) {
+        logZ += log(cprod);
+        cprod = 1.0;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          xn1[nt][e] = xn2[nt][e];
+          xn2[nt][e] = xq[nt][e];
+        }
+    }
+    const double c = row_sum(e_);
+    const double invc = 1.0 / c;
+    cprod *= c;
+    logZ += log(cprod) + (double)(T - 1) * gmax;
+    if (q == 0 && valid && p.logZ) p.logZ[b] = logZ;
+    if (p.fwd_only) return;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) e_[nt][e] *= invc;                      // ahat_{T-1} = E[z_{T-1}]
+    store_row(Ez, T - 1, e_);
+    if (T == 1 && p.Ez0) store_row(p.Ez0 + (size_t)b * K + 2 * q, 0, e_);
+  }
+  if (T == 1) return;
+
+  // ------------------------------------------------ backward -----------------------------------------------
+  double F[8][4];           // F[s][nt] = P'[k][j] = P[8 nt + g][8 (s>>1) + 2 q + (s&1)]
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int k = 8 * (s >> 1) + 2 * q + (s & 1), j = 8 * nt + g;
+      F[s][nt] = (k < K && j < K) ? exp(p.log_A[j * K + k] - gmax) : 0.0;
+    }
+  __syncwarp();             // the ahat rows this warp stored are read back below (same lanes, same addresses)
+  double bet[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) bet[nt][e] = in[nt][e] ? 1.0 : 0.0;
+  double xn[4][2], an[4][2];          // node[t+1], ahat_t of the CURRENT iteration
+  load_row(node, T - 1, xn, NEG);
+  {
+    // ahat_{T-2} was stored by this very lane; re-read through the normal path (not __ldg: written in this kernel)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) an[nt][e] = (in[nt][e] && valid) ? wsA[(size_t)(T - 2) * K + 8 * nt + e] : (in[nt][e] ? 1.0 / K : 0.0);
+  }
+  for (int t = T - 2; t >= 0; --t) {
+    double xp[4][2], ap[4][2];          // prefetch for iteration t - 1: node[t], ahat_{t-1}
+    if (t > 0) {
+      load_row(node, t, xp, NEG);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) ap[nt][e] = (in[nt][e] && valid) ? wsA[(size_t)(t - 1) * K + 8 * nt + e] : (in[nt][e] ? 1.0 / K : 0.0);
+    }
+    const double m = (double)row_maxf(xn);
+    double w[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) w[nt][e] = in[nt][e] ? exp(xn[nt][e] - m) * bet[nt][e] : 0.0;      // w_{t+1}
+    double bu[4][2];
+    matvec(w, F, bu);                                                     // P w_{t+1}
+    double prd[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) prd[nt][e] = an[nt][e] * bu[nt][e];
+    const double s = row_sum(prd);
+    const double invs = tc_rcp(s);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        prd[nt][e] *= invs;                                               // E[z_t]
+        w[nt][e] *= invs;                                                 // w_{t+1} / s_t
+        bet[nt][e] = bu[nt][e] * invs;
+      }
+    store_row(Ez, t, prd);
+    store_row(wsW, t, w);
+    if (t == 0 && p.Ez0) store_row(p.Ez0 + (size_t)b * K + 2 * q, 0, prd);
+    if (t > 0) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          xn[nt][e] = xp[nt][e];
+          an[nt][e] = ap[nt][e];
+        }
+    }
+  }
+}
+
+// ---- transition counts: one warp per sequence, contraction over time on the tensor cores -------------------------
+//   Etrans[i][j] = P[i][j] * sum_{t < T-1} ahat_t[i] (w_{t+1}/s_t)[j]
+constexpr int kTransWarps = 4;
+__global__ void __launch_bounds__(32 * kTransWarps) hmm_tc_trans_kernel(int B, int T, int K, const double* log_A,
+                                                                        const int* active, const double* wsA,
+                                                                        const double* wsW, double* Etrans) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const long long b = (long long)blockIdx.x * kTransWarps + (threadIdx.x >> 5);
+  if (b >= B) return;                                   // warp-uniform
+  if (active && active[b] == 0) return;
+  const double gmax = tc_gmax(log_A, K, lane);
+  const double* A = wsA + (size_t)b * T * K;
+  const double* W = wsW + (size_t)b * T * K;
+  double acc[4][4][2];
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+#pragma unroll
+    for (int jt = 0; jt < 4; ++jt) acc[it][jt][0] = acc[it][jt][1] = 0.0;
+  bool ing[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) ing[it] = (8 * it + g) < K;
+  const int steps = T - 1;                              // rows 0 .. T-2 of both arrays
+  double a[4], w[4];
+  auto fetch = [&](int t0, double (&av)[4], double (&wv)[4]) {
+    const int t = t0 + q;
+    const bool ok = t < steps;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const bool ld = ok && ing[it];
+      av[it] = ld ? A[(size_t)t * K + 8 * it + g] : 0.0;        // A[g][q] = ahat_{t0+q}[8 it + g]
+      wv[it] = ld ? W[(size_t)t * K + 8 * it + g] : 0.0;        // B[q][g] = (w/s)_{t0+q}[8 jt + g]
+    }
+  };
+  if (steps > 0) fetch(0, a, w);
+  for (int t0 = 0; t0 < steps; t0 += 4) {
+    double an[4], wn[4];
+    if (t0 + 4 < steps) fetch(t0 + 4, an, wn);
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+#pragma unroll
+      for (int jt = 0; jt < 4; ++jt) hmm_dmma(acc[it][jt][0], acc[it][jt][1], a[it], w[jt]);
+    if (t0 + 4 < steps) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) { a[it] = an[it]; w[it] = wn[it]; }
+    }
+  }
+  double* out = Etrans + (size_t)b * K * K;
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+#pragma unroll
+    for (int jt = 0; jt < 4; ++jt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = 8 * it + g, j = 8 * jt + 2 * q + e;
+        if (i < K && j < K) out[i * K + j] = exp(log_A[i * K + j] - gmax) * acc[it][jt][e];
+      }
+}
+
+}  // namespace svae
+
+// workspace doubles of the tensor-core path
+size_t svae_hmm_tc_workspace_bytes(int B, int T, int K) { return sizeof(double) * 2 * (size_t)B * (size_t)T * (size_t)K; }
+
+bool svae_hmm_tc_enabled() {
+  static const bool on = [] { const char* e = getenv("SVAE_HMM_TC"); return !(e && atoi(e) == 0); }();
+  return on;
+}
+
+// called by svae_hmm_estep_wide (hmm_wide.cu) for SVAE_HMM_TC_MIN_K <= K <= 32 when the caller brought the workspace
+int svae_hmm_estep_tc_launch(int B, int T, int K, bool fwd_only, const double* log_pi, const double* log_A, const double* node,
+                             const int* active, double* logZ, double* Ez0, double* Etrans, double* Ez, void* workspace,
+                             cudaStream_t s) {
+  svae::HmmTcParams p;
+  p.B = B; p.T = T; p.K = K; p.fwd_only = fwd_only ? 1 : 0;
+  p.log_pi = log_pi; p.log_A = log_A; p.node = node; p.active = active;
+  p.logZ = logZ; p.Ez0 = Ez0; p.Ez = Ez;
+  p.wsA = static_cast<double*>(workspace);
+  p.wsW = p.wsA + (size_t)B * T * K;
+  svae::hmm_tc_sweep_kernel<<<(unsigned)((B + 7) / 8), 32, 0, s>>>(p);
+  g_svae_launches.fetch_add(1);
+  if (!fwd_only && Etrans) {
+    svae::hmm_tc_trans_kernel<<<(unsigned)((B + svae::kTransWarps - 1) / svae::kTransWarps), 32 * svae::kTransWarps, 0, s>>>(
+        B, T, K, log_A, active, p.wsA, p.wsW, Etrans);
+    g_svae_launches.fetch_add(1);
+  }
+  return cudaGetLastError() == cudaSuccess ? SVAE_OK : SVAE_ERR_CUDA;
+}

@@ -45,22 +45,35 @@ cudaError_t allow_smem(Kern kern, size_t bytes) {
 
 }  // namespace
 
-extern "C" size_t svae_hmm_wide_workspace_bytes(int K) {
-  if (K <= SVAE_HMM_MAX_K || K > SVAE_HMM_WIDE_MAX_K) return 0;
+// hmm_tc.cu: the tensor-core path for SVAE_HMM_TC_MIN_K <= K <= SVAE_HMM_MAX_K
+size_t svae_hmm_tc_workspace_bytes(int B, int T, int K);
+bool svae_hmm_tc_enabled();
+int svae_hmm_estep_tc_launch(int B, int T, int K, bool fwd_only, const double* log_pi, const double* log_A, const double* node,
+                             const int* active, double* logZ, double* Ez0, double* Etrans, double* Ez, void* workspace,
+                             cudaStream_t s);
+
+extern "C" size_t svae_hmm_wide_workspace_bytes(int B, int T, int K) {
+  if (B <= 0 || T <= 0 || K < SVAE_HMM_TC_MIN_K || K > SVAE_HMM_WIDE_MAX_K) return 0;
+  if (K <= SVAE_HMM_MAX_K) return svae_hmm_tc_workspace_bytes(B, T, K);
   return sizeof(double) * (size_t)svae::hmm_wide_workspace_doubles(K);
 }
 
 extern "C" int svae_hmm_estep_wide(int B, int T, int K, int flags, const double* log_pi, const double* log_A,
                                    const double* node, const int* active, double* logZ, double* Ez0, double* Etrans,
                                    double* Ez, void* workspace, size_t workspace_bytes, void* stream) {
-  if (K <= SVAE_HMM_MAX_K)
-    return svae_hmm_estep_masked(B, T, K, flags, log_pi, log_A, node, active, logZ, Ez0, Etrans, Ez, stream);
-  if (B <= 0 || T <= 0) return SVAE_ERR_BAD_ARG;
+  if (B <= 0 || T <= 0 || K <= 0) return SVAE_ERR_BAD_ARG;
   if (!log_pi || !log_A || !node) return SVAE_ERR_BAD_ARG;
   const bool fwd_only = (flags & SVAE_HMM_LOGZ_ONLY) != 0;
   if (!fwd_only && !Ez) return SVAE_ERR_BAD_ARG;
+  if (K <= SVAE_HMM_MAX_K) {
+    // 17..32 states with the caller's workspace: the tensor-core kernels; otherwise the register-resident kernel
+    if (K >= SVAE_HMM_TC_MIN_K && workspace && workspace_bytes >= svae_hmm_wide_workspace_bytes(B, T, K) && svae_hmm_tc_enabled())
+      return svae_hmm_estep_tc_launch(B, T, K, fwd_only, log_pi, log_A, node, active, logZ, Ez0, Etrans, Ez, workspace,
+                                      static_cast<cudaStream_t>(stream));
+    return svae_hmm_estep_masked(B, T, K, flags, log_pi, log_A, node, active, logZ, Ez0, Etrans, Ez, stream);
+  }
   if (K > SVAE_HMM_WIDE_MAX_K) return SVAE_ERR_UNSUPPORTED;
-  if (!workspace || workspace_bytes < svae_hmm_wide_workspace_bytes(K)) return SVAE_ERR_WORKSPACE;
+  if (!workspace || workspace_bytes < svae_hmm_wide_workspace_bytes(B, T, K)) return SVAE_ERR_WORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   double* ws = static_cast<double*>(workspace);
   const int KP = svae::hmm_wide_kp(K);

@@ -6,9 +6,9 @@ Same names and return structure as the reference:
   hmm_viterbi(natparam)   -> int32 state path                                      (hmm_inference.py:54-63)
   hmm_estep_slow          == hmm_estep       (hmm_inference.py:65, vgrad(hmm_logZ))
 natparam = (init_params (K,), pair_params (K,K) row = from-state, node_params (T,K) or (B,T,K)), all log
-values.  Everything runs in the sm_100a kernels of libsvae_b200.so; no CPU path.  Up to 32 states: the register-resident
-kernels of csrc/hmm_estep.cu (lane = state); 33..1024 states: one CTA per sequence, thread = state (csrc/hmm_wide.cu) --
-the reference takes any K.
+values.  Everything runs in the sm_100a kernels of libsvae_b200.so; no CPU path.  Up to 16 states: the register-resident
+kernels of csrc/hmm_estep.cu (lane = state); 17..32: 8 sequences per warp on the fp64 tensor-core instruction
+(csrc/hmm_tc.cu); 33..1024: one CTA per sequence, thread = state (csrc/hmm_wide.cu) -- the reference takes any K.
 """
 from __future__ import annotations
 import ctypes
@@ -51,8 +51,10 @@ def hmm_estep_forward(lp, lA, node, logz_only=False, active=None, out=None):
     L = _lib.lib()
     flags = _lib.SVAE_HMM_LOGZ_ONLY if logz_only else 0
     act = None if active is None else ctypes.c_void_p(active.data_ptr())
-    if K > _lib.SVAE_HMM_MAX_K:      # one CTA per sequence, thread = state; scratch for exp(log A - max) and its transpose
-        wbytes = L.svae_hmm_wide_workspace_bytes(K)
+    if K >= _lib.SVAE_HMM_TC_MIN_K:
+        # 17..32 states: tensor-core kernels (scratch: scaled forward messages and w/s, 2 B T K doubles);
+        # more than 32: one CTA per sequence, thread = state (scratch: exp(log A - max) and its transpose)
+        wbytes = L.svae_hmm_wide_workspace_bytes(B, T, K)
         work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
         code = L.svae_hmm_estep_wide(B, T, K, flags, P(lp), P(lA), P(node), act, P(logZ), P(Ez0), P(Etrans), P(Ez),
                                      ctypes.c_void_p(work.data_ptr()), wbytes, _lib.stream_ptr(dev))

@@ -69,6 +69,51 @@ def test_hmm_wide_vs_oracle(K_, T, B):
         assert rel_err(b_.grad.cpu().numpy(), wEt.sum(0)) < RTOL
 
 
+@pytest.mark.parametrize("K_,T,B", [(32, 500, 64), (32, 37, 13), (17, 33, 9), (24, 2, 8), (31, 1, 3), (20, 100, 1), (32, 9, 17)])
+def test_hmm_tensor_core_path_equals_register_kernel(K_, T, B):
+    """17..32 states: the tensor-core kernels (csrc/hmm_tc.cu, taken whenever the caller brings the workspace -- the Python
+    wrapper always does) against the oracle AND against the register-resident kernel through its own C-ABI entry point;
+    ragged batches (B not a multiple of the 8 sequences a warp owns), a per-sequence mask, forbidden transitions."""
+    import ctypes
+    from svae_b200 import _lib
+    from svae_b200.hmm import hmm_inference as K
+    rng = np.random.default_rng(K_ * 100 + T + B)
+    lp, lA = H.rand_hmm_natparam(K_, rng)
+    lA = lA + rng.standard_normal((K_, 1))
+    lA[rng.random((K_, K_)) < 0.1] = -np.inf                   # forbidden transitions
+    lA[np.arange(K_), np.arange(K_)] = 0.0
+    node = 3.0 * rng.standard_normal((B, T, K_))
+    w_logZ, (wE0, wEt, wEz) = H.hmm_estep((lp, lA, node))
+    lpg, lAg, ng = _g(lp), _g(lA), _g(node)
+    logZ, Ez0, Etrans, Ez = K.hmm_estep_forward(lpg, lAg, ng)
+    assert rel_err(logZ.cpu().numpy(), w_logZ) < RTOL
+    assert rel_err(Ez.cpu().numpy(), wEz) < RTOL and rel_err(Ez0.cpu().numpy(), wE0) < RTOL
+    if T > 1:
+        assert rel_err(Etrans.cpu().numpy(), wEt) < RTOL
+    else:
+        assert float(Etrans.abs().max()) == 0.0
+    # the register-resident kernel on the same inputs
+    new = lambda *sh: torch.empty(sh, dtype=torch.float64, device="cuda")
+    l2, e02, et2, ez2 = new(B), new(B, K_), new(B, K_, K_), new(B, T, K_)
+    P = _lib.ptr
+    code = _lib.lib().svae_hmm_estep_masked(B, T, K_, 0, P(lpg), P(lAg), P(ng), None, P(l2), P(e02), P(et2), P(ez2),
+                                            _lib.stream_ptr(ng.device))
+    assert code == 0
+    for a, b_ in ((logZ, l2), (Ez0, e02), (Etrans, et2), (Ez, ez2)):
+        assert rel_err(a.cpu().numpy(), b_.cpu().numpy()) < 1e-12 or float(b_.abs().max()) == 0.0
+    # log-normaliser alone
+    lz, _, _, _ = K.hmm_estep_forward(lpg, lAg, ng, logz_only=True)
+    assert rel_err(lz.cpu().numpy(), w_logZ) < RTOL
+    # mask: skipped sequences keep what the output buffers held
+    if B >= 3:
+        active = torch.ones(B, dtype=torch.int32, device="cuda")
+        active[1::2] = 0
+        sent = tuple(torch.full_like(x, -7.0) for x in (logZ, Ez0, Etrans, Ez))
+        got = K.hmm_estep_forward(lpg, lAg, ng, active=active, out=sent)
+        for g_, f_ in zip(got, (logZ, Ez0, Etrans, Ez)):
+            assert torch.equal(g_[0::2], f_[0::2]) and float((g_[1::2] + 7.0).abs().max()) == 0.0
+
+
 def test_hmm_wide_mask_and_limits():
     from svae_b200.hmm import hmm_inference as K
     rng = np.random.default_rng(11)

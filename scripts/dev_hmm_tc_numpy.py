@@ -179,3 +179,145 @@ if __name__ == "__main__":
         if T > 1:
             assert err(Et, wt) < 1e-11, (K, T)
     print("sweep emulation ok")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# v2: FOUR warps per group of 8 sequences (warp w owns n-tile w: states 8 w + 2 q + e), the vector exchanged through shared
+# memory once per step, every row normaliser applied one step LATE so that a step needs a single barrier.
+# Mirrors hmm_tc_sweep4_kernel statement by statement; "smem" arrays are written in one phase and read in the next.
+# ---------------------------------------------------------------------------------------------------------------------
+def sweep_cta4(log_pi, log_A, node):
+    Bw, T, K = node.shape
+    assert Bw == 8
+    gmax = float(np.float32(log_A.max()))
+    Pp = np.zeros((32, 32)); Pp[:K, :K] = np.exp(log_A - gmax)
+    W4 = range(4)
+    st = lambda w, e: 8 * w + 2 * Q + e                       # (32,) states of warp w, element e
+    inm = [[st(w, e) < K for e in range(2)] for w in W4]
+
+    def tile_mv(vall, Pm, w):                                 # own n-tile of vall @ Pm, two accumulator chains
+        c = np.zeros((2, 32, 2))
+        for s in range(8):
+            dmma(c[s & 1], vall[s >> 1][s & 1], Pm[k_state(s), 8 * w + G])
+        return (c[0] + c[1]).T                                # (2, 32): element e, lane
+
+    def ld(arr, t, w, fill):                                  # own tile of row t: (2, 32)
+        X = np.full((8, 32), fill); X[:, :K] = arr[:, t]
+        return np.array([X[G, st(w, e)] for e in range(2)])
+
+    def quad_tot(x):                                          # (32,) -> per-lane total over the lane's quad
+        return x.reshape(8, 4).sum(1)[G]
+
+    def quad_max(x):
+        return x.reshape(8, 4).max(1)[G]
+
+    wsA, wsW, Ez = np.zeros((8, T, 32)), np.zeros((8, T, 32)), np.zeros((8, T, 32))
+
+    def st_row(dst, t, w, v):                                 # own tile store
+        for e in range(2):
+            ok = inm[w][e]
+            dst[G[ok], t, st(w, e)[ok]] = v[e][ok]
+
+    lp = np.full(32, -np.inf); lp[:K] = log_pi
+    # ---- forward ----
+    vec = np.zeros((2, 4, 2, 32)); psum = np.zeros((2, 4, 32)); pmax = np.full((2, 4, 32), -np.inf)
+    x0 = [ld(node, 0, w, -np.inf) + np.array([lp[st(w, e)] for e in range(2)]) for w in W4]
+    pm0 = np.array([quad_max(np.float32(np.maximum(x0[w][0], x0[w][1])).astype(np.float64)) for w in W4])   # phase A
+    m0 = pm0.max(0)                                                                                            # after barrier
+    e_own = [np.where(inm[w], np.exp(x0[w] - m0), 0.0) for w in W4]
+    logZ = m0.copy()
+    cprod = np.ones(32)
+    for w in W4:                                              # publish message 0 (+ partial sums, + partial max of node 1)
+        vec[1, w] = e_own[w]
+        psum[1, w] = quad_tot(e_own[w][0] + e_own[w][1])
+        if T > 1:
+            xn = ld(node, 1, w, -np.inf)
+            pmax[1, w] = quad_max(np.float32(np.maximum(xn[0], xn[1])).astype(np.float64))
+    for t in range(1, T):
+        buf = t & 1
+        new_e = []
+        c = psum[buf].sum(0); m = pmax[buf].max(0)            # after the barrier: everybody's partials
+        invc = 1.0 / c
+        vall = vec[buf]                                       # (4,2,32)
+        for w in W4:
+            d = tile_mv(vall, Pp, w)
+            xn1 = ld(node, t, w, -np.inf)
+            ah = e_own[w] * invc
+            st_row(wsA, t - 1, w, ah)
+            new_e.append(np.where(inm[w], d * invc * np.exp(xn1 - m), 0.0))
+        logZ += m
+        cprod *= c
+        if (t & 7) == 7:
+            logZ += np.log(cprod); cprod[:] = 1.0
+        for w in W4:
+            e_own[w] = new_e[w]
+            vec[buf ^ 1, w] = e_own[w]
+            psum[buf ^ 1, w] = quad_tot(e_own[w][0] + e_own[w][1])
+            if t + 1 < T:
+                xn = ld(node, t + 1, w, -np.inf)
+                pmax[buf ^ 1, w] = quad_max(np.float32(np.maximum(xn[0], xn[1])).astype(np.float64))
+    c = psum[T & 1].sum(0)
+    cprod *= c
+    logZ += np.log(cprod) + (T - 1) * gmax
+    for w in W4:
+        st_row(Ez, T - 1, w, e_own[w] / c)
+    # ---- backward (lagged normaliser) ----
+    if T > 1:
+        U = np.zeros((2, 4, 2, 32)); ps = np.zeros((2, 4, 32)); pmx = np.full((2, 4, 32), -np.inf)
+        # prologue: U_{T-1} = exp(x_{T-1} - m) * 1, s_{T-1} := 1
+        xl = [ld(node, T - 1, w, -np.inf) for w in W4]
+        mm = np.array([quad_max(np.float32(np.maximum(xl[w][0], xl[w][1])).astype(np.float64)) for w in W4]).max(0)
+        b0 = (T - 2) & 1
+        for w in W4:
+            U[b0, w] = np.where(inm[w], np.exp(xl[w] - mm), 0.0)
+            ps[b0, w] = 0.25
+            xn = ld(node, T - 2, w, -np.inf)
+            pmx[b0, w] = quad_max(np.float32(np.maximum(xn[0], xn[1])).astype(np.float64))
+        prd_prev = [None] * 4; uw_prev = [None] * 4
+        for t in range(T - 2, -1, -1):
+            buf = t & 1
+            s_next = ps[buf].sum(0); inv = 1.0 / s_next       # s_{t+1}
+            m = pmx[buf].max(0)                               # max of node_t
+            Uall = U[buf]
+            newU = []
+            for w in W4:
+                if t < T - 2:                                 # finish step t+1 now that s_{t+1} is known
+                    st_row(Ez, t + 1, w, prd_prev[w] * inv)
+                    st_row(wsW, t + 1, w, uw_prev[w] * inv)   # W_{t+1} = U_{t+2} / s_{t+2} / s_{t+1}
+                Bt = tile_mv(Uall, Pp.T, w) * inv             # bu_t (own tile)
+                an = np.array([np.where(inm[w][e], wsA[G, t, st(w, e)], 0.0) for e in range(2)])
+                prd_prev[w] = an * Bt
+                uw_prev[w] = Uall[w] * inv                    # w_{t+1} = U_{t+1} / s_{t+1}, own tile
+                xt = ld(node, t, w, -np.inf)
+                newU.append(np.where(inm[w], np.exp(xt - m) * Bt, 0.0))
+            for w in W4:
+                U[buf ^ 1, w] = newU[w]
+                ps[buf ^ 1, w] = quad_tot(prd_prev[w][0] + prd_prev[w][1])
+                if t > 0:
+                    xn = ld(node, t - 1, w, -np.inf)
+                    pmx[buf ^ 1, w] = quad_max(np.float32(np.maximum(xn[0], xn[1])).astype(np.float64))
+        s0 = ps[1].sum(0); inv0 = 1.0 / s0                    # buffer (0 ^ 1)
+        for w in W4:
+            st_row(Ez, 0, w, prd_prev[w] * inv0)
+            st_row(wsW, 0, w, uw_prev[w] * inv0)
+    Et = np.zeros((8, K, K))
+    for r in range(8):
+        O = etrans_time_contraction(wsA[r, :T - 1], wsW[r, :T - 1]) if T > 1 else np.zeros((32, 32))
+        Et[r] = Pp[:K, :K] * O[:K, :K]
+    lane0 = np.arange(8) * 4
+    return logZ[lane0], Ez[:, :, :K], Ez[:, 0, :K], Et
+
+
+if __name__ == "__main__":
+    rng = np.random.default_rng(2)
+    for K, T in ((32, 21), (17, 9), (25, 1), (32, 2), (20, 8), (32, 3)):
+        lp, lA = HO.rand_hmm_natparam(K, rng)
+        lA = lA + rng.standard_normal((K, 1))
+        node = 3.0 * rng.standard_normal((8, T, K))
+        w_logZ, (w0, wt, wz) = HO.hmm_estep((lp, lA, node))
+        logZ, Ez, Ez0, Et = sweep_cta4(lp, lA, node)
+        err = lambda a, b: np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+        assert err(logZ, w_logZ) < 1e-12 and err(Ez, wz) < 1e-11 and err(Ez0, w0) < 1e-11, (K, T, err(logZ, w_logZ), err(Ez, wz))
+        if T > 1:
+            assert err(Et, wt) < 1e-11, (K, T, err(Et, wt))
+    print("4-warp sweep emulation ok")

@@ -275,6 +275,203 @@ __global__ void __launch_bounds__(32) hmm_tc_sweep_kernel(const HmmTcParams p) {
   }
 }
 
+// ---- forward-backward sweep, FOUR warps per 8 sequences -----------------------------------------------------------
+// ncu on the one-warp sweep above at the BASELINE batch (2048 sequences = 256 warps on 592 schedulers): 2 886 cycles per
+// step for a lone warp -- its 32 dependent-chain mma run on ONE scheduler's quarter of the fp64 tensor pipe and its 8 exp()
+// per lane sit behind them (stall reason "wait" 60 %).  Here warp w of a 4-warp CTA owns n-tile w of the same 8 sequences
+// (states 8 w + 2 q + e): 8 mma (two accumulator chains) and 2 exp() per lane and step; the full state vector the mma
+// need as A operands is exchanged through 4 KB of shared memory with ONE barrier per step, which also carries the
+// per-warp partial row sums / maxima.  To get by with one barrier every row normaliser is applied one step late:
+//   forward : e_t = (e_{t-1} P) / sum(e_{t-1}) .* exp(node_t - max_t)         (partials of sum(e_{t-1}) travel with e_{t-1})
+//   backward: U_{t+1} = exp(node_{t+1} - max) .* B_{t+1} is published BEFORE s_{t+1} = <ahat_{t+1}, B_{t+1}> is known;
+//             B_t = P U_{t+1} / s_{t+1};  E[z_{t+1}] and W_{t+1} = U_{t+2} / (s_{t+2} s_{t+1}) are stored one step late.
+// scripts/dev_hmm_tc_numpy.py (sweep_cta4) is this kernel statement by statement in NumPy, against the oracle.
+__global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p) {
+  __shared__ __align__(16) double vec[2][4][2][32];      // [buffer][n-tile][element][lane]
+  __shared__ double psum[2][4][8];                       // [buffer][warp][row]: partial row sums
+  __shared__ float pmax[2][4][8];                        // partial row maxima of the next node potentials
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+  const int K = p.K, T = p.T;
+  const long long seq = (long long)blockIdx.x * 8 + g;
+  const long long b = seq < p.B ? seq : (long long)p.B - 1;
+  const bool valid = seq < p.B && (!p.active || p.active[b] != 0);
+  const double NEG = -INFINITY;
+  const double gmax = tc_gmax(p.log_A, K, lane);
+  const int s0 = 8 * w + 2 * q;                           // this lane's two states: s0, s0 + 1
+  const bool in0 = s0 < K, in1 = s0 + 1 < K;
+
+  const double* node = p.node + (size_t)b * T * K + s0;
+  double* Ez = p.Ez ? p.Ez + (size_t)b * T * K + s0 : nullptr;
+  double* wsA = p.wsA ? p.wsA + (size_t)b * T * K + s0 : nullptr;
+  double* wsW = p.wsW ? p.wsW + (size_t)b * T * K + s0 : nullptr;
+
+  auto ld2n = [&](int t, double& x0, double& x1) {       // node potentials of this lane's two states at time t
+    x0 = in0 ? __ldg(node + (size_t)t * K) : NEG;
+    x1 = in1 ? __ldg(node + (size_t)t * K + 1) : NEG;
+  };
+  auto st2 = [&](double* base, int t, double v0, double v1) {
+    if (!valid) return;
+    if (in0) base[(size_t)t * K] = v0;
+    if (in1) base[(size_t)t * K + 1] = v1;
+  };
+  auto pmaxf2 = [&](double x0, double x1) { return quad_maxf(fmaxf((float)x0, (float)x1)); };
+  // own n-tile of (vector in vec[buf]) times the matrix whose fragments are F[s]: two accumulator chains
+  auto tile_mv = [&](int buf, const double (&F)[8], double& d0, double& d1) {
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+#pragma unroll
+    for (int s = 0; s < 8; s += 2) {
+      hmm_dmma(c0, c1, vec[buf][s >> 1][0][lane], F[s]);
+      hmm_dmma(c2, c3, vec[buf][s >> 1][1][lane], F[s + 1]);
+    }
+    d0 = c0 + c2;
+    d1 = c1 + c3;
+  };
+  auto sum4 = [&](int buf) { return (psum[buf][0][g] + psum[buf][1][g]) + (psum[buf][2][g] + psum[buf][3][g]); };
+  auto max4 = [&](int buf) { return (double)fmaxf(fmaxf(pmax[buf][0][g], pmax[buf][1][g]), fmaxf(pmax[buf][2][g], pmax[buf][3][g])); };
+
+  // ------------------------------------------------ forward ------------------------------------------------
+  double e0, e1;            // this lane's two entries of the (unnormalised) message
+  {
+    double F[8];            // F[s] = P[8 (s>>1) + 2 q + (s&1)][8 w + g]
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int i = 8 * (s >> 1) + 2 * q + (s & 1), j = 8 * w + g;
+      F[s] = (i < K && j < K) ? exp(p.log_A[i * K + j] - gmax) : 0.0;
+    }
+    double x0, x1;
+    ld2n(0, x0, x1);
+    x0 = in0 ? p.log_pi[s0] + x0 : NEG;
+    x1 = in1 ? p.log_pi[s0 + 1] + x1 : NEG;
+    {
+      const float pm = pmaxf2(x0, x1);
+      if (q == 0) pmax[0][w][g] = pm;
+    }
+    __syncthreads();
+    double logZ = max4(0);
+    e0 = in0 ? exp(x0 - logZ) : 0.0;
+    e1 = in1 ? exp(x1 - logZ) : 0.0;
+    double xn0 = NEG, xn1 = NEG, xq0 = NEG, xq1 = NEG;   // node[t], node[t+1] of the running step
+    if (T > 1) ld2n(1, xn0, xn1);
+    if (T > 2) ld2n(2, xq0, xq1);
+    // publish message 0 into buffer 1
+    vec[1][w][0][lane] = e0;
+    vec[1][w][1][lane] = e1;
+    {
+      const double ps = quad_sum(e0 + e1);
+      const float pm = pmaxf2(xn0, xn1);
+      if (q == 0) { psum[1][w][g] = ps; pmax[1][w][g] = pm; }
+    }
+    double cprod = 1.0;
+    for (int t = 1; t < T; ++t) {
+      const int buf = t & 1;
+      __syncthreads();
+      double xr0 = NEG, xr1 = NEG;
+      if (t + 2 < T) ld2n(t + 2, xr0, xr1);
+      const double c = sum4(buf);
+      const double m = max4(buf);
+      double d0, d1;
+      tile_mv(buf, F, d0, d1);
+      const double invc = tc_rcp(c);
+      if (!p.fwd_only) st2(wsA, t - 1, e0 * invc, e1 * invc);             // ahat_{t-1}
+      e0 = in0 ? d0 * invc * exp(xn0 - m) : 0.0;
+      e1 = in1 ? d1 * invc * exp(xn1 - m) : 0.0;
+      logZ += m;
+      cprod *= c;
+      if ((t & 7) == 7) {
+        logZ += log(cprod);
+        cprod = 1.0;
+      }
+      xn0 = xq0; xn1 = xq1; xq0 = xr0; xq1 = xr1;
+      vec[buf ^ 1][w][0][lane] = e0;
+      vec[buf ^ 1][w][1][lane] = e1;
+      const double ps = quad_sum(e0 + e1);
+      const float pm = pmaxf2(xn0, xn1);
+      if (q == 0) { psum[buf ^ 1][w][g] = ps; pmax[buf ^ 1][w][g] = pm; }
+    }
+    __syncthreads();
+    const double c = sum4(T & 1);
+    cprod *= c;
+    logZ += log(cprod) + (double)(T - 1) * gmax;
+    if (w == 0 && q == 0 && valid && p.logZ) p.logZ[b] = logZ;
+    if (p.fwd_only) return;
+    const double invc = 1.0 / c;
+    e0 *= invc;
+    e1 *= invc;                                                            // ahat_{T-1} = E[z_{T-1}]
+    st2(Ez, T - 1, e0, e1);
+    if (T == 1 && p.Ez0) st2(p.Ez0 + (size_t)b * K + s0, 0, e0, e1);
+  }
+  if (T == 1) return;
+
+  // ------------------------------------------------ backward -----------------------------------------------
+  double F[8];              // F[s] = P'[k][j] = P[8 w + g][8 (s>>1) + 2 q + (s&1)]
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int k = 8 * (s >> 1) + 2 * q + (s & 1), j = 8 * w + g;
+    F[s] = (k < K && j < K) ? exp(p.log_A[j * K + k] - gmax) : 0.0;
+  }
+  // prologue: U_{T-1} = exp(node_{T-1} - max), s_{T-1} := 1; the maximum needs its own exchange
+  double xl0, xl1;
+  ld2n(T - 1, xl0, xl1);
+  __syncthreads();                                        // everybody is done with the forward buffers
+  {
+    const float pm = pmaxf2(xl0, xl1);
+    if (q == 0) pmax[0][w][g] = pm;
+  }
+  __syncthreads();
+  const double mm = max4(0);
+  __syncthreads();                                        // pmax[0] is rewritten below when (T-2) is even
+  const int b0 = (T - 2) & 1;
+  vec[b0][w][0][lane] = in0 ? exp(xl0 - mm) : 0.0;
+  vec[b0][w][1][lane] = in1 ? exp(xl1 - mm) : 0.0;
+  double xn0, xn1;                                        // node[t] of the running step
+  ld2n(T - 2, xn0, xn1);
+  {
+    const float pm = pmaxf2(xn0, xn1);
+    if (q == 0) { psum[b0][w][g] = 0.25; pmax[b0][w][g] = pm; }
+  }
+  double a0 = (in0 && valid) ? wsA[(size_t)(T - 2) * K] : (in0 ? 1.0 / K : 0.0);       // ahat_t (this lane stored it)
+  double a1 = (in1 && valid) ? wsA[(size_t)(T - 2) * K + 1] : (in1 ? 1.0 / K : 0.0);
+  double prd0 = 0.0, prd1 = 0.0, uw0 = 0.0, uw1 = 0.0;   // finished one step late
+  for (int t = T - 2; t >= 0; --t) {
+    const int buf = t & 1;
+    __syncthreads();
+    double xp0 = NEG, xp1 = NEG, ap0 = 0.0, ap1 = 0.0;   // prefetch for iteration t - 1
+    if (t > 0) {
+      ld2n(t - 1, xp0, xp1);
+      ap0 = (in0 && valid) ? wsA[(size_t)(t - 1) * K] : (in0 ? 1.0 / K : 0.0);
+      ap1 = (in1 && valid) ? wsA[(size_t)(t - 1) * K + 1] : (in1 ? 1.0 / K : 0.0);
+    }
+    const double inv = tc_rcp(sum4(buf));                 // 1 / s_{t+1}
+    const double m = max4(buf);                           // max of node_t
+    double d0, d1;
+    tile_mv(buf, F, d0, d1);                              // (P U_{t+1}), own tile
+    if (t < T - 2) {                                      // finish step t + 1
+      st2(Ez, t + 1, prd0 * inv, prd1 * inv);
+      st2(wsW, t + 1, uw0 * inv, uw1 * inv);
+    }
+    const double B0 = d0 * inv, B1 = d1 * inv;            // bu_t
+    prd0 = a0 * B0;
+    prd1 = a1 * B1;
+    uw0 = vec[buf][w][0][lane] * inv;                     // w_{t+1} = U_{t+1} / s_{t+1}
+    uw1 = vec[buf][w][1][lane] * inv;
+    vec[buf ^ 1][w][0][lane] = in0 ? exp(xn0 - m) * B0 : 0.0;             // U_t
+    vec[buf ^ 1][w][1][lane] = in1 ? exp(xn1 - m) * B1 : 0.0;
+    {
+      const double ps = quad_sum(prd0 + prd1);
+      const float pm = pmaxf2(xp0, xp1);
+      if (q == 0) { psum[buf ^ 1][w][g] = ps; pmax[buf ^ 1][w][g] = pm; }
+    }
+    xn0 = xp0; xn1 = xp1; a0 = ap0; a1 = ap1;
+  }
+  __syncthreads();
+  {
+    const double inv0 = 1.0 / sum4(1);                    // s_0 (published into buffer 0 ^ 1)
+    st2(Ez, 0, prd0 * inv0, prd1 * inv0);
+    st2(wsW, 0, uw0 * inv0, uw1 * inv0);
+    if (p.Ez0) st2(p.Ez0 + (size_t)b * K + s0, 0, prd0 * inv0, prd1 * inv0);
+  }
+}
+
 // ---- transition counts: one warp per sequence, contraction over time on the tensor cores -------------------------
 //   Etrans[i][j] = P[i][j] * sum_{t < T-1} ahat_t[i] (w_{t+1}/s_t)[j]
 constexpr int kTransWarps = 4;
@@ -353,7 +550,12 @@ int svae_hmm_estep_tc_launch(int B, int T, int K, bool fwd_only, const double* l
   p.logZ = logZ; p.Ez0 = Ez0; p.Ez = Ez;
   p.wsA = static_cast<double*>(workspace);
   p.wsW = p.wsA + (size_t)B * T * K;
-  svae::hmm_tc_sweep_kernel<<<(unsigned)((B + 7) / 8), 32, 0, s>>>(p);
+  // four warps per 8 sequences (one n-tile each) unless SVAE_HMM_TC_WARPS=1 asks for the one-warp sweep
+  static const int warps = [] { const char* e = getenv("SVAE_HMM_TC_WARPS"); return e ? atoi(e) : 4; }();
+  if (warps == 1)
+    svae::hmm_tc_sweep_kernel<<<(unsigned)((B + 7) / 8), 32, 0, s>>>(p);
+  else
+    svae::hmm_tc_sweep4_kernel<<<(unsigned)((B + 7) / 8), 128, 0, s>>>(p);
   g_svae_launches.fetch_add(1);
   if (!fwd_only && Etrans) {
     svae::hmm_tc_trans_kernel<<<(unsigned)((B + svae::kTransWarps - 1) / svae::kTransWarps), 32 * svae::kTransWarps, 0, s>>>(

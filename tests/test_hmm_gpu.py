@@ -114,6 +114,28 @@ def test_hmm_tensor_core_path_equals_register_kernel(K_, T, B):
             assert torch.equal(g_[0::2], f_[0::2]) and float((g_[1::2] + 7.0).abs().max()) == 0.0
 
 
+def test_hmm_tensor_core_one_warp_sweep_in_a_child_process():
+    """SVAE_HMM_TC_WARPS=1 selects the one-warp-per-8-sequences sweep (read once per process): same numbers."""
+    import os, subprocess, sys
+    from util import ROOT
+    code = (
+        "import numpy as np, torch\n"
+        "from oracle import hmm_numpy as H\n"
+        "from svae_b200.hmm import hmm_inference as K\n"
+        "rng = np.random.default_rng(5)\n"
+        "for K_, T, B in ((32, 40, 11), (19, 7, 8), (32, 1, 2)):\n"
+        "    lp, lA = H.rand_hmm_natparam(K_, rng); node = 3.0 * rng.standard_normal((B, T, K_))\n"
+        "    g = lambda x: torch.as_tensor(x, dtype=torch.float64, device='cuda')\n"
+        "    logZ, (E0, Et, Ez) = K.hmm_estep((g(lp), g(lA), g(node)))\n"
+        "    w_logZ, (w0, wt, wz) = H.hmm_estep((lp, lA, node))\n"
+        "    err = lambda a, b: float(np.abs(a.cpu().numpy() - b).max() / max(np.abs(b).max(), 1e-300))\n"
+        "    assert err(logZ, w_logZ) < 1e-9 and err(Ez, wz) < 1e-9 and err(E0, w0) < 1e-9 and (T == 1 or err(Et, wt) < 1e-9)\n"
+        "print('ONE_WARP_OK')\n")
+    env = dict(os.environ, SVAE_HMM_TC_WARPS="1", PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=180, cwd=ROOT)
+    assert "ONE_WARP_OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_hmm_wide_mask_and_limits():
     from svae_b200.hmm import hmm_inference as K
     rng = np.random.default_rng(11)

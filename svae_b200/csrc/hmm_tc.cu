@@ -286,7 +286,11 @@ __global__ void __launch_bounds__(32) hmm_tc_sweep_kernel(const HmmTcParams p) {
 //   backward: U_{t+1} = exp(node_{t+1} - max) .* B_{t+1} is published BEFORE s_{t+1} = <ahat_{t+1}, B_{t+1}> is known;
 //             B_t = P U_{t+1} / s_{t+1};  E[z_{t+1}] and W_{t+1} = U_{t+2} / (s_{t+2} s_{t+1}) are stored one step late.
 // scripts/dev_hmm_tc_numpy.py (sweep_cta4) is this kernel statement by statement in NumPy, against the oracle.
+#ifndef SVAE_HMM_TC_PF
+#define SVAE_HMM_TC_PF 4
+#endif
 __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p) {
+  constexpr int PF = SVAE_HMM_TC_PF;                     // prefetch depth (steps) of the global loads
   __shared__ __align__(16) double vec[2][4][2][32];      // [buffer][n-tile][element][lane]
   __shared__ double psum[2][4][8];                       // [buffer][warp][row]: partial row sums
   __shared__ float pmax[2][4][8];                        // partial row maxima of the next node potentials
@@ -350,15 +354,19 @@ __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p)
     double logZ = max4(0);
     e0 = in0 ? exp(x0 - logZ) : 0.0;
     e1 = in1 ? exp(x1 - logZ) : 0.0;
-    double xn0 = NEG, xn1 = NEG, xq0 = NEG, xq1 = NEG;   // node[t], node[t+1] of the running step
-    if (T > 1) ld2n(1, xn0, xn1);
-    if (T > 2) ld2n(2, xq0, xq1);
+    // node potentials of steps t .. t + PF - 1 ride in registers: a step (~1 000 cycles) is shorter than a DRAM round trip
+    double xq0[PF], xq1[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      xq0[i] = xq1[i] = NEG;
+      if (1 + i < T) ld2n(1 + i, xq0[i], xq1[i]);
+    }
     // publish message 0 into buffer 1
     vec[1][w][0][lane] = e0;
     vec[1][w][1][lane] = e1;
     {
       const double ps = quad_sum(e0 + e1);
-      const float pm = pmaxf2(xn0, xn1);
+      const float pm = pmaxf2(xq0[0], xq1[0]);
       if (q == 0) { psum[1][w][g] = ps; pmax[1][w][g] = pm; }
     }
     double cprod = 1.0;
@@ -366,7 +374,8 @@ __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p)
       const int buf = t & 1;
       __syncthreads();
       double xr0 = NEG, xr1 = NEG;
-      if (t + 2 < T) ld2n(t + 2, xr0, xr1);
+      if (t + PF < T) ld2n(t + PF, xr0, xr1);
+      const double xn0 = xq0[0], xn1 = xq1[0];
       const double c = sum4(buf);
       const double m = max4(buf);
       double d0, d1;
@@ -381,11 +390,14 @@ __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p)
         logZ += log(cprod);
         cprod = 1.0;
       }
-      xn0 = xq0; xn1 = xq1; xq0 = xr0; xq1 = xr1;
+#pragma unroll
+      for (int i = 0; i + 1 < PF; ++i) { xq0[i] = xq0[i + 1]; xq1[i] = xq1[i + 1]; }
+      xq0[PF - 1] = xr0;
+      xq1[PF - 1] = xr1;
       vec[buf ^ 1][w][0][lane] = e0;
       vec[buf ^ 1][w][1][lane] = e1;
       const double ps = quad_sum(e0 + e1);
-      const float pm = pmaxf2(xn0, xn1);
+      const float pm = pmaxf2(xq0[0], xq1[0]);
       if (q == 0) { psum[buf ^ 1][w][g] = ps; pmax[buf ^ 1][w][g] = pm; }
     }
     __syncthreads();
@@ -423,24 +435,35 @@ __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p)
   const int b0 = (T - 2) & 1;
   vec[b0][w][0][lane] = in0 ? exp(xl0 - mm) : 0.0;
   vec[b0][w][1][lane] = in1 ? exp(xl1 - mm) : 0.0;
-  double xn0, xn1;                                        // node[t] of the running step
-  ld2n(T - 2, xn0, xn1);
+  // node[t - i], ahat_{t-i} (this lane stored them) for i < PF ride in registers
+  auto lda = [&](int t, double& v0, double& v1) {
+    v0 = (in0 && valid) ? wsA[(size_t)t * K] : (in0 ? 1.0 / K : 0.0);
+    v1 = (in1 && valid) ? wsA[(size_t)t * K + 1] : (in1 ? 1.0 / K : 0.0);
+  };
+  double qn0[PF], qn1[PF], qa0[PF], qa1[PF];
+#pragma unroll
+  for (int i = 0; i < PF; ++i) {
+    qn0[i] = qn1[i] = NEG;
+    qa0[i] = qa1[i] = 0.0;
+    if (T - 2 - i >= 0) {
+      ld2n(T - 2 - i, qn0[i], qn1[i]);
+      lda(T - 2 - i, qa0[i], qa1[i]);
+    }
+  }
   {
-    const float pm = pmaxf2(xn0, xn1);
+    const float pm = pmaxf2(qn0[0], qn1[0]);
     if (q == 0) { psum[b0][w][g] = 0.25; pmax[b0][w][g] = pm; }
   }
-  double a0 = (in0 && valid) ? wsA[(size_t)(T - 2) * K] : (in0 ? 1.0 / K : 0.0);       // ahat_t (this lane stored it)
-  double a1 = (in1 && valid) ? wsA[(size_t)(T - 2) * K + 1] : (in1 ? 1.0 / K : 0.0);
   double prd0 = 0.0, prd1 = 0.0, uw0 = 0.0, uw1 = 0.0;   // finished one step late
   for (int t = T - 2; t >= 0; --t) {
     const int buf = t & 1;
     __syncthreads();
-    double xp0 = NEG, xp1 = NEG, ap0 = 0.0, ap1 = 0.0;   // prefetch for iteration t - 1
-    if (t > 0) {
-      ld2n(t - 1, xp0, xp1);
-      ap0 = (in0 && valid) ? wsA[(size_t)(t - 1) * K] : (in0 ? 1.0 / K : 0.0);
-      ap1 = (in1 && valid) ? wsA[(size_t)(t - 1) * K + 1] : (in1 ? 1.0 / K : 0.0);
+    double xp0 = NEG, xp1 = NEG, ap0 = 0.0, ap1 = 0.0;   // prefetch for iteration t - PF
+    if (t - PF >= 0) {
+      ld2n(t - PF, xp0, xp1);
+      lda(t - PF, ap0, ap1);
     }
+    const double xn0 = qn0[0], xn1 = qn1[0], a0 = qa0[0], a1 = qa1[0];
     const double inv = tc_rcp(sum4(buf));                 // 1 / s_{t+1}
     const double m = max4(buf);                           // max of node_t
     double d0, d1;
@@ -456,12 +479,14 @@ __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p)
     uw1 = vec[buf][w][1][lane] * inv;
     vec[buf ^ 1][w][0][lane] = in0 ? exp(xn0 - m) * B0 : 0.0;             // U_t
     vec[buf ^ 1][w][1][lane] = in1 ? exp(xn1 - m) * B1 : 0.0;
+#pragma unroll
+    for (int i = 0; i + 1 < PF; ++i) { qn0[i] = qn0[i + 1]; qn1[i] = qn1[i + 1]; qa0[i] = qa0[i + 1]; qa1[i] = qa1[i + 1]; }
+    qn0[PF - 1] = xp0; qn1[PF - 1] = xp1; qa0[PF - 1] = ap0; qa1[PF - 1] = ap1;
     {
       const double ps = quad_sum(prd0 + prd1);
-      const float pm = pmaxf2(xp0, xp1);
+      const float pm = pmaxf2(qn0[0], qn1[0]);            // node[t-1]: its maximum travels with U_t
       if (q == 0) { psum[buf ^ 1][w][g] = ps; pmax[buf ^ 1][w][g] = pm; }
     }
-    xn0 = xp0; xn1 = xp1; a0 = ap0; a1 = ap1;
   }
   __syncthreads();
   {
@@ -505,18 +530,23 @@ __global__ void __launch_bounds__(32 * kTransWarps) hmm_tc_trans_kernel(int B, i
       wv[it] = ld ? W[(size_t)t * K + 8 * it + g] : 0.0;        // B[q][g] = (w/s)_{t0+q}[8 jt + g]
     }
   };
+  // two groups of 4 time steps in flight ahead of the one being multiplied (ncu: long-scoreboard stalls with one)
+  double a1[4], w1[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) a[it] = w[it] = a1[it] = w1[it] = 0.0;
   if (steps > 0) fetch(0, a, w);
+  if (steps > 4) fetch(4, a1, w1);
   for (int t0 = 0; t0 < steps; t0 += 4) {
     double an[4], wn[4];
-    if (t0 + 4 < steps) fetch(t0 + 4, an, wn);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) an[it] = wn[it] = 0.0;
+    if (t0 + 8 < steps) fetch(t0 + 8, an, wn);
 #pragma unroll
     for (int it = 0; it < 4; ++it)
 #pragma unroll
       for (int jt = 0; jt < 4; ++jt) hmm_dmma(acc[it][jt][0], acc[it][jt][1], a[it], w[jt]);
-    if (t0 + 4 < steps) {
 #pragma unroll
-      for (int it = 0; it < 4; ++it) { a[it] = an[it]; w[it] = wn[it]; }
-    }
+    for (int it = 0; it < 4; ++it) { a[it] = a1[it]; w[it] = w1[it]; a1[it] = an[it]; w1[it] = wn[it]; }
   }
   double* out = Etrans + (size_t)b * K * K;
 #pragma unroll

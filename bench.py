@@ -581,6 +581,8 @@ def run_ours(args):
                 cfg["hmm_K%d_T%d_B%d" % (Kh, Th, Bh)] = dict(
                     value=Bh / (ms * 1e-3), unit=UNIT, ms=ms,
                     roofline=_roof(8 * (2 * Th * Kh + Kh * Kh + Kh + 1) * Bh, ms, peak),
+                    kernels="hmm_tc_sweep4_kernel + hmm_tc_trans_kernel (fp64 tensor-core instruction mma.m8n8k4, 8 sequences "
+                            "per fragment row block; workspace 2 B T K doubles allocated inside the timed call)",
                     cpu_baseline=cpu_rate("hmm", (Kh, Th), UNIT))
                 del nat
                 # SLDS K=8 d=10 T=200 B=1024: run_inference (mean-field fixed point + differentiable evaluation)

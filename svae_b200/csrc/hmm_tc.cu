@@ -286,11 +286,22 @@ __global__ void __launch_bounds__(32) hmm_tc_sweep_kernel(const HmmTcParams p) {
 //   backward: U_{t+1} = exp(node_{t+1} - max) .* B_{t+1} is published BEFORE s_{t+1} = <ahat_{t+1}, B_{t+1}> is known;
 //             B_t = P U_{t+1} / s_{t+1};  E[z_{t+1}] and W_{t+1} = U_{t+2} / (s_{t+2} s_{t+1}) are stored one step late.
 // scripts/dev_hmm_tc_numpy.py (sweep_cta4) is this kernel statement by statement in NumPy, against the oracle.
+// prefetch depth (steps) of the global loads, forward / backward sweep.  Measured (profiles/r02_hmm_tc_summary.txt): deeper
+// rings cost registers (80 -> 110) and occupancy at large batches for no gain at the BASELINE batch.
 #ifndef SVAE_HMM_TC_PF
-#define SVAE_HMM_TC_PF 4
+#define SVAE_HMM_TC_PF 2
+#endif
+#ifndef SVAE_HMM_TC_PB
+#define SVAE_HMM_TC_PB 1
+#endif
+#ifndef SVAE_HMM_TC_TRANS_AHEAD
+#define SVAE_HMM_TC_TRANS_AHEAD 1     // groups of 4 time steps in flight ahead of the one being multiplied (1 or 2)
+#endif
+#ifndef SVAE_HMM_TC_CHAINS
+#define SVAE_HMM_TC_CHAINS 2          // accumulate chains of a tile's 8 mma: 2 (x4 deep), 4 (x2 deep) or 8 (independent)
 #endif
 __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p) {
-  constexpr int PF = SVAE_HMM_TC_PF;                     // prefetch depth (steps) of the global loads
+  constexpr int PF = SVAE_HMM_TC_PF, PB = SVAE_HMM_TC_PB;
   __shared__ __align__(16) double vec[2][4][2][32];      // [buffer][n-tile][element][lane]
   __shared__ double psum[2][4][8];                       // [buffer][warp][row]: partial row sums
   __shared__ float pmax[2][4][8];                        // partial row maxima of the next node potentials
@@ -321,6 +332,25 @@ __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p)
   auto pmaxf2 = [&](double x0, double x1) { return quad_maxf(fmaxf((float)x0, (float)x1)); };
   // own n-tile of (vector in vec[buf]) times the matrix whose fragments are F[s]: two accumulator chains
   auto tile_mv = [&](int buf, const double (&F)[8], double& d0, double& d1) {
+#if SVAE_HMM_TC_CHAINS == 8
+    // eight independent mma (no accumulate chain at all), then an add tree
+    double c[8][2];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      c[s][0] = c[s][1] = 0.0;
+      hmm_dmma(c[s][0], c[s][1], vec[buf][s >> 1][s & 1][lane], F[s]);
+    }
+    d0 = ((c[0][0] + c[1][0]) + (c[2][0] + c[3][0])) + ((c[4][0] + c[5][0]) + (c[6][0] + c[7][0]));
+    d1 = ((c[0][1] + c[1][1]) + (c[2][1] + c[3][1])) + ((c[4][1] + c[5][1]) + (c[6][1] + c[7][1]));
+#elif SVAE_HMM_TC_CHAINS == 4
+    double c[4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k][0] = c[k][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) hmm_dmma(c[s & 3][0], c[s & 3][1], vec[buf][s >> 1][s & 1][lane], F[s]);
+    d0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
+    d1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+#else
     double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
 #pragma unroll
     for (int s = 0; s < 8; s += 2) {
@@ -329,6 +359,7 @@ __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p)
     }
     d0 = c0 + c2;
     d1 = c1 + c3;
+#endif
   };
   auto sum4 = [&](int buf) { return (psum[buf][0][g] + psum[buf][1][g]) + (psum[buf][2][g] + psum[buf][3][g]); };
   auto max4 = [&](int buf) { return (double)fmaxf(fmaxf(pmax[buf][0][g], pmax[buf][1][g]), fmaxf(pmax[buf][2][g], pmax[buf][3][g])); };
@@ -435,14 +466,14 @@ __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p)
   const int b0 = (T - 2) & 1;
   vec[b0][w][0][lane] = in0 ? exp(xl0 - mm) : 0.0;
   vec[b0][w][1][lane] = in1 ? exp(xl1 - mm) : 0.0;
-  // node[t - i], ahat_{t-i} (this lane stored them) for i < PF ride in registers
+  // node[t - i], ahat_{t-i} (this lane stored them) for i < PB ride in registers
   auto lda = [&](int t, double& v0, double& v1) {
     v0 = (in0 && valid) ? wsA[(size_t)t * K] : (in0 ? 1.0 / K : 0.0);
     v1 = (in1 && valid) ? wsA[(size_t)t * K + 1] : (in1 ? 1.0 / K : 0.0);
   };
-  double qn0[PF], qn1[PF], qa0[PF], qa1[PF];
+  double qn0[PB], qn1[PB], qa0[PB], qa1[PB];
 #pragma unroll
-  for (int i = 0; i < PF; ++i) {
+  for (int i = 0; i < PB; ++i) {
     qn0[i] = qn1[i] = NEG;
     qa0[i] = qa1[i] = 0.0;
     if (T - 2 - i >= 0) {
@@ -458,10 +489,10 @@ __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p)
   for (int t = T - 2; t >= 0; --t) {
     const int buf = t & 1;
     __syncthreads();
-    double xp0 = NEG, xp1 = NEG, ap0 = 0.0, ap1 = 0.0;   // prefetch for iteration t - PF
-    if (t - PF >= 0) {
-      ld2n(t - PF, xp0, xp1);
-      lda(t - PF, ap0, ap1);
+    double xp0 = NEG, xp1 = NEG, ap0 = 0.0, ap1 = 0.0;   // prefetch for iteration t - PB
+    if (t - PB >= 0) {
+      ld2n(t - PB, xp0, xp1);
+      lda(t - PB, ap0, ap1);
     }
     const double xn0 = qn0[0], xn1 = qn1[0], a0 = qa0[0], a1 = qa1[0];
     const double inv = tc_rcp(sum4(buf));                 // 1 / s_{t+1}
@@ -480,8 +511,8 @@ __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p)
     vec[buf ^ 1][w][0][lane] = in0 ? exp(xn0 - m) * B0 : 0.0;             // U_t
     vec[buf ^ 1][w][1][lane] = in1 ? exp(xn1 - m) * B1 : 0.0;
 #pragma unroll
-    for (int i = 0; i + 1 < PF; ++i) { qn0[i] = qn0[i + 1]; qn1[i] = qn1[i + 1]; qa0[i] = qa0[i + 1]; qa1[i] = qa1[i + 1]; }
-    qn0[PF - 1] = xp0; qn1[PF - 1] = xp1; qa0[PF - 1] = ap0; qa1[PF - 1] = ap1;
+    for (int i = 0; i + 1 < PB; ++i) { qn0[i] = qn0[i + 1]; qn1[i] = qn1[i + 1]; qa0[i] = qa0[i + 1]; qa1[i] = qa1[i + 1]; }
+    qn0[PB - 1] = xp0; qn1[PB - 1] = xp1; qa0[PB - 1] = ap0; qa1[PB - 1] = ap1;
     {
       const double ps = quad_sum(prd0 + prd1);
       const float pm = pmaxf2(qn0[0], qn1[0]);            // node[t-1]: its maximum travels with U_t
@@ -530,7 +561,7 @@ __global__ void __launch_bounds__(32 * kTransWarps) hmm_tc_trans_kernel(int B, i
       wv[it] = ld ? W[(size_t)t * K + 8 * it + g] : 0.0;        // B[q][g] = (w/s)_{t0+q}[8 jt + g]
     }
   };
-  // two groups of 4 time steps in flight ahead of the one being multiplied (ncu: long-scoreboard stalls with one)
+#if SVAE_HMM_TC_TRANS_AHEAD == 2
   double a1[4], w1[4];
 #pragma unroll
   for (int it = 0; it < 4; ++it) a[it] = w[it] = a1[it] = w1[it] = 0.0;
@@ -548,6 +579,23 @@ __global__ void __launch_bounds__(32 * kTransWarps) hmm_tc_trans_kernel(int B, i
 #pragma unroll
     for (int it = 0; it < 4; ++it) { a[it] = a1[it]; w[it] = w1[it]; a1[it] = an[it]; w1[it] = wn[it]; }
   }
+#else
+#pragma unroll
+  for (int it = 0; it < 4; ++it) a[it] = w[it] = 0.0;
+  if (steps > 0) fetch(0, a, w);
+  for (int t0 = 0; t0 < steps; t0 += 4) {
+    double an[4], wn[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) an[it] = wn[it] = 0.0;
+    if (t0 + 4 < steps) fetch(t0 + 4, an, wn);
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+#pragma unroll
+      for (int jt = 0; jt < 4; ++jt) hmm_dmma(acc[it][jt][0], acc[it][jt][1], a[it], w[jt]);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) { a[it] = an[it]; w[it] = wn[it]; }
+  }
+#endif
   double* out = Etrans + (size_t)b * K * K;
 #pragma unroll
   for (int it = 0; it < 4; ++it)

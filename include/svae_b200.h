@@ -280,7 +280,8 @@ int svae_hmm_estep_masked(int B, int T, int K, int flags, const double* log_pi, 
  *   K <  SVAE_HMM_TC_MIN_K        the register-resident kernel of svae_hmm_estep_masked (workspace ignored);
  *   SVAE_HMM_TC_MIN_K..32 states  with a workspace: 8 sequences per warp, the K x K products and the transition counts on
  *                                 the fp64 tensor-core instruction (csrc/hmm_tc.cu; the workspace holds the scaled forward
- *                                 messages and w_{t+1}/s_t, 2 B T K doubles); workspace NULL: as above;
+ *                                 messages and w_{t+1}/s_t, 2 B T K doubles; not needed with SVAE_HMM_LOGZ_ONLY);
+ *                                 workspace NULL otherwise: as above;
  *   33..SVAE_HMM_WIDE_MAX_K       one CTA per sequence, thread = state (csrc/hmm_wide.cu); the workspace (required) holds
  *                                 exp(log_A - max), its transpose and the shift, written by a one-CTA preparation launch.
  * Same arguments, outputs and mask otherwise; everything is enqueued on `stream`. */

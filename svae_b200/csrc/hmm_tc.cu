@@ -626,8 +626,8 @@ int svae_hmm_estep_tc_launch(int B, int T, int K, bool fwd_only, const double* l
   p.B = B; p.T = T; p.K = K; p.fwd_only = fwd_only ? 1 : 0;
   p.log_pi = log_pi; p.log_A = log_A; p.node = node; p.active = active;
   p.logZ = logZ; p.Ez0 = Ez0; p.Ez = Ez;
-  p.wsA = static_cast<double*>(workspace);
-  p.wsW = p.wsA + (size_t)B * T * K;
+  p.wsA = static_cast<double*>(workspace);              // NULL is fine for the log-normaliser alone
+  p.wsW = workspace ? p.wsA + (size_t)B * T * K : nullptr;
   // four warps per 8 sequences (one n-tile each) unless SVAE_HMM_TC_WARPS=1 asks for the one-warp sweep
   static const int warps = [] { const char* e = getenv("SVAE_HMM_TC_WARPS"); return e ? atoi(e) : 4; }();
   if (warps == 1)

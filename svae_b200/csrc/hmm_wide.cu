@@ -67,7 +67,9 @@ extern "C" int svae_hmm_estep_wide(int B, int T, int K, int flags, const double*
   if (!fwd_only && !Ez) return SVAE_ERR_BAD_ARG;
   if (K <= SVAE_HMM_MAX_K) {
     // 17..32 states with the caller's workspace: the tensor-core kernels; otherwise the register-resident kernel
-    if (K >= SVAE_HMM_TC_MIN_K && workspace && workspace_bytes >= svae_hmm_wide_workspace_bytes(B, T, K) && svae_hmm_tc_enabled())
+    // (the log-normaliser alone leaves nothing in the workspace: no buffer needed)
+    const bool ws_ok = fwd_only || (workspace && workspace_bytes >= svae_hmm_wide_workspace_bytes(B, T, K));
+    if (K >= SVAE_HMM_TC_MIN_K && ws_ok && svae_hmm_tc_enabled())
       return svae_hmm_estep_tc_launch(B, T, K, fwd_only, log_pi, log_A, node, active, logZ, Ez0, Etrans, Ez, workspace,
                                       static_cast<cudaStream_t>(stream));
     return svae_hmm_estep_masked(B, T, K, flags, log_pi, log_A, node, active, logZ, Ez0, Etrans, Ez, stream);

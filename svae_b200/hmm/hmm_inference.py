@@ -54,8 +54,9 @@ def hmm_estep_forward(lp, lA, node, logz_only=False, active=None, out=None):
     if K >= _lib.SVAE_HMM_TC_MIN_K:
         # 17..32 states: tensor-core kernels (scratch: scaled forward messages and w/s, 2 B T K doubles);
         # more than 32: one CTA per sequence, thread = state (scratch: exp(log A - max) and its transpose)
-        wbytes = L.svae_hmm_wide_workspace_bytes(B, T, K)
-        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        tc_logz = logz_only and K <= _lib.SVAE_HMM_MAX_K          # the tensor-core forward sweep alone stores nothing
+        wbytes = 0 if tc_logz else L.svae_hmm_wide_workspace_bytes(B, T, K)
+        work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=dev)
         code = L.svae_hmm_estep_wide(B, T, K, flags, P(lp), P(lA), P(node), act, P(logZ), P(Ez0), P(Etrans), P(Ez),
                                      ctypes.c_void_p(work.data_ptr()), wbytes, _lib.stream_ptr(dev))
         _lib.check(code, "svae_hmm_estep_wide")

@@ -8,8 +8,10 @@
 // warp-instructions per sequence-step; short-scoreboard (shared-memory) stalls dominate, and neither more resident warps
 // (the -DSVAE_HMM_OSMEM build: 16 instead of 8 per SM, same 1.13 ms) nor fewer registers move it.  The dense contraction
 // belongs on the tensor cores, with the BATCH as the M dimension:
-//   * a warp owns 8 sequences (row g = lane >> 2 of every fragment); a step's 8 x 32 by 32 x 32 product is 32 mma.m8n8k4
-//     whose B operands -- P = exp(log A - max) forward, P' backward -- stay in registers for the whole sweep;
+//   * 8 sequences form the rows of every fragment (row g = lane >> 2); a step's 8 x 32 by 32 x 32 product is 32 mma.m8n8k4
+//     whose B operands -- P = exp(log A - max) forward, P' backward -- stay in registers for the whole sweep.  The default
+//     sweep (hmm_tc_sweep4_kernel) spreads the four n-tiles of those 8 sequences over the four warps of a CTA; the one-warp
+//     sweep (hmm_tc_sweep_kernel, SVAE_HMM_TC_WARPS=1) keeps all of it in one warp and needs no shared memory at all;
 //   * state vectors live in the ACCUMULATOR layout (lane (g,q): states 8 nt + 2 q + e, nt < 4, e < 2), and the A operand of
 //     slab s is defined as element [s >> 1][s & 1] of it, i.e. the contraction runs over the states in the order
 //     8 (s >> 1) + 2 q + (s & 1): the output of one step is the input of the next with NO shuffle or shared memory (the P

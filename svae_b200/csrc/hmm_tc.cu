@@ -324,17 +324,16 @@ __global__ void __launch_bounds__(32) hmm_tc_sweep_kernel(const HmmTcParams p) {
 #ifndef SVAE_HMM_TC_PF
 #define SVAE_HMM_TC_PF 2
 #endif
-#ifndef SVAE_HMM_TC_PB
-#define SVAE_HMM_TC_PB 1
-#endif
+// (backward depth: a template parameter chosen at launch -- 2 while every CTA of the grid is resident anyway, 1 beyond)
 #ifndef SVAE_HMM_TC_TRANS_AHEAD
 #define SVAE_HMM_TC_TRANS_AHEAD 1     // groups of 4 time steps in flight ahead of the one being multiplied (1 or 2)
 #endif
 #ifndef SVAE_HMM_TC_CHAINS
 #define SVAE_HMM_TC_CHAINS 2          // accumulate chains of a tile's 8 mma: 2 (x4 deep), 4 (x2 deep) or 8 (independent)
 #endif
+template <int PB>
 __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p) {
-  constexpr int PF = SVAE_HMM_TC_PF, PB = SVAE_HMM_TC_PB;
+  constexpr int PF = SVAE_HMM_TC_PF;
   __shared__ __align__(16) double vec[2][4][2][32];      // [buffer][n-tile][element][lane]
   __shared__ double psum[2][4][8];                       // [buffer][warp][row]: partial row sums
   __shared__ float pmax[2][4][8];                        // partial row maxima of the next node potentials
@@ -665,8 +664,17 @@ int svae_hmm_estep_tc_launch(int B, int T, int K, bool fwd_only, const double* l
   static const int warps = [] { const char* e = getenv("SVAE_HMM_TC_WARPS"); return e ? atoi(e) : 4; }();
   if (warps == 1)
     svae::hmm_tc_sweep_kernel<<<(unsigned)((B + 7) / 8), 32, 0, s>>>(p);
-  else
-    svae::hmm_tc_sweep4_kernel<<<(unsigned)((B + 7) / 8), 128, 0, s>>>(p);
+  else {
+    // backward prefetch depth: 2 steps while every CTA of the grid is resident whatever its register count (measured
+    // 0.965 -> 0.930 ms at 2048 sequences), 1 beyond (the extra registers cost occupancy: 4.41 vs 4.54 ms at 16 384)
+    const unsigned grid = (unsigned)((B + 7) / 8);
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (grid <= 4u * (unsigned)sms)
+      svae::hmm_tc_sweep4_kernel<2><<<grid, 128, 0, s>>>(p);
+    else
+      svae::hmm_tc_sweep4_kernel<1><<<grid, 128, 0, s>>>(p);
+  }
   g_svae_launches.fetch_add(1);
   if (!fwd_only && Etrans) {
     svae::hmm_tc_trans_kernel<<<(unsigned)((B + svae::kTransWarps - 1) / svae::kTransWarps), 32 * svae::kTransWarps, 0, s>>>(

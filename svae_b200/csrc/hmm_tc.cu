@@ -560,6 +560,192 @@ __global__ void __launch_bounds__(128) hmm_tc_sweep4_kernel(const HmmTcParams p)
   }
 }
 
+// ---- forward-backward sweep, EIGHT warps per 8 sequences ----------------------------------------------------------
+// Same exchange scheme as the four-warp sweep; warps 2w and 2w+1 both form n-tile w (the fp64 tensor pipe is 12 % busy:
+// the duplicate mma are free) and each keeps ONE of the two accumulator elements, so a lane carries one state: half the
+// scalar work per warp-step (one exp, one store stream) and twice the warps per scheduler at a given batch.
+template <int PB>
+__global__ void __launch_bounds__(256) hmm_tc_sweep8_kernel(const HmmTcParams p) {
+  constexpr int PF = SVAE_HMM_TC_PF;
+  __shared__ __align__(16) double vec[2][4][2][32];      // [buffer][n-tile][element][lane]
+  __shared__ double psum[2][8][8];                       // [buffer][warp][row]: partial row sums
+  __shared__ float pmax[2][8][8];                        // partial row maxima of the next node potentials
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, w = wi >> 1, el = wi & 1, g = lane >> 2, q = lane & 3;
+  const int K = p.K, T = p.T;
+  const long long seq = (long long)blockIdx.x * 8 + g;
+  const long long b = seq < p.B ? seq : (long long)p.B - 1;
+  const bool valid = seq < p.B && (!p.active || p.active[b] != 0);
+  const double NEG = -INFINITY;
+  const double gmax = tc_gmax(p.log_A, K, lane);
+  const int s0 = 8 * w + 2 * q + el;                      // this lane's state
+  const bool in0 = s0 < K;
+
+  const double* node = p.node + (size_t)b * T * K + s0;
+  double* Ez = p.Ez ? p.Ez + (size_t)b * T * K + s0 : nullptr;
+  double* wsA = p.wsA ? p.wsA + (size_t)b * T * K + s0 : nullptr;
+  double* wsW = p.wsW ? p.wsW + (size_t)b * T * K + s0 : nullptr;
+
+  auto ldn = [&](int t) { return in0 ? __ldg(node + (size_t)t * K) : NEG; };
+  auto st1 = [&](double* base, int t, double v) {
+    if (valid && in0) base[(size_t)t * K] = v;
+  };
+  auto pmaxf1 = [&](double x) { return quad_maxf((float)x); };
+  auto tile_mv = [&](int buf, const double (&F)[8]) {     // element `el` of the own n-tile
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+#pragma unroll
+    for (int s = 0; s < 8; s += 2) {
+      hmm_dmma(c0, c1, vec[buf][s >> 1][0][lane], F[s]);
+      hmm_dmma(c2, c3, vec[buf][s >> 1][1][lane], F[s + 1]);
+    }
+    return el ? c1 + c3 : c0 + c2;
+  };
+  auto sum8 = [&](int buf) {
+    return ((psum[buf][0][g] + psum[buf][1][g]) + (psum[buf][2][g] + psum[buf][3][g])) +
+           ((psum[buf][4][g] + psum[buf][5][g]) + (psum[buf][6][g] + psum[buf][7][g]));
+  };
+  auto max8 = [&](int buf) {
+    return (double)fmaxf(fmaxf(fmaxf(pmax[buf][0][g], pmax[buf][1][g]), fmaxf(pmax[buf][2][g], pmax[buf][3][g])),
+                         fmaxf(fmaxf(pmax[buf][4][g], pmax[buf][5][g]), fmaxf(pmax[buf][6][g], pmax[buf][7][g])));
+  };
+
+  // ------------------------------------------------ forward ------------------------------------------------
+  double e0;                // this lane's entry of the (unnormalised) message
+  {
+    double F[8];            // F[s] = P[8 (s>>1) + 2 q + (s&1)][8 w + g]
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int i = 8 * (s >> 1) + 2 * q + (s & 1), j = 8 * w + g;
+      F[s] = (i < K && j < K) ? exp(p.log_A[i * K + j] - gmax) : 0.0;
+    }
+    double x0 = ldn(0);
+    x0 = in0 ? p.log_pi[s0] + x0 : NEG;
+    {
+      const float pm = pmaxf1(x0);
+      if (q == 0) pmax[0][wi][g] = pm;
+    }
+    __syncthreads();
+    double logZ = max8(0);
+    e0 = in0 ? tc_exp(x0 - logZ) : 0.0;
+    double xq0[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) xq0[i] = (1 + i < T) ? ldn(1 + i) : NEG;
+    vec[1][w][el][lane] = e0;
+    {
+      const double ps = quad_sum(e0);
+      const float pm = pmaxf1(xq0[0]);
+      if (q == 0) { psum[1][wi][g] = ps; pmax[1][wi][g] = pm; }
+    }
+    double cprod = 1.0;
+    for (int t = 1; t < T; ++t) {
+      const int buf = t & 1;
+      __syncthreads();
+      const double xr0 = (t + PF < T) ? ldn(t + PF) : NEG;
+      const double xn0 = xq0[0];
+      const double c = sum8(buf);
+      const double m = max8(buf);
+      const double d0 = tile_mv(buf, F);
+      const double invc = tc_rcp(c);
+      if (!p.fwd_only) st1(wsA, t - 1, e0 * invc);                        // ahat_{t-1}
+      e0 = in0 ? d0 * invc * tc_exp(xn0 - m) : 0.0;
+      logZ += m;
+      cprod *= c;
+      if ((t & 7) == 7) {
+        logZ += log(cprod);
+        cprod = 1.0;
+      }
+#pragma unroll
+      for (int i = 0; i + 1 < PF; ++i) xq0[i] = xq0[i + 1];
+      xq0[PF - 1] = xr0;
+      vec[buf ^ 1][w][el][lane] = e0;
+      const double ps = quad_sum(e0);
+      const float pm = pmaxf1(xq0[0]);
+      if (q == 0) { psum[buf ^ 1][wi][g] = ps; pmax[buf ^ 1][wi][g] = pm; }
+    }
+    __syncthreads();
+    const double c = sum8(T & 1);
+    cprod *= c;
+    logZ += log(cprod) + (double)(T - 1) * gmax;
+    if (wi == 0 && q == 0 && valid && p.logZ) p.logZ[b] = logZ;
+    if (p.fwd_only) return;
+    e0 *= 1.0 / c;                                                         // ahat_{T-1} = E[z_{T-1}]
+    st1(Ez, T - 1, e0);
+    if (T == 1 && p.Ez0) st1(p.Ez0 + (size_t)b * K + s0, 0, e0);
+  }
+  if (T == 1) return;
+
+  // ------------------------------------------------ backward -----------------------------------------------
+  double F[8];              // F[s] = P'[k][j] = P[8 w + g][8 (s>>1) + 2 q + (s&1)]
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int k = 8 * (s >> 1) + 2 * q + (s & 1), j = 8 * w + g;
+    F[s] = (k < K && j < K) ? exp(p.log_A[j * K + k] - gmax) : 0.0;
+  }
+  const double xl0 = ldn(T - 1);
+  __syncthreads();                                        // everybody is done with the forward buffers
+  {
+    const float pm = pmaxf1(xl0);
+    if (q == 0) pmax[0][wi][g] = pm;
+  }
+  __syncthreads();
+  const double mm = max8(0);
+  __syncthreads();                                        // pmax[0] is rewritten below when (T-2) is even
+  const int b0 = (T - 2) & 1;
+  vec[b0][w][el][lane] = in0 ? tc_exp(xl0 - mm) : 0.0;
+  auto lda = [&](int t) { return (in0 && valid) ? wsA[(size_t)t * K] : (in0 ? 1.0 / K : 0.0); };
+  double qn0[PB], qa0[PB];
+#pragma unroll
+  for (int i = 0; i < PB; ++i) {
+    qn0[i] = NEG;
+    qa0[i] = 0.0;
+    if (T - 2 - i >= 0) {
+      qn0[i] = ldn(T - 2 - i);
+      qa0[i] = lda(T - 2 - i);
+    }
+  }
+  {
+    const float pm = pmaxf1(qn0[0]);
+    if (q == 0) { psum[b0][wi][g] = 0.125; pmax[b0][wi][g] = pm; }
+  }
+  double prd0 = 0.0, uw0 = 0.0;                           // finished one step late
+  for (int t = T - 2; t >= 0; --t) {
+    const int buf = t & 1;
+    __syncthreads();
+    double xp0 = NEG, ap0 = 0.0;                          // prefetch for iteration t - PB
+    if (t - PB >= 0) {
+      xp0 = ldn(t - PB);
+      ap0 = lda(t - PB);
+    }
+    const double xn0 = qn0[0], a0 = qa0[0];
+    const double inv = tc_rcp(sum8(buf));                 // 1 / s_{t+1}
+    const double m = max8(buf);                           // max of node_t
+    const double d0 = tile_mv(buf, F);                    // (P U_{t+1}), own element
+    if (t < T - 2) {                                      // finish step t + 1
+      st1(Ez, t + 1, prd0 * inv);
+      st1(wsW, t + 1, uw0 * inv);
+    }
+    const double B0 = d0 * inv;                           // bu_t
+    prd0 = a0 * B0;
+    uw0 = vec[buf][w][el][lane] * inv;                    // w_{t+1} = U_{t+1} / s_{t+1}
+    vec[buf ^ 1][w][el][lane] = in0 ? tc_exp(xn0 - m) * B0 : 0.0;         // U_t
+#pragma unroll
+    for (int i = 0; i + 1 < PB; ++i) { qn0[i] = qn0[i + 1]; qa0[i] = qa0[i + 1]; }
+    qn0[PB - 1] = xp0;
+    qa0[PB - 1] = ap0;
+    {
+      const double ps = quad_sum(prd0);
+      const float pm = pmaxf1(qn0[0]);                    // node[t-1]: its maximum travels with U_t
+      if (q == 0) { psum[buf ^ 1][wi][g] = ps; pmax[buf ^ 1][wi][g] = pm; }
+    }
+  }
+  __syncthreads();
+  {
+    const double inv0 = 1.0 / sum8(1);                    // s_0 (published into buffer 0 ^ 1)
+    st1(Ez, 0, prd0 * inv0);
+    st1(wsW, 0, uw0 * inv0);
+    if (p.Ez0) st1(p.Ez0 + (size_t)b * K + s0, 0, prd0 * inv0);
+  }
+}
+
 // ---- transition counts: one warp per sequence, contraction over time on the tensor cores -------------------------
 //   Etrans[i][j] = P[i][j] * sum_{t < T-1} ahat_t[i] (w_{t+1}/s_t)[j]
 constexpr int kTransWarps = 4;
@@ -664,6 +850,10 @@ int svae_hmm_estep_tc_launch(int B, int T, int K, bool fwd_only, const double* l
   static const int warps = [] { const char* e = getenv("SVAE_HMM_TC_WARPS"); return e ? atoi(e) : 4; }();
   if (warps == 1)
     svae::hmm_tc_sweep_kernel<<<(unsigned)((B + 7) / 8), 32, 0, s>>>(p);
+  else if (warps == 8)
+    svae::hmm_tc_sweep8_kernel<2><<<(unsigned)((B + 7) / 8), 256, 0, s>>>(p);
+  else if (warps == 81)
+    svae::hmm_tc_sweep8_kernel<1><<<(unsigned)((B + 7) / 8), 256, 0, s>>>(p);
   else {
     // backward prefetch depth: 2 steps while every CTA of the grid is resident whatever its register count (measured
     // 0.965 -> 0.930 ms at 2048 sequences), 1 beyond (the extra registers cost occupancy: 4.41 vs 4.54 ms at 16 384)

@@ -321,3 +321,25 @@ if __name__ == "__main__":
         if T > 1:
             assert err(Et, wt) < 1e-11, (K, T, err(Et, wt))
     print("4-warp sweep emulation ok")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# v3: EIGHT warps per group of 8 sequences -- warps 2w and 2w+1 both form n-tile w and keep element e = warp & 1 of it (one
+# state per lane).  Only the partial sums / maxima change (8 per row instead of 4); checked here against the 4-warp statement.
+# ---------------------------------------------------------------------------------------------------------------------
+def partials_8_equal_4(rng):
+    v = rng.standard_normal((4, 2, 32))                       # a published vector [tile][element][lane]
+    quad = lambda x: x.reshape(8, 4).sum(1)[G]
+    p4 = np.array([quad(v[w][0] + v[w][1]) for w in range(4)]).sum(0)
+    p8 = np.array([quad(v[wi >> 1][wi & 1]) for wi in range(8)]).sum(0)
+    assert np.allclose(p4, p8)
+    # and the per-lane state of warp wi is 8 (wi >> 1) + 2 q + (wi & 1): every state of the 8 x 32 block exactly once
+    seen = np.zeros((8, 32), dtype=int)
+    for wi in range(8):
+        seen[G, 8 * (wi >> 1) + 2 * Q + (wi & 1)] += 1
+    assert (seen == 1).all()
+
+
+if __name__ == "__main__":
+    partials_8_equal_4(np.random.default_rng(3))
+    print("8-warp partials ok")

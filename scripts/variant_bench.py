@@ -121,6 +121,7 @@ def worker(tag):
     if "lds10s0" in cases: lds_case(10, 200, 4096, 0)
     if "lds16" in cases: lds_case(16, 200, 4096, 1)
     if "lds10small" in cases: lds_case(10, 7, 5, 1)
+    if "vjp10" in cases: vjp_case(10, 200, 4096, 1)
     if "vjp16" in cases: vjp_case(16, 200, 4096, 1)
     if "vjp12" in cases: vjp_case(12, 200, 4096, 1)
     if "vjp14" in cases: vjp_case(14, 200, 4096, 1)

@@ -334,7 +334,7 @@ int svae_hmm_chain_messages(int B, int C, int K, const double* log_pi, const dou
  *   svae_hmm_chain_viterbi: max-product recursion over the chunk matrices and back-tracking: boundary_states (B,C+1)
  *       int32 = the optimal state at every chunk boundary (first maximal index on ties); delta_scratch (B,C+1,K).
  * Stage 3 is svae_hmm_viterbi on the B*C chunks with both end states pinned by -1e300 penalties.  The phase code of both
- * is pinned on CPU (tests/test_hmm_pit_cpu.py); their first GPU run is pending (tests/test_hmm_pit_gpu.py, xfail). */
+ * is pinned on CPU (tests/test_hmm_pit_cpu.py) and checked on the GPU against the sequential kernel (tests/test_hmm_pit_gpu.py). */
 int svae_hmm_compose_chunks_maxplus(int B, int T, int K, int chunk_len, const double* log_A, const double* node,
                                     double* chunk_V, void* stream);
 int svae_hmm_chain_viterbi(int B, int C, int K, const double* log_pi, const double* chunk_V,

@@ -319,6 +319,8 @@ __global__ void __launch_bounds__(32) hmm_tc_sweep_kernel(const HmmTcParams p) {
 //   backward: U_{t+1} = exp(node_{t+1} - max) .* B_{t+1} is published BEFORE s_{t+1} = <ahat_{t+1}, B_{t+1}> is known;
 //             B_t = P U_{t+1} / s_{t+1};  E[z_{t+1}] and W_{t+1} = U_{t+2} / (s_{t+2} s_{t+1}) are stored one step late.
 // scripts/dev_hmm_tc_numpy.py (sweep_cta4) is this kernel statement by statement in NumPy, against the oracle.
+//
+// Build-time knobs, each measured on a B200 (profiles/r02_hmm_tc_summary.txt) -- the defaults are the winners:
 // prefetch depth (steps) of the global loads, forward / backward sweep.  Measured (profiles/r02_hmm_tc_summary.txt): deeper
 // rings cost registers (80 -> 110) and occupancy at large batches for no gain at the BASELINE batch.
 #ifndef SVAE_HMM_TC_PF

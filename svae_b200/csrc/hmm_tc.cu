@@ -750,7 +750,10 @@ __global__ void __launch_bounds__(256) hmm_tc_sweep8_kernel(const HmmTcParams p)
 
 // ---- transition counts: one warp per sequence, contraction over time on the tensor cores -------------------------
 //   Etrans[i][j] = P[i][j] * sum_{t < T-1} ahat_t[i] (w_{t+1}/s_t)[j]
-constexpr int kTransWarps = 4;
+#ifndef SVAE_HMM_TC_TRANS_WARPS
+#define SVAE_HMM_TC_TRANS_WARPS 4
+#endif
+constexpr int kTransWarps = SVAE_HMM_TC_TRANS_WARPS;
 __global__ void __launch_bounds__(32 * kTransWarps) hmm_tc_trans_kernel(int B, int T, int K, const double* log_A,
                                                                         const int* active, const double* wsA,
                                                                         const double* wsW, double* Etrans) {

@@ -105,7 +105,8 @@ def lds_estep_forward(init_params, pair_params, node_params, num_samples=1, eps=
         nJd, nJ = nJ, torch.zeros_like(nh)
     if n > _lib.SVAE_LDS_MAX_N:
         raise ValueError("latent dimension %d > %d: the fused kernel is compiled for n <= %d; the reference-named drivers "
-                         "(natural_lds_inference_general, natural_lds_estep_general, natural_lds_sample) take larger n "
+                         "and primitives (natural_lds_inference_general, natural_lds_estep_general, natural_lds_sample, "
+                         "natural_filter_forward_general, natural_smoother_general, natural_sample_backward) take larger n "
                          "through lds_large.py" % (n, _lib.SVAE_LDS_MAX_N, _lib.SVAE_LDS_MAX_N))
     iJ, ih, ilogZ = _canonical_init_params(init_params, device)
     init_per_seq = iJ.dim() == 3
@@ -622,6 +623,12 @@ def natural_filter_forward_general(init_params, pair_params, node_params):
     Messages are natural-parameter pairs (J (B,T,n,n), h (B,T,n)) [no B axis for unbatched node_params];
     the filtered message is the prediction message conditioned on the node potential (pyx:64-66).
     Differentiable w.r.t. the node potentials (natural_filter_grad, pyx:92-145)."""
+    if _latent_dim(node_params) > _lib.SVAE_LDS_MAX_N:      # batched device linear algebra + autograd (lds_large.py)
+        from . import lds_large
+        msgs, lognorm, batched = lds_large.filter_forward(init_params, pair_params, node_params)
+        if not batched:
+            return tuple(tuple(x[0] for x in m) for m in msgs), lognorm[0]
+        return msgs, lognorm
     h_any = node_params[1]
     device = h_any.device if torch.is_tensor(h_any) and h_any.is_cuda else torch.device("cuda", torch.cuda.current_device())
     nJ, nh, nlogZ, batched = _canonical_node_params(node_params, device)
@@ -689,6 +696,11 @@ def _messages_run(forward_messages, pair_params, num_samples, eps, generator, wa
     B, T, n = h_filt.shape
     homog = _is_homog(pair_params)
     S = int(num_samples) if num_samples else 0
+    if n > _lib.SVAE_LDS_MAX_N:                              # batched device linear algebra + autograd (lds_large.py)
+        from . import lds_large
+        o = lds_large.from_messages(J_filt, h_filt, pair_params, S, eps, not homog, want_stats, generator)
+        o["batched"] = batched
+        return o, homog
     if needs_grad:
         if eps is None and S > 0:
             eps = torch.randn((B, T, S, n), dtype=torch.float64, device=device, generator=generator)

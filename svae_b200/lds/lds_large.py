@@ -21,9 +21,12 @@ import torch
 from .. import _lib
 
 
-def _run(iJ, ih, ilogZ, J11, J12, J22, plogZ, nJ, nh, nlogZ, eps, S, per_t, want_stats=True):
+def _run(iJ, ih, ilogZ, J11, J12, J22, plogZ, nJ, nh, nlogZ, eps, S, per_t, want_stats=True, msgs_out=False, from_msgs=None):
     """All arguments canonical fp64 tensors on one device.  iJ (n,n)|(B,n,n), ih (n)|(B,n); pair blocks (n,n) | (T-1,n,n) |
-    (B,T-1,n,n) natural form; nJ (B,T,n) diagonal or (B,T,n,n) dense natural form; nh (B,T,n); eps (B,T,S,n) or None."""
+    (B,T-1,n,n) natural form; nJ (B,T,n) diagonal or (B,T,n,n) dense natural form; nh (B,T,n); eps (B,T,S,n) or None.
+    msgs_out: also return the prediction messages (natural form) as o["J_pred"], o["h_pred"] (natural_filter_forward_general).
+    from_msgs = (J_filt (B,T,n,n), h_filt (B,T,n)) natural form: run the backward sweeps from GIVEN filtered messages
+    (natural_smoother_general / natural_sample_backward; node potentials and init are then ignored, lognorm is meaningless)."""
     B, T, n = nh.shape
     dense = nJ.dim() == 4
     dev, dt = nh.device, nh.dtype
@@ -43,9 +46,19 @@ def _run(iJ, ih, ilogZ, J11, J12, J22, plogZ, nJ, nh, nlogZ, eps, S, per_t, want
     lognorm = torch.zeros(B, dtype=dt, device=dev)
     info_max = torch.zeros((), dtype=torch.int32, device=dev)
     Gs, Minvs, ms, bs = [], [], [], []
+    Jp, hp = [], []
     for t in range(T):
-        M = a + (-2.0 * nJ[:, t] if dense else torch.diag_embed(-2.0 * nJ[:, t]))
-        hf = hpred + nh[:, t]
+        if from_msgs is not None:
+            M = -2.0 * from_msgs[0][:, t]
+            if t < T - 1:
+                M = M - 2.0 * pair(t)[0]
+            hf = from_msgs[1][:, t]
+        else:
+            if msgs_out:      # a = J_pred (information form) + J11 of this step
+                Jp.append(-0.5 * (a + 2.0 * pair(t)[0]) if t < T - 1 else -0.5 * a)
+                hp.append(hpred)
+            M = a + (-2.0 * nJ[:, t] if dense else torch.diag_embed(-2.0 * nJ[:, t]))
+            hf = hpred + nh[:, t]
         L, info = torch.linalg.cholesky_ex(M)
         info_max = torch.maximum(info_max, info.max())
         eye = torch.eye(n, dtype=dt, device=dev).expand(B, n, n)
@@ -106,6 +119,8 @@ def _run(iJ, ih, ilogZ, J11, J12, J22, plogZ, nJ, nh, nlogZ, eps, S, per_t, want
     o["E_node_x"] = E_x
     o["E_node_xx"] = Exx_t if dense else torch.diagonal(Exx_t, dim1=-2, dim2=-1)
     o["samples"] = torch.stack(xs, 1).transpose(-1, -2) if S > 0 else None        # (B,T,S,n)
+    if msgs_out and from_msgs is None:
+        o["J_pred"], o["h_pred"] = torch.stack([x.expand(B, n, n) for x in Jp], 1), torch.stack([x.expand(B, n) for x in hp], 1)
     if want_stats:
         o["E_init_xx"], o["E_init_x"] = Exx[0], mus[0]
         if T > 1:
@@ -152,4 +167,45 @@ def estep(init_params, pair_params, node_params, num_samples, eps, per_t, genera
     if check_status and int(o["status"].item()):
         raise FloatingPointError("LDS E-step: a filtered precision is not positive definite (reference asserts: "
                                  "svae/lds/gaussian.py:48,64)")
+    return o
+
+
+def filter_forward(init_params, pair_params, node_params):
+    """natural_filter_forward_general for n > 16: ((J_pred, h_pred), (J_filt, h_filt)) natural form, lognorm; batched."""
+    from . import lds_inference as LI
+    h_any = node_params[1]
+    device = h_any.device if torch.is_tensor(h_any) and h_any.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    nJ, nh, nlogZ, batched = LI._canonical_node_params(node_params, device)
+    if not nh.is_cuda:
+        raise RuntimeError("svae_b200: the LDS E-step runs on CUDA tensors only (there is no CPU path)")
+    B, T, n = nh.shape
+    iJ, ih, ilogZ = LI._canonical_init_params(init_params, device)
+    J11, J12, J22, plogZ, _, _ = LI._canonical_pair_params(pair_params, B, T, n, device)
+    det = lambda v: None if v is None else v.detach()
+    o = _run(det(iJ), det(ih), det(ilogZ), det(J11), det(J12), det(J22), det(plogZ), nJ, nh, nlogZ, None, 0, False,
+             want_stats=False, msgs_out=True)
+    J_filt = o["J_pred"] + (nJ if nJ.dim() == 4 else torch.diag_embed(nJ))
+    return ((o["J_pred"], o["h_pred"]), (J_filt, o["h_pred"] + nh)), o["lognorm"], batched
+
+
+def from_messages(J_filt, h_filt, pair_params, num_samples, eps, per_t, want_stats, generator=None):
+    """natural_smoother_general / natural_sample_backward for n > 16 from given filtered messages (B,T,n,n), (B,T,n):
+    the dict lds_inference._pack_stats consumes; gradients reach the messages through autograd."""
+    from . import lds_inference as LI
+    if not h_filt.is_cuda:
+        raise RuntimeError("svae_b200: the LDS E-step runs on CUDA tensors only (there is no CPU path)")
+    B, T, n = h_filt.shape
+    device = h_filt.device
+    J11, J12, J22, plogZ, _, _ = LI._canonical_pair_params(pair_params, B, T, n, device)
+    S = int(num_samples) if num_samples else 0
+    if eps is not None:
+        eps = _lib.f64(eps, device)
+    elif S > 0:
+        eps = torch.randn((B, T, S, n), dtype=torch.float64, device=device, generator=generator)
+    det = lambda v: None if v is None else v.detach()
+    z = torch.zeros((B, T, n), dtype=torch.float64, device=device)
+    eye = -0.5 * torch.eye(n, dtype=torch.float64, device=device)
+    o = _run(eye, z[0, 0], None, det(J11), det(J12), det(J22), None, z, z, None, det(eps), S, per_t, want_stats,
+             from_msgs=(J_filt, h_filt))
+    o["lognorm"] = torch.zeros(B, dtype=torch.float64, device=device)
     return o

@@ -80,3 +80,33 @@ def test_vjp_matches_oracle_autograd():
         + (o["E_node_xx"] * t64(g_stats[2][0])).sum() + (o["E_node_x"] * t64(g_stats[2][1])).sum()
     gJ, gh = torch.autograd.grad(total, (nJ, nh))
     assert rel_err(gJ.numpy(), wJ) < 1e-9 and rel_err(gh.numpy(), wh) < 1e-9
+
+
+def test_message_ports_match_oracle():
+    """The three primitives one by one (natural_filter_forward_general, natural_smoother_general, natural_sample_backward) through
+    the message modes of the same recursion."""
+    rng = np.random.default_rng(21)
+    n, T, B, S = 18, 8, 2, 2
+    init, pair = O.rand_lds_natparam(n, rng)
+    node = O.rand_node_potentials(B, T, n, rng)
+    eps = rng.standard_normal((B, T, S, n))
+    (w_pred, w_filt), w_lognorm = O.natural_filter_forward_general(init, pair, node)
+    iJ, ih, ilz = (t64(x) for x in init)
+    J11, J12, J22, plz = (t64(x) for x in pair)
+    o = LL._run(iJ, ih, ilz.reshape(-1), J11, J12, J22, plz, t64(node[0]), t64(node[1]), t64(node[2]), None, 0, False,
+                want_stats=False, msgs_out=True)
+    assert rel_err(o["J_pred"].numpy(), w_pred[0]) < 1e-11 and rel_err(o["h_pred"].numpy(), w_pred[1]) < 1e-11
+    assert rel_err(o["lognorm"].numpy(), w_lognorm) < 1e-11
+    J_filt = o["J_pred"] + torch.diag_embed(t64(node[0]))
+    h_filt = o["h_pred"] + t64(node[1])
+    assert rel_err(J_filt.numpy(), w_filt[0]) < 1e-11 and rel_err(h_filt.numpy(), w_filt[1]) < 1e-11
+    wE_init, wE_pair, wE_node = O.natural_smoother_general((w_pred, w_filt), pair)
+    w_samples = O.natural_sample_backward_general((w_pred, w_filt), pair, eps)
+    z = torch.zeros(B, T, n, dtype=torch.float64)
+    o2 = LL._run(-0.5 * torch.eye(n, dtype=torch.float64), z[0, 0], None, J11, J12, J22, None, z, z, None, t64(eps), S, False,
+                 from_msgs=(t64(w_filt[0]), t64(w_filt[1])))
+    assert rel_err(o2["samples"].numpy(), w_samples) < 1e-10
+    assert rel_err(o2["E_node_x"].numpy(), wE_node[1]) < 1e-10 and rel_err(o2["E_node_xx"].numpy(), wE_node[0]) < 1e-10
+    assert rel_err(o2["E_init_xx"].numpy(), wE_init[0]) < 1e-10
+    for k, name in enumerate(("E_pair_xx", "E_pair_xxn", "E_pair_xnxn")):
+        assert rel_err(o2[name].numpy(), wE_pair[k]) < 1e-10, name

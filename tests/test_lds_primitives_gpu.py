@@ -241,3 +241,26 @@ def test_message_gradients_reach_a_custom_producer():
         fd = (f(Jf + eps * dJ, hf + eps * dh) - f(Jf - eps * dJ, hf - eps * dh)) / (2 * eps)
     an = (Jf.grad * dJ).sum() + (hf.grad * dh).sum()
     assert abs(float(fd) - float(an)) < 1e-6 * max(1.0, abs(float(an)))
+
+
+def test_primitives_above_the_compiled_latent_dimension():
+    """n > 16: the three primitives run the same recursions as batched device linear algebra (svae_b200/lds/lds_large.py)
+    behind the same names; filter differentiable w.r.t. the node potentials, smoother / sampler w.r.t. the messages."""
+    from svae_b200.lds import lds_inference as K
+    rng = np.random.default_rng(31)
+    n, T, B, S = 19, 7, 3, 1
+    init, pair = O.rand_lds_natparam(n, rng)
+    node = O.rand_node_potentials(B, T, n, rng)
+    eps = rng.standard_normal((B, T, S, n))
+    (w_pred, w_filt), w_lognorm = O.natural_filter_forward_general(init, pair, node)
+    nJ, nh = _gpu(node[0]).requires_grad_(True), _gpu(node[1]).requires_grad_(True)
+    ((Jp, hp), (Jf, hf)), lognorm = K.natural_filter_forward_general(_g(init), _g(pair), (nJ, nh))
+    for got, want in ((Jp, w_pred[0]), (hp, w_pred[1]), (Jf, w_filt[0]), (hf, w_filt[1]), (lognorm, w_lognorm)):
+        assert rel_err(got.detach().cpu().numpy(), want) < RTOL
+    wE_init, wE_pair, wE_node = O.natural_smoother_general((w_pred, w_filt), pair)
+    E_init, E_pair, E_node = K.natural_smoother_general(((Jp, hp), (Jf, hf)), _g(pair))
+    assert rel_err(E_node[1].detach().cpu().numpy(), wE_node[1]) < RTOL and rel_err(E_pair[1].detach().cpu().numpy(), wE_pair[1]) < RTOL
+    smp = K.natural_sample_backward(((Jp, hp), (Jf, hf)), _g(pair), S, _gpu(eps))
+    assert rel_err(smp.detach().cpu().numpy(), O.natural_sample_backward_general((w_pred, w_filt), pair, eps)) < RTOL
+    (smp.sum() + E_node[1].sum() - lognorm.sum()).backward()          # the chain filter -> smoother / sampler is differentiable
+    assert bool(torch.isfinite(nJ.grad).all()) and bool(torch.isfinite(nh.grad).all()) and float(nh.grad.abs().max()) > 0

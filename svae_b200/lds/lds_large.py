@@ -198,8 +198,12 @@ def from_messages(J_filt, h_filt, pair_params, num_samples, eps, per_t, want_sta
     device = h_filt.device
     J11, J12, J22, plogZ, _, _ = LI._canonical_pair_params(pair_params, B, T, n, device)
     S = int(num_samples) if num_samples else 0
+    if J_filt.shape != (B, T, n, n):
+        raise ValueError("forward messages must be ((B,T,n,n), (B,T,n))")
     if eps is not None:
         eps = _lib.f64(eps, device)
+        if eps.shape != (B, T, S, n):
+            raise ValueError("eps must be (B,T,S,n) = %s, got %s" % ((B, T, S, n), tuple(eps.shape)))
     elif S > 0:
         eps = torch.randn((B, T, S, n), dtype=torch.float64, device=device, generator=generator)
     det = lambda v: None if v is None else v.detach()
